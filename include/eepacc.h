@@ -1,0 +1,208 @@
+/*
+ * eepacc.h -- C ABI of the B200-native batched EEPACC MPC engine.
+ *
+ * Every entry point keeps the calling convention of a CasADi-generated function,
+ *
+ *     int F(const double** arg, double** res, long long* iw, double* w, int mem);
+ *
+ * i.e. the convention that the reference evaluates through
+ * casadi_c_eval_id(id,arg,res,iw,w,mem)     (ACCMPC-ABO_CasADi/casadi_fun.c:170,
+ * casadi_3_6_3/include/casadi/casadi_c.h:128-129), with the function id folded into
+ * the symbol name and ONE extension: a leading batch dimension.
+ *
+ *   - arg[i] / res[i] point to `double[B][nnz_i]` (batch-leading; the slice of one
+ *     vehicle is exactly what one reference call would see, dense column-major).
+ *   - iw[0] = B (batch), iw[1] = flags (EEPACC_FLAG_*).  F_work() reports sz_iw >= 2.
+ *   - `mem` is the handle returned by F_checkout() (casadi_c.h:51-64 semantics: one
+ *     per host thread / CUDA stream).  It owns the device-resident per-vehicle state
+ *     (plant state, warm-start working set, FB A/D quirk rows) and the scenario data.
+ *   - return 0 = success, non-zero = failure (casadi_fun.c:64,170-172).  Per-vehicle
+ *     solver status is an OUTPUT (res[...]), never the return code
+ *     (error_on_fail=false, RunOpt_FBMPC.m:127,281).
+ *
+ * There is no CPU fallback: every F() launches sm_100a kernels and fails with
+ * EEPACC_ERR_NO_DEVICE when no CUDA device is usable.
+ */
+#ifndef EEPACC_H
+#define EEPACC_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EEPACC_N_HOR        20   /* Settings.m:99-100 (sum(moveBlockingSettings)); only horizon with golden data */
+#define EEPACC_MAX_SL       16   /* speed-limit PWA points  (GenerateUseCase.m:57-70)  */
+#define EEPACC_MAX_CURV     48   /* curvature PWA points    (GenerateUseCase.m:75-92)  */
+#define EEPACC_MAX_SLOPE    24   /* road-slope PWA points   (GenerateUseCase.m:97-107) */
+#define EEPACC_MAX_STOP     8    /* stop locations          (Settings.m:178)           */
+#define EEPACC_MAX_TL       4    /* traffic lights          (Settings.m:188)           */
+
+/* controller kinds (RunOpt_ABMPC.m / RunOpt_FBMPC.m / RunOpt_BLMPC.m / RunOpt_TVMPC.m) */
+enum { EEPACC_AB = 0, EEPACC_FB = 1, EEPACC_BL = 2, EEPACC_TV = 3 };
+
+/* iw[1] flags */
+#define EEPACC_FLAG_DEVICE_PTR  1   /* arg/res are device pointers: no hidden copies  */
+
+/* return codes */
+#define EEPACC_OK               0
+#define EEPACC_ERR_ARG          1
+#define EEPACC_ERR_NO_DEVICE    2
+#define EEPACC_ERR_CUDA         3
+#define EEPACC_ERR_MEM          4
+
+/* per-vehicle QP status written to the status output (qpOASES returnValue classes) */
+#define EEPACC_QP_OK            0
+#define EEPACC_QP_MAXITER       1   /* RET_MAX_NWSR_REACHED                */
+#define EEPACC_QP_INFEASIBLE    2   /* RET_*_STOPPED_INFEASIBILITY         */
+#define EEPACC_QP_UNBOUNDED     3   /* RET_*_STOPPED_UNBOUNDEDNESS         */
+#define EEPACC_QP_NUMERIC       4   /* NaN / factorisation breakdown       */
+
+/* All tunables of Settings.m + SetVehicleParameters.m that reach the hot path. */
+typedef struct eepacc_params {
+    /* --- vehicle (Functions/Settings/SetVehicleParameters.m, both trees) --- */
+    double m, L, h_g, L_f, c_r, R_w, phi;
+    double P_m_max, T_m_max, omega_m_r, eta_TF, lambda, mu, g, zeta_a, v_max;
+    double F2, p10, p01;            /* Daily coast-down / efficiency-map fit (ABO tree only; 0 for the i3) */
+    /* --- objective weights (Settings.m:13-76) --- */
+    double W_FB[7];                 /* w_P w_a w_j w_v w_h w_s w_f                          */
+    double W_AB[7];                 /* w_FC w_a w_j w_v w_h w_s w_f (w_FC=0 in the MC tree) */
+    double W_BL[4];                 /* w_v w_a w_j w_f                                      */
+    double W_TV[4];
+    /* --- horizon / estimation (Settings.m:96-120) --- */
+    double Ts;
+    double tConstACC_ego, tConstACC_tar;
+    int    N;                       /* must equal EEPACC_N_HOR                              */
+    int    n_integrate_plant;       /* RK4 sub-steps of the plant (Settings.m:109)          */
+    int    est_ego, est_tar;        /* paramEstSetting, TVestSetting                        */
+    int    est_bl, est_tv;          /* BL_trajEstSett, TV_trajEstSett                       */
+    int    ab_route_rows;           /* 1: MC CreateQP_AB.m:307-329 rows present; 0: ABO     */
+    int    fb_ad_quirk;             /* 1: reproduce RunOpt_FBMPC.m:251-254 (A(k)/D(k) bug)  */
+    /* --- use case (Settings.m:141,201-224; CreateQP_FB.m:461-463) --- */
+    double s_goal, h_min, tau_min;
+    double stopVel, stopRefDist, stopRefVelSlope, TLStopRegionSize, TLstopVel, alpha_TTL;
+    double T_hwp, A_hwp, G_hwp;
+    double BL_a_low, BL_a_high, BL_j_low, BL_j_high;
+    double TV_a_low, TV_a_high, TV_j_low, TV_j_high;
+    /* --- power-map fits (Settings.m:227-236) --- */
+    double b_quadr[6];
+    double b_fifth[21];
+    /* --- initial conditions (Settings.m:83-85, 206-207) --- */
+    double s_init, v_init, a_minus1_init;
+} eepacc_params;
+
+/* One scenario's route preview (GenerateUseCase.m output), contiguous so that a CTA
+ * pulls it with one bulk copy.  Unused tail entries are ignored (counts below). */
+typedef struct eepacc_route {
+    double s_speedLim[EEPACC_MAX_SL],   v_speedLim[EEPACC_MAX_SL];
+    double s_curv[EEPACC_MAX_CURV],     curvature[EEPACC_MAX_CURV];
+    double s_slope[EEPACC_MAX_SLOPE],   slope[EEPACC_MAX_SLOPE];
+    double stopLoc[EEPACC_MAX_STOP];
+    double TLLoc[EEPACC_MAX_TL][4];     /* [pos, phase, red, green] (Settings.m:187)        */
+    double mass_scale;                  /* per-scenario vehicle-mass factor (1 = nominal)   */
+    int    n_sl, n_curv, n_slope, n_stop, n_tl, pad_;
+} eepacc_route;
+
+/* problem sizes of the dense QP of each controller */
+int eepacc_qp_nvar(int ctrl);                              /* 100 / 120 / 40 / 40             */
+int eepacc_qp_ncon(int ctrl, const eepacc_params* p);      /* 362|282 / 522 / 262 / 220       */
+
+/* ------------------------------------------------------------------------------------
+ * mem objects (casadi_c.h:51-64: checkout/release are NOT thread safe, incref/decref are)
+ * ------------------------------------------------------------------------------------ */
+/* Bind scenario data to a checked-out mem: copies params + B route blocks to the device,
+ * allocates per-vehicle state and resets it to the initial conditions.  `routes` is a host
+ * pointer to B blocks.  device < 0 keeps the current CUDA device. */
+int eepacc_mem_setup(int mem, int ctrl, const eepacc_params* p, const eepacc_route* routes,
+                     long long B, int device);
+/* Reset plant / warm-start state to step 0 without re-uploading the scenario. */
+int eepacc_mem_reset(int mem);
+/* Upload a whole lead trace: host double[n_steps][B][2] = (s_tv, v_tv) per step.  Enables
+ * eepacc_run_*(): the whole closed loop without per-step host involvement. */
+int eepacc_mem_set_lead(int mem, const double* lead, long long n_steps);
+/* CUDA stream (cudaStream_t as void*) the mem launches on; default stream if never set. */
+int eepacc_mem_set_stream(int mem, void* stream);
+/* Number of kernel launches issued through this mem so far (bench.py's gpu_launches). */
+long long eepacc_mem_launch_count(int mem);
+/* Per-vehicle counters accumulated so far: double[B][4] = working-set changes, failed QPs,
+ * refactorisations with dropped rows, flips.  Host pointer. */
+int eepacc_mem_get_counters(int mem, double* out);
+const char* eepacc_last_error(void);
+/* FP64-FMA peak microbenchmark (register-resident DFMA chains); returns GFLOP/s or <0. */
+double eepacc_measure_dfma_peak(int device);
+
+/* ------------------------------------------------------------------------------------
+ * CasADi-style function families.  For each F below the library exports
+ *   int F(const double** arg, double** res, long long* iw, double* w, int mem);
+ *   long long F_n_in(void), F_n_out(void);
+ *   const char* F_name_in(long long i), F_name_out(long long i);
+ *   const long long* F_sparsity_in(long long i), F_sparsity_out(long long i);   (CCS, dense)
+ *   int F_work(long long* sz_arg, long long* sz_res, long long* sz_iw, long long* sz_w);
+ *   void F_incref(void), F_decref(void);  int F_checkout(void);  void F_release(int mem);
+ *   double F_default_in(long long i);
+ * mirroring casadi_c_{n_in,n_out,name_in,name_out,sparsity_in,sparsity_out,work,incref,
+ * decref,checkout,release,default_in}_id (casadi_c.h:98-129).
+ * ------------------------------------------------------------------------------------ */
+#define EEPACC_DECLARE(F)                                                                   \
+    int F(const double** arg, double** res, long long* iw, double* w, int mem);             \
+    long long F##_n_in(void);                                                               \
+    long long F##_n_out(void);                                                              \
+    const char* F##_name_in(long long i);                                                   \
+    const char* F##_name_out(long long i);                                                  \
+    const long long* F##_sparsity_in(long long i);                                          \
+    const long long* F##_sparsity_out(long long i);                                         \
+    int F##_work(long long* sz_arg, long long* sz_res, long long* sz_iw, long long* sz_w);  \
+    void F##_incref(void);                                                                  \
+    void F##_decref(void);                                                                  \
+    int F##_checkout(void);                                                                 \
+    void F##_release(int mem);                                                              \
+    double F##_default_in(long long i);
+
+/* K1 -- expression evaluator (RunOpt_NLP.m:225-245,263-288; GetMotorPower_*.m)
+ *   eepacc_f      : (x[4]=[s v theta j], u[6]=[Fm Fb xi_v xi_h xi_s xi_f]) -> (xdot[4], L[1])
+ *   eepacc_F      : (x0[4], p[6]) -> (xf[4], qf[1])      4 RK4 steps over Ts
+ *   eepacc_F_jac  : (x0[4], p[6]) -> (xf[4], qf[1], J[5x10] col-major = d[xf;qf]/d[x0;p])
+ *   eepacc_power5 : (Fm[1], rpm[1]) -> (P[1])            quintic surface
+ *   eepacc_power2 : (Fm[1], rpm[1]) -> (P[1])            quadratic fit                    */
+EEPACC_DECLARE(eepacc_f)
+EEPACC_DECLARE(eepacc_F)
+EEPACC_DECLARE(eepacc_F_jac)
+EEPACC_DECLARE(eepacc_power5)
+EEPACC_DECLARE(eepacc_power2)
+
+/* K4 -- plant step (RunPlantModel.m:27-44):  (x[2]=[s v], u[2]=[Fm Fb]) -> (x_next[2])     */
+EEPACC_DECLARE(eepacc_plant)
+
+/* K2 -- bounds + QP build + condensing (CreateQP_*.m + TransformToDenseFormulation.m)
+ *   in : x0[2]=[s v], a_minus1[1], lead[3]=[s_tv v_tv a_tv], t0[1]
+ *   out: h[n x n], g[n], a[m x n], lba[m], uba[m]   (conic scheme names, conic.hpp:170-208) */
+EEPACC_DECLARE(eepacc_qpbuild_ab)
+EEPACC_DECLARE(eepacc_qpbuild_fb)
+EEPACC_DECLARE(eepacc_qpbuild_bl)
+EEPACC_DECLARE(eepacc_qpbuild_tv)
+
+/* K3 -- dense warm-started active-set QP, the CasADi conic('qpoases') boundary
+ *   (RunOpt_ABMPC.m:252, RunOpt_FBMPC.m:278).  in : h g a lba uba lbx ubx x0 lam_x0 lam_a0
+ *   out: x cost lam_a lam_x status iter.  Dimensions follow the mem's controller.        */
+EEPACC_DECLARE(eepacc_qpsolve)
+
+/* Fused closed-loop step K5->K4->K2->K3 (+AB force allocation); one call == one iteration
+ * of the `for kk = 0:N_sim` loop (RunOpt_FBMPC.m:161-331).
+ *   in : lead[2]=[s_tv(k) v_tv(k)]
+ *   out: z1[8]=[s v Fm Fb xi_v xi_h xi_s xi_f], a[1], status[1], iter[1]                  */
+EEPACC_DECLARE(eepacc_step_ab)
+EEPACC_DECLARE(eepacc_step_fb)
+EEPACC_DECLARE(eepacc_step_bl)
+EEPACC_DECLARE(eepacc_step_tv)
+
+/* Whole closed loop on the device (needs eepacc_mem_set_lead):  in: n_steps[1] (scalar, NOT
+ * batched); out: log[n_steps][B][10] = z1[8], a, status;  kpi[B][8] (see eepacc_kpi below). */
+EEPACC_DECLARE(eepacc_run)
+
+/* KPI block per scenario (Main.m:191-263): energy J (Ts*sum quintic), distance m, travel
+ * time to cut-off s, max|a|, rms a, rms jerk, count(xi_s>0 | xi_f>0), failed QPs.          */
+#define EEPACC_N_KPI 8
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EEPACC_H */
