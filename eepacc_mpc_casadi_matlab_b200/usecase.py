@@ -1,0 +1,192 @@
+"""Scenario side of the hot path: route previews, lead traces, batch perturbations.
+
+Restates (host, set-up time only):
+* GenerateUseCase.m:50-116 + SimplifyPWA.m:14-49 (incl. the ``doms(j)`` quirk at :43-44)
+* Run_DrivingCycle.m:16-46 + Main.m:88 (lead trace from a 10 Hz cycle)
+* the synthetic perturbed-scenario recipe of SURVEY.md section 8(d) (configs 2-4).
+"""
+import math
+
+import numpy as np
+
+from .settings import (MAX_CURV, MAX_SL, MAX_SLOPE, MAX_STOP, MAX_TL, Route)
+
+
+def simplify_pwa(doms, vals):
+    """SimplifyPWA.m:14-49, bug-compatible."""
+    doms = list(map(float, doms))
+    vals = list(map(float, vals))
+    d_, v_ = [doms[0]], [vals[0]]
+    for i in range(1, len(doms) - 1):
+        with np.errstate(divide="ignore", invalid="ignore"):
+            prev = np.float64(vals[i] - vals[i - 1]) / np.float64(doms[i] - doms[i - 1])
+            curr = np.float64(vals[i + 1] - vals[i]) / np.float64(doms[i + 1] - doms[i])
+        if prev != curr:                       # NaN ~= NaN is true in MATLAB as well
+            d_.append(doms[i])
+            v_.append(vals[i])
+    doms = d_ + [doms[-1]]
+    vals = v_ + [vals[-1]]
+    dn, vn = [], []
+    j = 0                                      # 0-based write cursor == MATLAB j-1
+    for i in range(len(doms) - 1):
+        if doms[i] == doms[i + 1]:
+            if vals[i] == vals[i + 1]:
+                pass
+            else:
+                dn.append(doms[i] - .1)
+                vn.append(vals[i])
+                j += 1
+        else:
+            dn.append(doms[j])                 # sic: doms(j), not doms(i)
+            vn.append(vals[j])
+            j += 1
+    return dn + [doms[-1]], vn + [vals[-1]]
+
+
+def generate_use_case(speed_lim_zones=None, curves=None, slopes=None, stops=(), tls=(),
+                      mass_scale=1.0):
+    """GenerateUseCase.m -> Route.  speed_lim_zones [[km/h, start m]], curves [[1/m, s0, s1]],
+    slopes [[%, s0, s1]], stops [m], tls [[pos, phase, red, green]]."""
+    if speed_lim_zones is None or len(speed_lim_zones) == 0:
+        speed_lim_zones = [[1e5, 0], [1e5, 1]]
+    if curves is None or len(curves) == 0:
+        curves = [[1 / 1e5, 1, 2]]
+    if slopes is None or len(slopes) == 0:
+        slopes = [[0, 1, 2]]
+    z = sorted([[float(a), float(b)] for a, b in speed_lim_zones], key=lambda r: r[1])
+    nz = len(z)
+    z = [[a / 3.6, b] for a, b in z]
+    z.append([z[-1][0], 1e5])
+    v_sl = [0.0] * (2 * nz + 1)
+    s_sl = [0.0] * (2 * nz + 1)
+    s_sl[0], v_sl[0] = -1.0, z[0][0]
+    for i in range(1, 2 * nz, 2):              # MATLAB i = 1:2:2*nz
+        k = (i + 1) // 2                       # 1-based zone
+        s_sl[i], v_sl[i] = z[k - 1][1], z[k - 1][0]
+        s_sl[i + 1], v_sl[i + 1] = z[k][1] - 1, z[k - 1][0]
+    s_sl, v_sl = simplify_pwa(s_sl, v_sl)
+    # curvature sampled at 1 m (sRes = 1)
+    n = int(max(c[2] for c in curves))
+    curv = [0.0] * n
+    for c in curves:
+        for i in range(int(c[1]), int(c[2]) + 1):
+            curv[i - 1] = abs(c[0])
+    curv = [1e-6 if abs(c) <= 1e-6 else c for c in curv]
+    s_c, curv = simplify_pwa(range(1, n + 1), curv)
+    s_c = s_c + [s_c[-1] + 1, s_c[-1] + 2]
+    curv = curv + [1e-6, 1e-6]
+    n = int(max(s[2] for s in slopes))
+    sl = [0.0] * n
+    for s in slopes:
+        for i in range(int(s[1]), int(s[2]) + 1):
+            sl[i - 1] = s[0]
+    sl = [math.atan(v / 100) for v in sl]
+    s_s, sl = simplify_pwa(range(1, n + 1), sl)
+    return make_route(s_sl, v_sl, s_c, curv, s_s, sl, stops, tls, mass_scale)
+
+
+def make_route(s_sl, v_sl, s_c, curv, s_s, sl, stops=(), tls=(), mass_scale=1.0):
+    r = Route()
+    for name, arr, cap in (("s_speedLim", s_sl, MAX_SL), ("v_speedLim", v_sl, MAX_SL),
+                           ("s_curv", s_c, MAX_CURV), ("curvature", curv, MAX_CURV),
+                           ("s_slope", s_s, MAX_SLOPE), ("slope", sl, MAX_SLOPE),
+                           ("stopLoc", list(stops), MAX_STOP)):
+        if len(arr) > cap:
+            raise ValueError(f"{name}: {len(arr)} points exceed the route block capacity {cap}")
+        getattr(r, name)[:len(arr)] = [float(a) for a in arr]
+    if len(tls) > MAX_TL:
+        raise ValueError("too many traffic lights")
+    for j, tl in enumerate(tls):
+        r.TLLoc[j][:] = [float(a) for a in tl]
+    r.n_sl, r.n_curv, r.n_slope = len(s_sl), len(s_c), len(s_s)
+    r.n_stop, r.n_tl = len(stops), len(tls)
+    r.mass_scale = float(mass_scale)
+    return r
+
+
+def default_route(mass_scale=1.0):
+    """Use case 0 (Settings.m:148-190): 60 km/h until 1000 m, then 50 km/h."""
+    return generate_use_case([[60, 0], [50, 1000]], mass_scale=mass_scale)
+
+
+def lead_from_half_hz(y, t_sim=435.0, ts=0.5, init_dist=10.0, tv_length=4.0):
+    """Run_DrivingCycle.m:35-46 + Main.m:88 given the 2 Hz (already resampled, thresholded)
+    speed samples ``y``.  Returns (s_tv, v_tv), each n+1 long."""
+    n = int(round(t_sim / ts))
+    v = np.zeros(n + 1)
+    s = np.zeros(n + 1)
+    s[0] = init_dist
+    for i in range(1, n):
+        v[i] = y[i]
+        s[i] = s[i - 1] + ts * y[i]
+    v[n] = v[n - 1]
+    s[n] = s[n - 1]
+    return s - tv_length, v
+
+
+def _uniform(rng, lo, hi, size=None):
+    return lo + (hi - lo) * rng.random(size)
+
+
+def perturbed_scenarios(B, base_v_2hz, seed=0xEE9ACC, highway_v_2hz=None, mass=False,
+                        full_route=False, n_steps=871, ts=0.5):
+    """Synthetic scenario batch.  Scenario 0 is the unperturbed
+    golden case.  Returns (routes: Route*B ctypes array, lead: float64[n_steps, B, 2]).
+
+    base_v_2hz / highway_v_2hz: 2 Hz lead speed samples (after resample + threshold)."""
+    routes = (Route * B)()
+    lead = np.zeros((n_steps, B, 2))
+    t = np.arange(n_steps) * ts
+    for b in range(B):
+        rng = np.random.Generator(np.random.Philox(key=seed, counter=[b, 0, 0, 0]))
+        hw = highway_v_2hz is not None and (b % 2 == 1)
+        y = np.array(highway_v_2hz if hw else base_v_2hz, dtype=np.float64)[:n_steps].copy()
+        if len(y) < n_steps:
+            y = np.concatenate([y, np.full(n_steps - len(y), y[-1])])
+        zones = [[80, 0], [120, 2000], [100, 9000]] if hw else [[60, 0], [50, 1000]]
+        gap = 10.0
+        ms = 1.0
+        if b > 0:
+            y *= _uniform(rng, 0.85, 1.15)
+            delay = int(rng.integers(0, 21))
+            if delay:
+                y = np.concatenate([np.zeros(delay), y[:-delay]])
+            gap = _uniform(rng, 6.0, 30.0)
+            for _ in range(3):
+                A, f, ph = _uniform(rng, 0, 0.3), _uniform(rng, 0.01, 0.1), _uniform(rng, 0, 2 * math.pi)
+                y = y + A * np.sin(2 * math.pi * f * t + ph) * (y > 0)
+            y = np.maximum(y, 0.0)
+            y[y < 0.1] = 0.0
+            zones = [[v + float(rng.choice([-10, 0, 10])), s] for v, s in zones]
+            for k in range(1, len(zones)):
+                zones[k][1] = max(zones[k - 1][1] + 50.0, round(zones[k][1] + _uniform(rng, -200, 200)))
+            if mass:
+                ms = _uniform(rng, 0.9, 1.1)
+        curves, slopes, stops, tls = None, None, (), ()
+        if full_route and b > 0:
+            nc = int(rng.integers(0, 11))
+            curves, pos = [], 150.0
+            for _ in range(nc):
+                pos += _uniform(rng, 100, 600)
+                ln = _uniform(rng, 5, 350)
+                kappa = float(rng.choice([-1, 1])) / _uniform(rng, 9, 75)
+                curves.append([kappa, int(pos), int(pos + ln)])
+                pos += ln
+            stops = sorted(_uniform(rng, 200, 4000, int(rng.integers(0, 6))).tolist())
+            tls = [[_uniform(rng, 200, 4000), _uniform(rng, 0, 20), _uniform(rng, 10, 17),
+                    _uniform(rng, 10, 15)] for _ in range(int(rng.integers(0, 4)))]
+            ns = int(rng.integers(0, 4))
+            slopes, pos = [], 100.0
+            for _ in range(ns):
+                pos += _uniform(rng, 100, 800)
+                ln = _uniform(rng, 50, 400)
+                slopes.append([_uniform(rng, 0, 8), int(pos), int(pos + ln)])
+                pos += ln
+        try:
+            routes[b] = generate_use_case(zones, curves, slopes, stops, tls, ms)
+        except ValueError:
+            routes[b] = generate_use_case(zones, None, None, stops, tls, ms)
+        s_tv, v_tv = lead_from_half_hz(y, t_sim=(n_steps - 1) * ts, ts=ts, init_dist=gap)
+        lead[:, b, 0] = s_tv
+        lead[:, b, 1] = v_tv
+    return routes, lead

@@ -68,6 +68,7 @@ typedef struct eepacc_params {
     double W_AB[7];                 /* w_FC w_a w_j w_v w_h w_s w_f (w_FC=0 in the MC tree) */
     double W_BL[4];                 /* w_v w_a w_j w_f                                      */
     double W_TV[4];
+    double W_NLP[7];                /* w_P w_a w_j w_v w_h w_s w_f (Settings.m:13-28; stage cost L of eepacc_f) */
     /* --- horizon / estimation (Settings.m:96-120) --- */
     double Ts;
     double tConstACC_ego, tConstACC_tar;
@@ -77,6 +78,8 @@ typedef struct eepacc_params {
     int    est_bl, est_tv;          /* BL_trajEstSett, TV_trajEstSett                       */
     int    ab_route_rows;           /* 1: MC CreateQP_AB.m:307-329 rows present; 0: ABO     */
     int    fb_ad_quirk;             /* 1: reproduce RunOpt_FBMPC.m:251-254 (A(k)/D(k) bug)  */
+    int    nlp_use_fifth;           /* useFifthOrderFit_NLP (Settings.m:92)                 */
+    int    pad0_;
     /* --- use case (Settings.m:141,201-224; CreateQP_FB.m:461-463) --- */
     double s_goal, h_min, tau_min;
     double stopVel, stopRefDist, stopRefVelSlope, TLStopRegionSize, TLstopVel, alpha_TTL;
@@ -88,6 +91,7 @@ typedef struct eepacc_params {
     double b_fifth[21];
     /* --- initial conditions (Settings.m:83-85, 206-207) --- */
     double s_init, v_init, a_minus1_init;
+    double cutOffDist;              /* KPI cut-off distance (Settings.m:190, Main.m:136-148) */
 } eepacc_params;
 
 /* One scenario's route preview (GenerateUseCase.m output), contiguous so that a CTA
