@@ -1,0 +1,719 @@
+// eepacc_capi.cu -- the C-ABI of include/eepacc.h: CasADi-codegen style entry points
+//   int F(const double** arg, double** res, long long* iw, double* w, int mem)
+// (casadi_c_eval_id, casadi_c.h:128-129; called from ACCMPC-ABO_CasADi/casadi_fun.c:170) with a
+// leading batch dimension, plus the mem objects that own device-resident per-vehicle state.
+// No CPU fallback: every F() launches sm_100a kernels or fails.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "eepacc_kernels.h"
+
+#define NH EEPACC_N_HOR
+#define ACC_W 20
+#define MAX_MEM 64
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const char* what, cudaError_t e = cudaSuccess)
+{
+    char buf[512];
+    if (e != cudaSuccess) snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+    else snprintf(buf, sizeof buf, "%s", what);
+    g_err = buf;
+    return code;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(EEPACC_ERR_CUDA, #call, e_); } while (0)
+
+struct DBuf {
+    void* p = nullptr; size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) return fail(EEPACC_ERR_MEM, "cudaMalloc", e);
+        cap = bytes;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct Mem {
+    bool used = false, ready = false;
+    int ctrl = 0, n = 0, m = 0, device = 0;
+    long long B = 0;
+    cudaStream_t stream = nullptr;
+    eepacc_params p;
+    long long launches = 0;
+    int kk = 0;
+    double t0 = 0.0;
+    long long n_lead = 0;
+    DBuf routes, s_prev, v_prev, Fm_prev, Fb_prev, a_minus1, v_tv_meas, fbA, fbD, prev_sol, x0, dyn;
+    DBuf H, g, A, lba, uba;
+    DBuf wx, wy, widx, wside, wnA, warm, xsol, cost, status, iter, counters;
+    DBuf kpi_acc, kpi, lead, lead_step, logrow, dbg;
+    DBuf in[12], out[8];        // staging for host-pointer calls
+    bool timing = false;        // CUDA-event timing of every kernel launch (bench.py roofline leg)
+    std::vector<cudaEvent_t> evs;
+    int ev_steps = 0;
+    void release_all()
+    {
+        DBuf* all[] = { &routes, &s_prev, &v_prev, &Fm_prev, &Fb_prev, &a_minus1, &v_tv_meas, &fbA, &fbD, &prev_sol,
+                        &x0, &dyn, &H, &g, &A, &lba, &uba, &wx, &wy, &widx, &wside, &wnA, &warm, &xsol, &cost,
+                        &status, &iter, &counters, &kpi_acc, &kpi, &lead, &lead_step, &logrow, &dbg };
+        for (DBuf* b : all) b->release();
+        for (auto& b : in) b.release();
+        for (auto& b : out) b.release();
+        for (auto e : evs) cudaEventDestroy(e);
+        evs.clear(); ev_steps = 0;
+        ready = false;
+    }
+};
+
+Mem g_mem[MAX_MEM];
+std::mutex g_mu;
+int g_refcount = 0;
+int g_last_ctrl = EEPACC_FB;
+int g_last_m = 522;
+
+Mem* get_mem(int mem)
+{
+    if (mem < 0 || mem >= MAX_MEM || !g_mem[mem].used) { fail(EEPACC_ERR_ARG, "invalid mem handle"); return nullptr; }
+    return &g_mem[mem];
+}
+
+int nvar(int ctrl) { return ctrl == EEPACC_FB ? 120 : ctrl == EEPACC_AB ? 100 : 40; }
+int ncon(int ctrl, const eepacc_params* p)
+{
+    switch (ctrl) {
+    case EEPACC_FB: return 522;
+    case EEPACC_AB: return (p && !p->ab_route_rows) ? 282 : 362;
+    case EEPACC_BL: return 262;
+    default: return 220;
+    }
+}
+
+int reset_state(Mem* M)
+{
+    const long long B = M->B;
+    CK(cudaMemsetAsync(M->s_prev.p, 0, B * 8, M->stream));
+    CK(cudaMemsetAsync(M->v_prev.p, 0, B * 8, M->stream));
+    CK(cudaMemsetAsync(M->Fm_prev.p, 0, B * 8, M->stream));
+    CK(cudaMemsetAsync(M->Fb_prev.p, 0, B * 8, M->stream));
+    CK(cudaMemsetAsync(M->v_tv_meas.p, 0, B * 8, M->stream));
+    CK(cudaMemsetAsync(M->prev_sol.p, 0, B * 2 * (NH + 1) * 8, M->stream));
+    CK(cudaMemsetAsync(M->warm.p, 0, B * sizeof(int), M->stream));
+    CK(cudaMemsetAsync(M->wnA.p, 0, B * sizeof(int), M->stream));
+    CK(cudaMemsetAsync(M->counters.p, 0, B * 4 * sizeof(unsigned long long), M->stream));
+    CK(cudaMemsetAsync(M->kpi_acc.p, 0, B * ACC_W * 8, M->stream));
+    CK(cudaMemsetAsync(M->A.p, 0, (size_t)B * M->m * M->n * 8, M->stream));   // K2 writes structural non-zeros only
+    // a_minus1 and the FB A/D rows start from their Settings.m / RunOpt_FBMPC.m:78-90 values
+    std::vector<double> am1((size_t)B, M->p.a_minus1_init);
+    CK(cudaMemcpyAsync(M->a_minus1.p, am1.data(), B * 8, cudaMemcpyHostToDevice, M->stream));
+    CK(cudaStreamSynchronize(M->stream));
+    M->kk = 0; M->t0 = 0.0;
+    return EEPACC_OK;
+}
+
+// copy-in helper: returns device pointer for input `src` (host or device)
+int stage_in(Mem* M, int slot, const double* src, size_t count, bool dev, const double** out)
+{
+    if (!src) { *out = nullptr; return 0; }
+    if (dev) { *out = src; return 0; }
+    if (M->in[slot].ensure(count * 8)) return EEPACC_ERR_MEM;
+    CK(cudaMemcpyAsync(M->in[slot].p, src, count * 8, cudaMemcpyHostToDevice, M->stream));
+    *out = M->in[slot].as<double>();
+    return 0;
+}
+int stage_out(Mem* M, int slot, double* dst, size_t count, bool dev, double** out)
+{
+    if (!dst) { *out = nullptr; return 0; }
+    if (dev) { *out = dst; return 0; }
+    if (M->out[slot].ensure(count * 8)) return EEPACC_ERR_MEM;
+    *out = M->out[slot].as<double>();
+    return 0;
+}
+int copy_out(Mem* M, int slot, double* dst, size_t count, bool dev)
+{
+    if (!dst || dev) return 0;
+    CK(cudaMemcpyAsync(dst, M->out[slot].p, count * 8, cudaMemcpyDeviceToHost, M->stream));
+    return 0;
+}
+
+struct CallCtx { Mem* M; long long B; bool dev; };
+int begin_call(int mem, long long* iw, CallCtx& c)
+{
+    Mem* M = get_mem(mem);
+    if (!M) return EEPACC_ERR_ARG;
+    if (!M->ready) return fail(EEPACC_ERR_ARG, "mem not set up (call eepacc_mem_setup)");
+    if (!iw) return fail(EEPACC_ERR_ARG, "iw is NULL (iw[0] = batch, iw[1] = flags)");
+    CK(cudaSetDevice(M->device));
+    c.M = M; c.B = iw[0]; c.dev = (iw[1] & EEPACC_FLAG_DEVICE_PTR) != 0;
+    if (c.B < 0) return fail(EEPACC_ERR_ARG, "negative batch");
+    return 0;
+}
+int end_call(CallCtx& c)
+{
+    CK(cudaGetLastError());
+    if (!c.dev) CK(cudaStreamSynchronize(c.M->stream));
+    return EEPACC_OK;
+}
+
+eep_build_io make_build_io(Mem* M, int mode)
+{
+    eep_build_io io;
+    memset(&io, 0, sizeof io);
+    io.B = M->B; io.ctrl = M->ctrl; io.m = M->m; io.mode = mode; io.kk = M->kk; io.t0 = M->t0;
+    io.routes = M->routes.as<eepacc_route>(); io.route_stride = 1;
+    io.s_prev = M->s_prev.as<double>(); io.v_prev = M->v_prev.as<double>();
+    io.Fm_prev = M->Fm_prev.as<double>(); io.Fb_prev = M->Fb_prev.as<double>();
+    io.a_minus1 = M->a_minus1.as<double>(); io.v_tv_meas = M->v_tv_meas.as<double>();
+    io.fbA = M->fbA.as<double>(); io.fbD = M->fbD.as<double>();
+    io.prev_sol = M->prev_sol.as<double>();
+    io.x0 = M->x0.as<double>();
+    io.H = M->H.as<double>(); io.g = M->g.as<double>(); io.A = M->A.as<double>();
+    io.lba = M->lba.as<double>(); io.uba = M->uba.as<double>();
+    io.dyn = M->dyn.as<double>();
+    return io;
+}
+eep_qp_io make_qp_io(Mem* M)
+{
+    eep_qp_io io;
+    memset(&io, 0, sizeof io);
+    io.B = M->B; io.n = M->n; io.m = M->m;
+    io.H = M->H.as<double>(); io.g = M->g.as<double>(); io.A = M->A.as<double>();
+    io.lba = M->lba.as<double>(); io.uba = M->uba.as<double>();
+    io.wx = M->wx.as<double>(); io.wy = M->wy.as<double>();
+    io.widx = M->widx.as<short>(); io.wside = M->wside.as<signed char>();
+    io.wnA = M->wnA.as<int>(); io.warm = M->warm.as<int>();
+    io.x = M->xsol.as<double>(); io.cost = M->cost.as<double>();
+    io.status = M->status.as<double>(); io.iter = M->iter.as<double>();
+    io.counters = M->counters.as<unsigned long long>();
+    io.dbg = M->dbg.as<double>(); io.dbg_cap = M->dbg.p ? 4096 : 0;
+    return io;
+}
+
+// one closed-loop step on the device: K5/K4/K2 -> K3 -> post.  lead_dev: [B][2] device pointer.
+int device_step(Mem* M, const double* lead_dev, double* log_dev)
+{
+    eep_build_io bio = make_build_io(M, 0);
+    bio.lead = lead_dev;
+    cudaEvent_t* ev = nullptr;
+    if (M->timing) {
+        const size_t need = (size_t)(M->kk + 1) * 4;
+        while (M->evs.size() < need) { cudaEvent_t e; CK(cudaEventCreate(&e)); M->evs.push_back(e); }
+        ev = &M->evs[(size_t)M->kk * 4];
+        M->ev_steps = M->kk + 1;
+        CK(cudaEventRecord(ev[0], M->stream));
+    }
+    int rc = eep_launch_build(&M->p, &bio, M->stream);
+    if (ev) CK(cudaEventRecord(ev[1], M->stream));
+    if (rc) return fail(EEPACC_ERR_CUDA, "k2_build launch", (cudaError_t)rc);
+    eep_qp_io qio = make_qp_io(M);
+    rc = eep_launch_qp(&qio, M->stream);
+    if (rc) return fail(EEPACC_ERR_CUDA, "k3_qp launch", (cudaError_t)rc);
+    if (ev) CK(cudaEventRecord(ev[2], M->stream));
+    eep_post_io pio;
+    memset(&pio, 0, sizeof pio);
+    pio.B = M->B; pio.ctrl = M->ctrl; pio.n = M->n; pio.kk = M->kk;
+    pio.routes = M->routes.as<eepacc_route>(); pio.route_stride = 1;
+    pio.x = M->xsol.as<double>(); pio.x0 = M->x0.as<double>(); pio.dyn = M->dyn.as<double>();
+    pio.status = M->status.as<double>(); pio.iter = M->iter.as<double>(); pio.cost = M->cost.as<double>();
+    pio.s_prev = M->s_prev.as<double>(); pio.v_prev = M->v_prev.as<double>();
+    pio.Fm_prev = M->Fm_prev.as<double>(); pio.Fb_prev = M->Fb_prev.as<double>();
+    pio.prev_sol = M->prev_sol.as<double>();
+    pio.log = log_dev;
+    pio.kpi_acc = M->kpi_acc.as<double>();
+    rc = eep_launch_post(&M->p, &pio, M->stream);
+    if (rc) return fail(EEPACC_ERR_CUDA, "k4_post launch", (cudaError_t)rc);
+    if (ev) CK(cudaEventRecord(ev[3], M->stream));
+    M->launches += 3;
+    M->kk += 1;
+    M->t0 += M->p.Ts;
+    return EEPACC_OK;
+}
+
+// ---------------- metadata ----------------
+struct Port { const char* name; int rows, cols; };   // rows < 0: resolved from the last set-up controller
+enum { DIM_N = -1, DIM_M = -2, DIM_NN = -3, DIM_MN = -4 };
+
+const long long* dense_ccs(int rows, int cols)
+{
+    static std::mutex mu;
+    static std::vector<std::vector<long long>> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto& v : cache) if (v[0] == rows && v[1] == cols) return v.data();
+    std::vector<long long> v;
+    v.push_back(rows); v.push_back(cols);
+    for (int c = 0; c <= cols; ++c) v.push_back((long long)c * rows);
+    for (int c = 0; c < cols; ++c) for (int r = 0; r < rows; ++r) v.push_back(r);
+    cache.push_back(std::move(v));
+    return cache.back().data();
+}
+void resolve(const Port& p, int ctrl, int m, int& rows, int& cols)
+{
+    const int n = nvar(ctrl);
+    rows = p.rows; cols = p.cols;
+    if (p.rows == DIM_N) { rows = n; cols = 1; }
+    else if (p.rows == DIM_M) { rows = m; cols = 1; }
+    else if (p.rows == DIM_NN) { rows = n; cols = n; }
+    else if (p.rows == DIM_MN) { rows = m; cols = n; }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* eepacc_last_error(void) { return g_err.c_str(); }
+int eepacc_qp_nvar(int ctrl) { return nvar(ctrl); }
+int eepacc_qp_ncon(int ctrl, const eepacc_params* p) { return ncon(ctrl, p); }
+long long eepacc_sizeof_params(void) { return (long long)sizeof(eepacc_params); }
+long long eepacc_sizeof_route(void) { return (long long)sizeof(eepacc_route); }
+
+static int checkout_impl(void)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (int i = 0; i < MAX_MEM; ++i)
+        if (!g_mem[i].used) { g_mem[i] = Mem(); g_mem[i].used = true; return i; }
+    fail(EEPACC_ERR_MEM, "no free mem slot");
+    return -1;
+}
+static void release_impl(int mem)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (mem < 0 || mem >= MAX_MEM || !g_mem[mem].used) return;
+    if (g_mem[mem].ready) cudaSetDevice(g_mem[mem].device);
+    g_mem[mem].release_all();
+    g_mem[mem].used = false;
+}
+
+int eepacc_mem_setup(int mem, int ctrl, const eepacc_params* p, const eepacc_route* routes, long long B, int device)
+{
+    Mem* M = get_mem(mem);
+    if (!M) return EEPACC_ERR_ARG;
+    if (!p || !routes || B <= 0) return fail(EEPACC_ERR_ARG, "eepacc_mem_setup: bad arguments");
+    if (ctrl < EEPACC_AB || ctrl > EEPACC_TV) return fail(EEPACC_ERR_ARG, "unknown controller");
+    if (p->N != NH) return fail(EEPACC_ERR_ARG, "params.N must equal EEPACC_N_HOR (20)");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return fail(EEPACC_ERR_NO_DEVICE, "no CUDA device (there is no CPU fallback)");
+    if (device < 0) { CK(cudaGetDevice(&device)); }
+    if (device >= ndev) return fail(EEPACC_ERR_NO_DEVICE, "device index out of range");
+    CK(cudaSetDevice(device));
+    M->release_all();
+    M->device = device; M->ctrl = ctrl; M->p = *p; M->B = B;
+    M->n = nvar(ctrl); M->m = ncon(ctrl, p);
+    g_last_ctrl = ctrl; g_last_m = M->m;
+    const size_t n = M->n, m = M->m;
+    struct { DBuf* b; size_t bytes; } plan[] = {
+        { &M->routes, (size_t)B * sizeof(eepacc_route) },
+        { &M->s_prev, (size_t)B * 8 }, { &M->v_prev, (size_t)B * 8 }, { &M->Fm_prev, (size_t)B * 8 },
+        { &M->Fb_prev, (size_t)B * 8 }, { &M->a_minus1, (size_t)B * 8 }, { &M->v_tv_meas, (size_t)B * 8 },
+        { &M->fbA, (size_t)B * NH * 8 }, { &M->fbD, (size_t)B * NH * 8 },
+        { &M->prev_sol, (size_t)B * 2 * (NH + 1) * 8 }, { &M->x0, (size_t)B * 2 * 8 }, { &M->dyn, (size_t)B * 2 * NH * 8 },
+        { &M->H, (size_t)B * n * n * 8 }, { &M->g, (size_t)B * n * 8 }, { &M->A, (size_t)B * m * n * 8 },
+        { &M->lba, (size_t)B * m * 8 }, { &M->uba, (size_t)B * m * 8 },
+        { &M->wx, (size_t)B * n * 8 }, { &M->wy, (size_t)B * n * 8 }, { &M->widx, (size_t)B * n * 2 },
+        { &M->wside, (size_t)B * n }, { &M->wnA, (size_t)B * 4 }, { &M->warm, (size_t)B * 4 },
+        { &M->xsol, (size_t)B * n * 8 }, { &M->cost, (size_t)B * 8 }, { &M->status, (size_t)B * 8 },
+        { &M->iter, (size_t)B * 8 }, { &M->counters, (size_t)B * 4 * 8 },
+        { &M->kpi_acc, (size_t)B * ACC_W * 8 }, { &M->kpi, (size_t)B * EEPACC_N_KPI * 8 },
+        { &M->lead_step, (size_t)B * 2 * 8 }, { &M->logrow, (size_t)B * EEPACC_LOG_W * 8 },
+    };
+    for (auto& e : plan) if (e.b->ensure(e.bytes)) return EEPACC_ERR_MEM;
+    CK(cudaMemcpyAsync(M->routes.p, routes, (size_t)B * sizeof(eepacc_route), cudaMemcpyHostToDevice, M->stream));
+    // FB dynamics rows before the first step (RunOpt_FBMPC.m:78-90)
+    {
+        std::vector<double> fa((size_t)B * NH), fd((size_t)B * NH);
+        for (long long b = 0; b < B; ++b) {
+            double mass = p->m * routes[b].mass_scale;
+            for (int k = 0; k < NH; ++k) {
+                fa[b * NH + k] = 1 - 2 * p->Ts * p->zeta_a * p->v_init * p->v_init / p->lambda / mass;
+                fd[b * NH + k] = p->Ts / p->lambda / mass * (p->zeta_a * p->v_init * p->v_init);
+            }
+        }
+        CK(cudaMemcpyAsync(M->fbA.p, fa.data(), fa.size() * 8, cudaMemcpyHostToDevice, M->stream));
+        CK(cudaMemcpyAsync(M->fbD.p, fd.data(), fd.size() * 8, cudaMemcpyHostToDevice, M->stream));
+        CK(cudaStreamSynchronize(M->stream));
+    }
+    M->ready = true;
+    return reset_state(M);
+}
+
+int eepacc_mem_reset(int mem)
+{
+    Mem* M = get_mem(mem);
+    if (!M || !M->ready) return fail(EEPACC_ERR_ARG, "mem not set up");
+    CK(cudaSetDevice(M->device));
+    return reset_state(M);
+}
+
+int eepacc_mem_set_step(int mem, int kk, double t0)
+{
+    Mem* M = get_mem(mem);
+    if (!M) return EEPACC_ERR_ARG;
+    M->kk = kk; M->t0 = t0;
+    return EEPACC_OK;
+}
+
+int eepacc_mem_set_lead(int mem, const double* lead, long long n_steps)
+{
+    Mem* M = get_mem(mem);
+    if (!M || !M->ready) return fail(EEPACC_ERR_ARG, "mem not set up");
+    if (!lead || n_steps <= 0) return fail(EEPACC_ERR_ARG, "bad lead trace");
+    CK(cudaSetDevice(M->device));
+    size_t bytes = (size_t)n_steps * M->B * 2 * 8;
+    if (M->lead.ensure(bytes)) return EEPACC_ERR_MEM;
+    CK(cudaMemcpyAsync(M->lead.p, lead, bytes, cudaMemcpyHostToDevice, M->stream));
+    CK(cudaStreamSynchronize(M->stream));
+    M->n_lead = n_steps;
+    return EEPACC_OK;
+}
+
+int eepacc_mem_set_stream(int mem, void* stream)
+{
+    Mem* M = get_mem(mem);
+    if (!M) return EEPACC_ERR_ARG;
+    M->stream = (cudaStream_t)stream;
+    return EEPACC_OK;
+}
+
+long long eepacc_mem_launch_count(int mem)
+{
+    Mem* M = get_mem(mem);
+    return M ? M->launches : -1;
+}
+
+int eepacc_mem_get_counters(int mem, double* out)
+{
+    Mem* M = get_mem(mem);
+    if (!M || !M->ready || !out) return fail(EEPACC_ERR_ARG, "bad arguments");
+    CK(cudaSetDevice(M->device));
+    std::vector<unsigned long long> h((size_t)M->B * 4);
+    CK(cudaMemcpyAsync(h.data(), M->counters.p, h.size() * 8, cudaMemcpyDeviceToHost, M->stream));
+    CK(cudaStreamSynchronize(M->stream));
+    for (size_t i = 0; i < h.size(); ++i) out[i] = (double)h[i];
+    return EEPACC_OK;
+}
+
+/* device pointer of the per-vehicle KPI block [B][EEPACC_N_KPI] after eepacc_run (for NCCL gathers) */
+void* eepacc_mem_kpi_device_ptr(int mem)
+{
+    Mem* M = get_mem(mem);
+    return (M && M->ready) ? M->kpi.p : nullptr;
+}
+
+double eepacc_measure_dfma_peak(int device) { return eep_dfma_peak(device); }
+
+/* CUDA-event timing of the closed-loop kernels on the mem's stream.  enable: on = 1.
+ * get: tot[4] = summed ms of k2_build, k3_qp, k4_post over the steps since the last reset and the
+ * number of steps; step_ms[cap] = per-step latency (build start -> post end). */
+int eepacc_mem_enable_timing(int mem, int on)
+{
+    Mem* M = get_mem(mem);
+    if (!M) return EEPACC_ERR_ARG;
+    M->timing = on != 0;
+    return EEPACC_OK;
+}
+int eepacc_mem_get_timing(int mem, double* tot, double* step_ms, long long cap)
+{
+    Mem* M = get_mem(mem);
+    if (!M || !M->ready || !tot) return fail(EEPACC_ERR_ARG, "bad arguments");
+    CK(cudaSetDevice(M->device));
+    CK(cudaStreamSynchronize(M->stream));
+    tot[0] = tot[1] = tot[2] = 0.0; tot[3] = (double)M->ev_steps;
+    for (int k = 0; k < M->ev_steps; ++k) {
+        cudaEvent_t* ev = &M->evs[(size_t)k * 4];
+        float a = 0, b = 0, c2 = 0;
+        CK(cudaEventElapsedTime(&a, ev[0], ev[1]));
+        CK(cudaEventElapsedTime(&b, ev[1], ev[2]));
+        CK(cudaEventElapsedTime(&c2, ev[2], ev[3]));
+        tot[0] += a; tot[1] += b; tot[2] += c2;
+        if (step_ms && k < cap) step_ms[k] = (double)a + b + c2;
+    }
+    return EEPACC_OK;
+}
+
+/* Developer aid: enable (cap > 0) / fetch the per-iteration trace of vehicle 0's last solve:
+ * out[cap][4] = tau, ratio-test key, |W|, exchanges.  Returns 0 on success. */
+int eepacc_mem_debug_trace(int mem, double* out, int cap)
+{
+    Mem* M = get_mem(mem);
+    if (!M || !M->ready) return fail(EEPACC_ERR_ARG, "mem not set up");
+    CK(cudaSetDevice(M->device));
+    if (!M->dbg.p) {
+        if (M->dbg.ensure(4096 * 4 * 8)) return EEPACC_ERR_MEM;
+        CK(cudaMemset(M->dbg.p, 0, 4096 * 4 * 8));
+        return EEPACC_OK;
+    }
+    if (out && cap > 0) {
+        if (cap > 4096) cap = 4096;
+        CK(cudaMemcpy(out, M->dbg.p, (size_t)cap * 4 * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemset(M->dbg.p, 0, 4096 * 4 * 8));
+    }
+    return EEPACC_OK;
+}
+
+// ---------------- CasADi-style families ----------------
+#define FAMILY_META(F, NIN, NOUT, INS, OUTS)                                                              \
+    long long F##_n_in(void) { return NIN; }                                                              \
+    long long F##_n_out(void) { return NOUT; }                                                            \
+    const char* F##_name_in(long long i) { static const Port p[] = INS; return (i >= 0 && i < NIN) ? p[i].name : 0; }   \
+    const char* F##_name_out(long long i) { static const Port p[] = OUTS; return (i >= 0 && i < NOUT) ? p[i].name : 0; } \
+    const long long* F##_sparsity_in(long long i) { static const Port p[] = INS; if (i < 0 || i >= NIN) return 0;        \
+        int r, c; resolve(p[i], F##_ctrl(), F##_m(), r, c); return dense_ccs(r, c); }                    \
+    const long long* F##_sparsity_out(long long i) { static const Port p[] = OUTS; if (i < 0 || i >= NOUT) return 0;     \
+        int r, c; resolve(p[i], F##_ctrl(), F##_m(), r, c); return dense_ccs(r, c); }                    \
+    int F##_work(long long* sz_arg, long long* sz_res, long long* sz_iw, long long* sz_w) {              \
+        if (sz_arg) *sz_arg = NIN; if (sz_res) *sz_res = NOUT; if (sz_iw) *sz_iw = 2; if (sz_w) *sz_w = 0; return 0; } \
+    void F##_incref(void) { std::lock_guard<std::mutex> lk(g_mu); ++g_refcount; }                         \
+    void F##_decref(void) { std::lock_guard<std::mutex> lk(g_mu); --g_refcount; }                         \
+    int F##_checkout(void) { return checkout_impl(); }                                                    \
+    void F##_release(int mem) { release_impl(mem); }                                                      \
+    double F##_default_in(long long) { return 0.0; }
+
+#define BR(...) { __VA_ARGS__ }
+#define FIXED_CTRL(F, CTRL, MEXPR) static int F##_ctrl() { return CTRL; } static int F##_m() { return MEXPR; }
+
+FIXED_CTRL(eepacc_f, g_last_ctrl, g_last_m)
+FAMILY_META(eepacc_f, 2, 2, BR({"x", 4, 1}, {"u", 6, 1}), BR({"xdot", 4, 1}, {"L", 1, 1}))
+FIXED_CTRL(eepacc_F, g_last_ctrl, g_last_m)
+FAMILY_META(eepacc_F, 2, 2, BR({"x0", 4, 1}, {"p", 6, 1}), BR({"xf", 4, 1}, {"qf", 1, 1}))
+FIXED_CTRL(eepacc_F_jac, g_last_ctrl, g_last_m)
+FAMILY_META(eepacc_F_jac, 2, 3, BR({"x0", 4, 1}, {"p", 6, 1}), BR({"xf", 4, 1}, {"qf", 1, 1}, {"jac", 5, 10}))
+FIXED_CTRL(eepacc_power5, g_last_ctrl, g_last_m)
+FAMILY_META(eepacc_power5, 2, 1, BR({"Fm", 1, 1}, {"rpm", 1, 1}), BR({"P", 1, 1}))
+FIXED_CTRL(eepacc_power2, g_last_ctrl, g_last_m)
+FAMILY_META(eepacc_power2, 2, 1, BR({"Fm", 1, 1}, {"rpm", 1, 1}), BR({"P", 1, 1}))
+FIXED_CTRL(eepacc_plant, g_last_ctrl, g_last_m)
+FAMILY_META(eepacc_plant, 2, 1, BR({"x", 2, 1}, {"u", 2, 1}), BR({"x_next", 2, 1}))
+
+#define QPB_INS BR({"x0", 2, 1}, {"a_minus1", 1, 1}, {"lead", 3, 1}, {"t0", 1, 1})
+#define QPB_OUTS BR({"h", DIM_NN, 0}, {"g", DIM_N, 0}, {"a", DIM_MN, 0}, {"lba", DIM_M, 0}, {"uba", DIM_M, 0})
+FIXED_CTRL(eepacc_qpbuild_ab, EEPACC_AB, (g_last_ctrl == EEPACC_AB ? g_last_m : 362))
+FAMILY_META(eepacc_qpbuild_ab, 4, 5, QPB_INS, QPB_OUTS)
+FIXED_CTRL(eepacc_qpbuild_fb, EEPACC_FB, 522)
+FAMILY_META(eepacc_qpbuild_fb, 4, 5, QPB_INS, QPB_OUTS)
+FIXED_CTRL(eepacc_qpbuild_bl, EEPACC_BL, 262)
+FAMILY_META(eepacc_qpbuild_bl, 4, 5, QPB_INS, QPB_OUTS)
+FIXED_CTRL(eepacc_qpbuild_tv, EEPACC_TV, 220)
+FAMILY_META(eepacc_qpbuild_tv, 4, 5, QPB_INS, QPB_OUTS)
+
+FIXED_CTRL(eepacc_qpsolve, g_last_ctrl, g_last_m)
+FAMILY_META(eepacc_qpsolve, 10, 6,
+            BR({"h", DIM_NN, 0}, {"g", DIM_N, 0}, {"a", DIM_MN, 0}, {"lba", DIM_M, 0}, {"uba", DIM_M, 0},
+               {"lbx", DIM_N, 0}, {"ubx", DIM_N, 0}, {"x0", DIM_N, 0}, {"lam_x0", DIM_N, 0}, {"lam_a0", DIM_M, 0}),
+            BR({"x", DIM_N, 0}, {"cost", 1, 1}, {"lam_a", DIM_M, 0}, {"lam_x", DIM_N, 0}, {"status", 1, 1}, {"iter", 1, 1}))
+
+#define STEP_INS BR({"lead", 2, 1})
+#define STEP_OUTS BR({"z1", 8, 1}, {"a", 1, 1}, {"status", 1, 1}, {"iter", 1, 1})
+FIXED_CTRL(eepacc_step_ab, EEPACC_AB, 362)
+FAMILY_META(eepacc_step_ab, 1, 4, STEP_INS, STEP_OUTS)
+FIXED_CTRL(eepacc_step_fb, EEPACC_FB, 522)
+FAMILY_META(eepacc_step_fb, 1, 4, STEP_INS, STEP_OUTS)
+FIXED_CTRL(eepacc_step_bl, EEPACC_BL, 262)
+FAMILY_META(eepacc_step_bl, 1, 4, STEP_INS, STEP_OUTS)
+FIXED_CTRL(eepacc_step_tv, EEPACC_TV, 220)
+FAMILY_META(eepacc_step_tv, 1, 4, STEP_INS, STEP_OUTS)
+
+FIXED_CTRL(eepacc_run, g_last_ctrl, g_last_m)
+FAMILY_META(eepacc_run, 1, 2, BR({"n_steps", 1, 1}), BR({"log", EEPACC_LOG_W, 1}, {"kpi", EEPACC_N_KPI, 1}))
+
+// ---------------- evaluation ----------------
+static int eval_k1(int which, const double** arg, double** res, long long* iw, int mem)
+{
+    CallCtx c;
+    int rc = begin_call(mem, iw, c);
+    if (rc) return rc;
+    if (!arg || !res) return fail(EEPACC_ERR_ARG, "arg/res is NULL");
+    Mem* M = c.M; const long long B = c.B;
+    if (B == 0) return EEPACC_OK;
+    const int nx = (which >= 3) ? 1 : 4, nuu = (which >= 3) ? 1 : 6;
+    const double *dx, *du;
+    if ((rc = stage_in(M, 0, arg[0], (size_t)B * nx, c.dev, &dx))) return rc;
+    if ((rc = stage_in(M, 1, arg[1], (size_t)B * nuu, c.dev, &du))) return rc;
+    if (!dx || !du) return fail(EEPACC_ERR_ARG, "missing input");
+    double *o0, *o1 = nullptr, *o2 = nullptr;
+    const size_t n0 = (which >= 3) ? 1 : 4;
+    if ((rc = stage_out(M, 0, res[0], (size_t)B * n0, c.dev, &o0))) return rc;
+    if (which <= 2 && (rc = stage_out(M, 1, res[1], (size_t)B, c.dev, &o1))) return rc;
+    if (which == 2 && (rc = stage_out(M, 2, res[2], (size_t)B * 50, c.dev, &o2))) return rc;
+    if (!o0 || (which <= 2 && !o1) || (which == 2 && !o2)) return fail(EEPACC_ERR_ARG, "missing output buffer");
+    switch (which) {
+    case 0: eep_launch_f(&M->p, B, dx, du, o0, o1, M->stream); break;
+    case 1: eep_launch_F(&M->p, B, dx, du, o0, o1, M->stream); break;
+    case 2: eep_launch_Fjac(&M->p, B, dx, du, o0, o1, o2, M->stream); break;
+    case 3: eep_launch_power(&M->p, B, 1, dx, du, o0, M->stream); break;
+    default: eep_launch_power(&M->p, B, 0, dx, du, o0, M->stream); break;
+    }
+    M->launches += 1;
+    if ((rc = copy_out(M, 0, res[0], (size_t)B * n0, c.dev))) return rc;
+    if (which <= 2 && (rc = copy_out(M, 1, res[1], (size_t)B, c.dev))) return rc;
+    if (which == 2 && (rc = copy_out(M, 2, res[2], (size_t)B * 50, c.dev))) return rc;
+    return end_call(c);
+}
+
+int eepacc_f(const double** arg, double** res, long long* iw, double*, int mem) { return eval_k1(0, arg, res, iw, mem); }
+int eepacc_F(const double** arg, double** res, long long* iw, double*, int mem) { return eval_k1(1, arg, res, iw, mem); }
+int eepacc_F_jac(const double** arg, double** res, long long* iw, double*, int mem) { return eval_k1(2, arg, res, iw, mem); }
+int eepacc_power5(const double** arg, double** res, long long* iw, double*, int mem) { return eval_k1(3, arg, res, iw, mem); }
+int eepacc_power2(const double** arg, double** res, long long* iw, double*, int mem) { return eval_k1(4, arg, res, iw, mem); }
+
+int eepacc_plant(const double** arg, double** res, long long* iw, double*, int mem)
+{
+    CallCtx c;
+    int rc = begin_call(mem, iw, c);
+    if (rc) return rc;
+    if (!arg || !res) return fail(EEPACC_ERR_ARG, "arg/res is NULL");
+    Mem* M = c.M; const long long B = c.B;
+    if (B == 0) return EEPACC_OK;
+    if (B > M->B) return fail(EEPACC_ERR_ARG, "batch exceeds the routes bound to mem");
+    const double *dx, *du; double* o;
+    if ((rc = stage_in(M, 0, arg[0], (size_t)B * 2, c.dev, &dx))) return rc;
+    if ((rc = stage_in(M, 1, arg[1], (size_t)B * 2, c.dev, &du))) return rc;
+    if ((rc = stage_out(M, 0, res[0], (size_t)B * 2, c.dev, &o))) return rc;
+    if (!dx || !du || !o) return fail(EEPACC_ERR_ARG, "missing buffer");
+    eep_launch_plant(&M->p, B, M->routes.as<eepacc_route>(), 1, dx, du, o, M->stream);
+    M->launches += 1;
+    if ((rc = copy_out(M, 0, res[0], (size_t)B * 2, c.dev))) return rc;
+    return end_call(c);
+}
+
+static int eval_qpbuild(int ctrl, const double** arg, double** res, long long* iw, int mem)
+{
+    CallCtx c;
+    int rc = begin_call(mem, iw, c);
+    if (rc) return rc;
+    Mem* M = c.M;
+    if (M->ctrl != ctrl) return fail(EEPACC_ERR_ARG, "mem was set up for a different controller");
+    if (c.B != M->B) return fail(EEPACC_ERR_ARG, "batch must equal the batch bound to mem");
+    if (!arg || !res) return fail(EEPACC_ERR_ARG, "arg/res is NULL");
+    const size_t B = (size_t)M->B, n = M->n, m = M->m;
+    eep_build_io io = make_build_io(M, 1);
+    if ((rc = stage_in(M, 0, arg[0], B * 2, c.dev, &io.in_x0))) return rc;
+    if ((rc = stage_in(M, 1, arg[1], B, c.dev, &io.in_am1))) return rc;
+    if ((rc = stage_in(M, 2, arg[2], B * 3, c.dev, &io.in_lead))) return rc;
+    if ((rc = stage_in(M, 3, arg[3], B, c.dev, &io.in_t0))) return rc;
+    if (!io.in_x0 || !io.in_am1 || !io.in_lead || !io.in_t0) return fail(EEPACC_ERR_ARG, "missing input");
+    const size_t cnt[5] = { B * n * n, B * n, B * m * n, B * m, B * m };
+    double* o[5];
+    for (int k = 0; k < 5; ++k) {
+        if ((rc = stage_out(M, k, res[k], cnt[k], c.dev, &o[k]))) return rc;
+        if (!o[k]) return fail(EEPACC_ERR_ARG, "missing output buffer");
+    }
+    io.H = o[0]; io.g = o[1]; io.A = o[2]; io.lba = o[3]; io.uba = o[4];
+    CK(cudaMemsetAsync(io.A, 0, cnt[2] * 8, M->stream));
+    rc = eep_launch_build(&M->p, &io, M->stream);
+    if (rc) return fail(EEPACC_ERR_CUDA, "k2_build launch", (cudaError_t)rc);
+    M->launches += 1;
+    for (int k = 0; k < 5; ++k) if ((rc = copy_out(M, k, res[k], cnt[k], c.dev))) return rc;
+    return end_call(c);
+}
+int eepacc_qpbuild_ab(const double** a, double** r, long long* iw, double*, int mem) { return eval_qpbuild(EEPACC_AB, a, r, iw, mem); }
+int eepacc_qpbuild_fb(const double** a, double** r, long long* iw, double*, int mem) { return eval_qpbuild(EEPACC_FB, a, r, iw, mem); }
+int eepacc_qpbuild_bl(const double** a, double** r, long long* iw, double*, int mem) { return eval_qpbuild(EEPACC_BL, a, r, iw, mem); }
+int eepacc_qpbuild_tv(const double** a, double** r, long long* iw, double*, int mem) { return eval_qpbuild(EEPACC_TV, a, r, iw, mem); }
+
+int eepacc_qpsolve(const double** arg, double** res, long long* iw, double*, int mem)
+{
+    CallCtx c;
+    int rc = begin_call(mem, iw, c);
+    if (rc) return rc;
+    Mem* M = c.M;
+    if (c.B != M->B) return fail(EEPACC_ERR_ARG, "batch must equal the batch bound to mem (warm-start state is per vehicle)");
+    if (!arg || !res) return fail(EEPACC_ERR_ARG, "arg/res is NULL");
+    const size_t B = (size_t)M->B, n = M->n, m = M->m;
+    eep_qp_io io = make_qp_io(M);
+    const size_t icnt[7] = { B * n * n, B * n, B * m * n, B * m, B * m, B * n, B * n };
+    const double* in[7];
+    for (int k = 0; k < 7; ++k) if ((rc = stage_in(M, k, arg[k], icnt[k], c.dev, &in[k]))) return rc;
+    for (int k = 0; k < 5; ++k) if (!in[k]) return fail(EEPACC_ERR_ARG, "h, g, a, lba, uba are required");
+    io.H = in[0]; io.g = in[1]; io.A = in[2]; io.lba = in[3]; io.uba = in[4]; io.lbx = in[5]; io.ubx = in[6];
+    /* arg[7..9] (x0, lam_x0, lam_a0) are accepted for scheme compatibility; the hot start lives in mem,
+       exactly like the plugin's implicit qpOASES hot start. */
+    const size_t ocnt[6] = { B * n, B, B * m, B * n, B, B };
+    double* o[6];
+    for (int k = 0; k < 6; ++k) if ((rc = stage_out(M, k, res[k], ocnt[k], c.dev, &o[k]))) return rc;
+    if (!o[0]) return fail(EEPACC_ERR_ARG, "output x is required");
+    io.x = o[0];
+    if (o[1]) io.cost = o[1];
+    io.lam_a = o[2]; io.lam_x = o[3];
+    if (o[4]) io.status = o[4];
+    if (o[5]) io.iter = o[5];
+    rc = eep_launch_qp(&io, M->stream);
+    if (rc) return fail(EEPACC_ERR_CUDA, "k3_qp launch", (cudaError_t)rc);
+    M->launches += 1;
+    for (int k = 0; k < 6; ++k) if ((rc = copy_out(M, k, res[k], ocnt[k], c.dev))) return rc;
+    return end_call(c);
+}
+
+static int eval_step(int ctrl, const double** arg, double** res, long long* iw, int mem)
+{
+    CallCtx c;
+    int rc = begin_call(mem, iw, c);
+    if (rc) return rc;
+    Mem* M = c.M;
+    if (M->ctrl != ctrl) return fail(EEPACC_ERR_ARG, "mem was set up for a different controller");
+    if (c.B != M->B) return fail(EEPACC_ERR_ARG, "batch must equal the batch bound to mem");
+    if (!res) return fail(EEPACC_ERR_ARG, "res is NULL");
+    const size_t B = (size_t)M->B;
+    const double* lead = nullptr;
+    if (ctrl != EEPACC_TV) {
+        if (!arg || !arg[0]) return fail(EEPACC_ERR_ARG, "lead input is required");
+        if ((rc = stage_in(M, 0, arg[0], B * 2, c.dev, &lead))) return rc;
+    }
+    double* log = M->logrow.as<double>();
+    if ((rc = device_step(M, lead, log))) return rc;
+    // unpack the log row into the four outputs (device-side strided copies)
+    const size_t W = EEPACC_LOG_W * 8;
+    const int off[4] = { 0, 8, 9, 10 }, wid[4] = { 8, 1, 1, 1 };
+    for (int k = 0; k < 4; ++k) {
+        if (!res[k]) continue;
+        CK(cudaMemcpy2DAsync(res[k], wid[k] * 8, log + off[k], W, wid[k] * 8, B,
+                             c.dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, M->stream));
+    }
+    return end_call(c);
+}
+int eepacc_step_ab(const double** a, double** r, long long* iw, double*, int mem) { return eval_step(EEPACC_AB, a, r, iw, mem); }
+int eepacc_step_fb(const double** a, double** r, long long* iw, double*, int mem) { return eval_step(EEPACC_FB, a, r, iw, mem); }
+int eepacc_step_bl(const double** a, double** r, long long* iw, double*, int mem) { return eval_step(EEPACC_BL, a, r, iw, mem); }
+int eepacc_step_tv(const double** a, double** r, long long* iw, double*, int mem) { return eval_step(EEPACC_TV, a, r, iw, mem); }
+
+int eepacc_run(const double** arg, double** res, long long* iw, double*, int mem)
+{
+    CallCtx c;
+    int rc = begin_call(mem, iw, c);
+    if (rc) return rc;
+    Mem* M = c.M;
+    if (!arg || !arg[0] || !res) return fail(EEPACC_ERR_ARG, "n_steps input is required (host scalar)");
+    const long long n_steps = (long long)arg[0][0];
+    if (n_steps <= 0) return fail(EEPACC_ERR_ARG, "n_steps must be positive");
+    if (M->ctrl != EEPACC_TV && M->n_lead < n_steps) return fail(EEPACC_ERR_ARG, "lead trace shorter than n_steps (eepacc_mem_set_lead)");
+    const size_t B = (size_t)M->B;
+    if ((rc = reset_state(M))) return rc;
+    double* log_dev = nullptr;
+    if (res[0]) {
+        if (c.dev) log_dev = res[0];
+        else { if (M->out[0].ensure((size_t)n_steps * B * EEPACC_LOG_W * 8)) return EEPACC_ERR_MEM; log_dev = M->out[0].as<double>(); }
+    }
+    for (long long k = 0; k < n_steps; ++k) {
+        const double* lead = (M->ctrl == EEPACC_TV) ? nullptr : M->lead.as<double>() + (size_t)k * B * 2;
+        double* lg = log_dev ? log_dev + (size_t)k * B * EEPACC_LOG_W : nullptr;
+        if ((rc = device_step(M, lead, lg))) return rc;
+    }
+    rc = eep_launch_kpi_final(&M->p, M->B, (int)n_steps, M->kpi_acc.as<double>(), M->kpi.as<double>(), M->stream);
+    if (rc) return fail(EEPACC_ERR_CUDA, "kpi launch", (cudaError_t)rc);
+    M->launches += 1;
+    if (res[0] && !c.dev) CK(cudaMemcpyAsync(res[0], log_dev, (size_t)n_steps * B * EEPACC_LOG_W * 8, cudaMemcpyDeviceToHost, M->stream));
+    if (res[1]) CK(cudaMemcpyAsync(res[1], M->kpi.p, B * EEPACC_N_KPI * 8, c.dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, M->stream));
+    return end_call(c);
+}
+
+}  // extern "C"

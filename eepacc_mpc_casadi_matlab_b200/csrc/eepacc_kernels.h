@@ -1,0 +1,74 @@
+// eepacc_kernels.h -- host-visible launch interface of the sm_100a kernels (internal to the library).
+#pragma once
+#include <cuda_runtime.h>
+#include "../../include/eepacc.h"
+
+#define EEPACC_MAX_NVAR 120     // FB: 6*20
+#define EEPACC_MAX_NCON 522     // FB: 26*20+2
+#define EEPACC_LOG_W    12      // z1[8], a, status, iter, cost
+
+// K2 (k2_build.cu)
+struct eep_build_io {
+    long long B;
+    int ctrl, m, mode, kk;      // mode 0: closed loop (plant + bookkeeping inside), 1: inputs given
+    double t0;
+    const eepacc_route* routes; long long route_stride;
+    // closed-loop state, SoA [B]
+    double *s_prev, *v_prev, *Fm_prev, *Fb_prev, *a_minus1, *v_tv_meas;
+    double *fbA, *fbD;          // [B][N] FB dynamics rows (A(k,2,2), D(k,2)) incl. the A(k) quirk
+    const double* prev_sol;     // [B][2][N+1] previous predicted (s, v) (estimator mode 2 only)
+    const double* lead;         // [B][2] this step's (s_tv, v_tv)
+    // API-mode inputs
+    const double *in_x0, *in_am1, *in_lead, *in_t0;
+    // outputs
+    double *x0;                 // [B][2] measured state
+    double *H, *g, *A, *lba, *uba;
+    double *dyn;                // [B][2][N] alpha_k, Dv_k for the post kernel (may be null)
+};
+
+// K3 (k3_qp.cu)
+struct eep_qp_io {
+    long long B;
+    int n, m;
+    const double *H, *g, *A, *lba, *uba, *lbx, *ubx;   // lbx/ubx may be null (= +-inf)
+    // warm-start state (device, owned by the mem object)
+    double *wx, *wy;            // [B][n]
+    short *widx;                // [B][n]   constraint index per Q column
+    signed char *wside;         // [B][n]
+    int *wnA, *warm;            // [B]
+    // outputs
+    double *x, *cost, *lam_a, *lam_x, *status, *iter;   // lam_* may be null
+    unsigned long long *counters;   // [B][4] working-set changes, failed, exchanges, refactorisations
+    double *dbg; int dbg_cap;       // optional per-iteration trace of vehicle 0: tau, key, nA, exchanges
+};
+
+// post kernel (k4_post.cu): z recovery, force allocation, logging, KPI accumulation
+struct eep_post_io {
+    long long B;
+    int ctrl, n, kk;
+    const eepacc_route* routes; long long route_stride;
+    const double *x, *x0, *dyn, *status, *iter, *cost;
+    double *s_prev, *v_prev, *Fm_prev, *Fb_prev;
+    double *prev_sol;           // [B][2][N+1]
+    double *log;                // [B][EEPACC_LOG_W] for this step (may be null)
+    double *kpi_acc;            // [B][12] running KPI accumulators
+};
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+void eep_launch_f(const eepacc_params* p, long long B, const double* x, const double* u, double* xdot, double* L, cudaStream_t st);
+void eep_launch_F(const eepacc_params* p, long long B, const double* x, const double* u, double* xf, double* qf, cudaStream_t st);
+void eep_launch_Fjac(const eepacc_params* p, long long B, const double* x, const double* u, double* xf, double* qf, double* J, cudaStream_t st);
+void eep_launch_power(const eepacc_params* p, long long B, int fifth, const double* Fm, const double* rpm, double* P, cudaStream_t st);
+void eep_launch_plant(const eepacc_params* p, long long B, const eepacc_route* routes, long long route_stride,
+                      const double* x, const double* u, double* xn, cudaStream_t st);
+int eep_launch_build(const eepacc_params* p, const eep_build_io* io, cudaStream_t st);
+int eep_launch_qp(const eep_qp_io* io, cudaStream_t st);
+size_t eep_qp_smem_bytes(int n, int m);
+int eep_launch_post(const eepacc_params* p, const eep_post_io* io, cudaStream_t st);
+int eep_launch_kpi_final(const eepacc_params* p, long long B, int n_steps, const double* kpi_acc, double* kpi, cudaStream_t st);
+double eep_dfma_peak(int device);
+#ifdef __cplusplus
+}
+#endif

@@ -120,6 +120,9 @@ int eepacc_mem_setup(int mem, int ctrl, const eepacc_params* p, const eepacc_rou
                      long long B, int device);
 /* Reset plant / warm-start state to step 0 without re-uploading the scenario. */
 int eepacc_mem_reset(int mem);
+/* Set the simulation-step counter / clock used by the stand-alone eepacc_qpbuild_*() calls
+ * (FB A(k) quirk row, traffic-light phase); the step functions advance both themselves. */
+int eepacc_mem_set_step(int mem, int kk, double t0);
 /* Upload a whole lead trace: host double[n_steps][B][2] = (s_tv, v_tv) per step.  Enables
  * eepacc_run_*(): the whole closed loop without per-step host involvement. */
 int eepacc_mem_set_lead(int mem, const double* lead, long long n_steps);
@@ -130,7 +133,21 @@ long long eepacc_mem_launch_count(int mem);
 /* Per-vehicle counters accumulated so far: double[B][4] = working-set changes, failed QPs,
  * refactorisations with dropped rows, flips.  Host pointer. */
 int eepacc_mem_get_counters(int mem, double* out);
+/* Device pointer (double[B][EEPACC_N_KPI]) of the KPI block after eepacc_run(): lets the caller
+ * gather KPIs GPU-to-GPU (NCCL) without a host bounce. */
+void* eepacc_mem_kpi_device_ptr(int mem);
+/* ABI guards for bindings (ctypes / cgo / JNI): sizeof the two PODs as compiled. */
+long long eepacc_sizeof_params(void);
+long long eepacc_sizeof_route(void);
 const char* eepacc_last_error(void);
+/* CUDA-event timing of every closed-loop kernel launch on the mem's stream (roofline evidence).
+ * tot[4] = summed ms of k2_build, k3_qp, k4_post and the number of steps since the last reset;
+ * step_ms[cap] (may be NULL) = per-step batch latency. */
+int eepacc_mem_enable_timing(int mem, int on);
+int eepacc_mem_get_timing(int mem, double* tot, double* step_ms, long long cap);
+/* Developer aid: first call enables a per-iteration solver trace for vehicle 0; later calls fetch
+ * out[cap][4] = step length, ratio-test key, |working set|, exchanges of the last solve. */
+int eepacc_mem_debug_trace(int mem, double* out, int cap);
 /* FP64-FMA peak microbenchmark (register-resident DFMA chains); returns GFLOP/s or <0. */
 double eepacc_measure_dfma_peak(int device);
 
@@ -199,11 +216,12 @@ EEPACC_DECLARE(eepacc_step_bl)
 EEPACC_DECLARE(eepacc_step_tv)
 
 /* Whole closed loop on the device (needs eepacc_mem_set_lead):  in: n_steps[1] (scalar, NOT
- * batched); out: log[n_steps][B][10] = z1[8], a, status;  kpi[B][8] (see eepacc_kpi below). */
+ * batched); out: log[n_steps][B][12] = z1[8], a, status, iter, cost (may be NULL);  kpi[B][8]. */
 EEPACC_DECLARE(eepacc_run)
 
-/* KPI block per scenario (Main.m:191-263): energy J (Ts*sum quintic), distance m, travel
- * time to cut-off s, max|a|, rms a, rms jerk, count(xi_s>0 | xi_f>0), failed QPs.          */
+/* KPI block per scenario (Main.m:136-148,218-258; RunOpt_FBMPC.m:334-339):
+ * [0] E_opt(end) J   [1] s_opt(end) m   [2] travel time at cutOffDist s   [3] E_opt at cut-off J
+ * [4] max a   [5] min a   [6] rms a (over 1..distInd)   [7] failed QPs (sum exitMessage)       */
 #define EEPACC_N_KPI 8
 
 #ifdef __cplusplus

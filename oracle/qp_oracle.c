@@ -33,6 +33,7 @@
 #define EPS_LI    1.0e-10    /* linear-independence test, relative to |a|                 */
 #define EPS_PD    1.0e-9     /* projected-Hessian pivot test, relative to max|diag H|     */
 #define EPS_RATE  1.0e-12
+#define EPS_ROW   1.0e-12    /* |a'dx| below EPS_ROW*|a|_1*|dx|_inf is numerically zero      */
 #define LP_REG    1.0e-6
 
 struct orc_qpws {
@@ -45,6 +46,7 @@ struct orc_qpws {
     double *g_cur, *lb_cur, *ub_cur, *lb_new, *ub_new;
     double *Q, *T, *R;                 /* n x n each */
     double *dx, *dyW, *Adx, *tmp1, *tmp2, *tmp3, *tmp4, *dg, *dlb, *dub;
+    double *anorm;    /* [mt] L1 norm of every constraint row */
     const double *H, *A, *g_new;
     double hscale;
     double reg;       /* Tikhonov term for an all-zero Hessian (LP), see orc_qpsolve */
@@ -67,6 +69,7 @@ orc_qpws* orc_qpws_new(int n, int m)
     w->dx = dalloc(n); w->dyW = dalloc(n); w->Adx = dalloc(w->mt);
     w->tmp1 = dalloc(w->mt); w->tmp2 = dalloc(w->mt); w->tmp3 = dalloc(w->mt); w->tmp4 = dalloc(w->mt);
     w->dg = dalloc(n); w->dlb = dalloc(w->mt); w->dub = dalloc(w->mt);
+    w->anorm = dalloc(w->mt);
     return w;
 }
 
@@ -76,7 +79,7 @@ void orc_qpws_free(orc_qpws* w)
     free(w->widx); free(w->st); free(w->x); free(w->y); free(w->Ax); free(w->g_cur);
     free(w->lb_cur); free(w->ub_cur); free(w->lb_new); free(w->ub_new); free(w->Q); free(w->T);
     free(w->R); free(w->dx); free(w->dyW); free(w->Adx); free(w->tmp1); free(w->tmp2);
-    free(w->tmp3); free(w->tmp4); free(w->dg); free(w->dlb); free(w->dub);
+    free(w->tmp3); free(w->tmp4); free(w->dg); free(w->dlb); free(w->dub); free(w->anorm);
     free(w);
 }
 
@@ -465,11 +468,12 @@ static int resolve_pending(orc_qpws* w, int c_out, int side_out, int dbg)
         for (int cc = 0; cc < mt; ++cc) {
             if (w->st[cc] != 0) continue;
             double adx = w->Adx[cc];
-            if (adx < -1e-11 * dn && !isinf(w->lb_cur[cc])) {
+            const double rz = EPS_ROW * w->anorm[cc] * dn;
+            if (adx < -rz && !isinf(w->lb_cur[cc])) {
                 double sl = w->Ax[cc] - w->lb_cur[cc]; if (sl < 0) sl = 0;
                 double t = sl / (-adx);
                 if (t < tmin) { tmin = t; j = cc; jside = -1; }
-            } else if (adx > 1e-11 * dn && !isinf(w->ub_cur[cc])) {
+            } else if (adx > rz && !isinf(w->ub_cur[cc])) {
                 double sl = w->ub_cur[cc] - w->Ax[cc]; if (sl < 0) sl = 0;
                 double t = sl / adx;
                 if (t < tmin) { tmin = t; j = cc; jside = 1; }
@@ -543,6 +547,11 @@ int orc_qpsolve(orc_qpws* w, const double* H, const double* g, const double* A,
     }
     if (w->hscale < LP_REG) w->hscale = LP_REG;
 
+    for (int c = 0; c < m; ++c) w->anorm[c] = 0.0;
+    for (int j = 0; j < n; ++j)
+        for (int c = 0; c < m; ++c) w->anorm[c] += fabs(A[(size_t)j * m + c]);
+    for (int j = 0; j < n; ++j) w->anorm[m + j] = 1.0;
+
     /* ---------------- set-up: working set, factorisation, auxiliary QP ---------------- */
     int need_cold = !w->warm;
     if (!need_cold) {
@@ -610,12 +619,15 @@ int orc_qpsolve(orc_qpws* w, const double* H, const double* g, const double* A,
 
         /* ratio tests */
         double tau = 1.0; int blk = -1, blk_side = 0, blk_dual = -1;
+        double dxmax = 0;
+        for (int i = 0; i < n; ++i) if (fabs(w->dx[i]) > dxmax) dxmax = fabs(w->dx[i]);
         for (int c = 0; c < mt; ++c) {
             if (w->st[c] != 0) continue;
             double adx = w->Adx[c];
+            const double rz = EPS_ROW * w->anorm[c] * dxmax;
             if (!isinf(w->lb_cur[c])) {
                 double rate = adx - w->dlb[c];
-                if (rate < -EPS_RATE * (1.0 + fabs(adx) + fabs(w->dlb[c]))) {
+                if (rate < -(EPS_RATE * (1.0 + fabs(adx) + fabs(w->dlb[c])) + rz)) {
                     double sl = w->Ax[c] - w->lb_cur[c]; if (sl < 0) sl = 0;
                     double t = sl / (-rate);
                     if (t < tau) { tau = t; blk = c; blk_side = -1; }
@@ -623,7 +635,7 @@ int orc_qpsolve(orc_qpws* w, const double* H, const double* g, const double* A,
             }
             if (!isinf(w->ub_cur[c])) {
                 double rate = w->dub[c] - adx;
-                if (rate < -EPS_RATE * (1.0 + fabs(adx) + fabs(w->dub[c]))) {
+                if (rate < -(EPS_RATE * (1.0 + fabs(adx) + fabs(w->dub[c])) + rz)) {
                     double sl = w->ub_cur[c] - w->Ax[c]; if (sl < 0) sl = 0;
                     double t = sl / (-rate);
                     if (t < tau) { tau = t; blk = c; blk_side = 1; }
