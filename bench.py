@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""bench.py -- closed-loop batched MPC throughput (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One bench "step" = one full closed-loop driving cycle (871 MPC steps, each = K5/K4/K2 build ->
+K3 QP solve -> post) for this rank's batch of synthetic perturbed scenarios:
+    N = 1 : BASELINE config[1]  "ABMPC closed loop, batch 4096 perturbed urban lead-vehicle scenarios"
+    N > 1 : weak scaling, 4096 scenarios per GPU, contiguous block partition of the scenario index,
+            no data-path collective; one NCCL all_gather of the KPI block at the end of each step.
+value = closed-loop QP solves / s with the lead traces and route previews resident in HBM;
+e2e   = the same through the C-ABI with HOST buffers (lead upload + KPI download in the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+METRIC = "closed-loop QP solves/sec (batched MPC, full driving cycle)"
+UNIT = "QP solves/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ctrl", default="ab", choices=["ab", "fb", "bl", "tv"])
+    ap.add_argument("--batch", type=int, default=4096, help="scenarios per GPU")
+    ap.add_argument("--cycle-steps", type=int, default=871, help="MPC steps per driving cycle")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="scenarios per core for the CPU baseline (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def lead_2hz():
+    d = np.load(os.path.join(GOLDEN, "lead_TO01_EAD.npz"))
+    s = d["s_tv"]
+    return np.r_[0.0, np.diff(s) / 0.5]
+
+
+def make_workload(ctrl, B, first, n_steps):
+    """Scenarios [first, first+B) of the global synthetic batch (counter-based RNG => rank independent)."""
+    from eepacc_mpc_casadi_matlab_b200 import settings as S, usecase as U
+    p = S.default_params("mc")
+    hw = None
+    if ctrl == "fb":
+        w = np.load(os.path.join(GOLDEN, "lead_WLTC.npz"))
+        hw = np.r_[0.0, np.diff(w["s_tv"]) / 0.5]
+    routes, lead = U.perturbed_scenarios(B, lead_2hz(), highway_v_2hz=hw, mass=(ctrl == "fb"),
+                                         full_route=(ctrl in ("bl", "tv")), n_steps=n_steps, first=first)
+    return p, routes, lead
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle (a C port of the reference path; CasADi+qpOASES cannot be built here)
+# ---------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    ctrl, first, count, n_steps = args
+    from eepacc_mpc_casadi_matlab_b200 import settings as S
+    from oracle import oracle as O
+    p, routes, lead = make_workload(ctrl, count, first, n_steps)
+    t0 = time.perf_counter()
+    for b in range(count):
+        O.run(S.CTRL_NAMES[ctrl], p, routes[b], lead[:, b, :])
+    return time.perf_counter() - t0
+
+
+def cpu_run(ctrl, n_steps, per_core):
+    """All host cores, one process per core, `per_core` scenarios each.  -> (solves/s, cores, sample)."""
+    import multiprocessing as mp
+    from oracle import oracle as O
+    O.build()
+    cores = os.cpu_count() or 1
+    cores = min(cores, 64)
+    jobs = [(ctrl, c * per_core, per_core, n_steps) for c in range(cores)]
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(cores) as pool:
+        pool.map(_cpu_worker, jobs)
+    wall = time.perf_counter() - t0
+    solves = cores * per_core * n_steps
+    return solves / wall, cores, f"{cores * per_core} scenarios x {n_steps} MPC steps, one process per core"
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_core = args.cpu_sample or 1
+    # scenario generation happens inside the workers and is excluded from their timers only
+    vals = []
+    for _ in range(args.warmup if args.warmup < 1 else 1):
+        cpu_run(args.ctrl, min(args.cycle_steps, 60), per_core)
+    t_all = time.perf_counter()
+    for _ in range(args.steps):
+        v, cores, sample = cpu_run(args.ctrl, args.cycle_steps, per_core)
+        vals.append(v)
+    wall = time.perf_counter() - t_all
+    value = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, args.steps),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.ctrl.upper()}MPC closed loop, perturbed urban lead-vehicle scenarios, "
+                               f"{args.cycle_steps} MPC steps/cycle (bounded CPU sample of the same batch)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "oracle/ C port of the reference path (CasADi 3.6.3 + qpOASES 3.2 are binary-only/absent and cannot be built here)",
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.rows.append([c.strip() for c in ln.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for k, nm in enumerate(names):
+                    if r[2 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+    import torch
+    import torch.distributed as dist
+    from eepacc_mpc_casadi_matlab_b200 import api, settings as S
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback in the product path)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B, ns = args.batch, args.cycle_steps
+    p, routes, lead = make_workload(args.ctrl, B, rank * B, ns)
+    eng = api.Engine(args.ctrl, p, routes, B=B, device=local)
+    n, m = eng.n, eng.m
+    lead_pinned = torch.from_numpy(np.ascontiguousarray(lead)).pin_memory()
+    eng.set_lead(lead_pinned.numpy())
+    kpi_dev = torch.empty((B, S.N_KPI), dtype=torch.float64, device="cuda")
+    gathered = [torch.empty_like(kpi_dev) for _ in range(world)] if world > 1 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run_resident():
+        _, k = eng.run(ns, want_log=False, device_out=kpi_dev)
+        if world > 1:
+            dist.all_gather(gathered, k)          # the only collective: final KPIs over NVLink
+        return k
+
+    def run_e2e():
+        eng.set_lead(lead_pinned.numpy())         # H2D of this step's inputs (pinned host memory)
+        _, k = eng.run(ns, want_log=False)         # host KPI buffer: D2H inside the call
+        return k
+
+    for _ in range(max(args.warmup, 0)):
+        run_resident()
+    # ---- timed: resident inputs ----
+    eng.enable_timing(True)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    l0 = eng.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    step_lat = []
+    kt = {"build_ms": 0.0, "qp_ms": 0.0, "post_ms": 0.0}
+    for _ in range(args.steps):
+        run_resident()
+        t = eng.timing(ns)
+        step_lat.append(t["step_ms"].copy())
+        for k_ in kt:
+            kt[k_] += t[k_]
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = eng.launch_count() - l0
+    ms = ev0.elapsed_time(ev1)
+    eng.enable_timing(False)
+    ctr = eng.counters()
+    # ---- timed: end to end through the C-ABI with host buffers ----
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        kh = run_e2e()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    # max over ranks
+    if world > 1:
+        tt = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = tt.tolist()
+    else:
+        e2e_ms = e2e_s * 1e3
+    solves = world * B * ns * args.steps
+    value = solves / (ms * 1e-3)
+    e2e_val = solves / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, burst)" if peaks else "fallback 6650 GB/s"
+        launches_qp = args.steps * ns
+        qp_ms = kt["qp_ms"] / launches_qp
+        # algorithmic bytes of one K3 launch: the dense conic operands of B QPs read once + x written
+        bytes_qp = B * ((n * n + m * n + n + 2 * m) * 8 + n * 8 + 3 * 8)
+        achieved = bytes_qp / (qp_ms * 1e-3) / 1e9
+        it_mean = float(ctr[:, 0].mean()) / ns          # counters restart with every cycle
+        lat = np.concatenate(step_lat)
+        tot_k = kt["build_ms"] + kt["qp_ms"] + kt["post_ms"]
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.ctrl.upper()}MPC closed loop, batch {B} perturbed urban lead-vehicle "
+                                   f"scenarios per GPU, {ns} MPC steps/cycle (BASELINE configs[1] at N=1)",
+                       "controller": args.ctrl, "batch_per_gpu": B, "cycle_steps": ns, "qp_n": n, "qp_m": m,
+                       "l2": "per-step working set (dense H+A of all vehicles, "
+                             f"{B * (n * n + m * n) * 8 / 1e6:.0f} MB) exceeds the 126 MB L2"},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(lead_pinned.numel() * 8),
+                    "d2h_bytes_per_step": int(B * S.N_KPI * 8)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "k3_qp_kernel", "achieved": achieved, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "ms_per_launch": qp_ms, "share_of_step": kt["qp_ms"] / tot_k if tot_k else None},
+            "kernel_ms_per_cycle": {k_: v / args.steps for k_, v in kt.items()},
+            "latency_ms": {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)),
+                           "max": float(lat.max()), "what": "one batched MPC step (build+solve+post), CUDA events"},
+            "solver": {"mean_ws_changes_per_qp": it_mean, "failed_qps": int(ctr[:, 1].sum())},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            v, cores, sample = cpu_run(args.ctrl, ns, args.cpu_sample or 1)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

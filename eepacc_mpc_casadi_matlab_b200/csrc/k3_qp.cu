@@ -33,6 +33,7 @@
 #define EPS_PD    1.0e-9
 #define EPS_RATE  1.0e-12
 #define EPS_ROW   1.0e-12
+#define FEAS_TOL  1.0e-10
 #define LP_REG    1.0e-6
 
 struct Ctx {
@@ -47,6 +48,7 @@ struct Ctx {
     double *Ax, *lbc, *ubc, *Adx, *anorm;
     short* widx;            // [n] by Q column r
     signed char* st;        // [mt]
+    signed char* tabu;      // [mt] anti-cycling flags
     double* red;            // [2*NT/32 + 8]
     int* ired;
 };
@@ -432,7 +434,7 @@ __device__ void reanchor(Ctx& C, bool recompute_y)
 }
 
 // see oracle/qp_oracle.c:resolve_pending
-__device__ int resolve_pending(Ctx& C, int c_out, int side_out, unsigned long long& n_exch)
+__device__ int resolve_pending(Ctx& C, int c_out, int side_out, unsigned long long& n_exch, bool zero_step)
 {
     const int n = C.n, mt = C.mt;
     bool first = true, moved = false;
@@ -481,7 +483,7 @@ __device__ int resolve_pending(Ctx& C, int c_out, int side_out, unsigned long lo
         dn = sqrt(block_sum(C, dn));
         double tmin = INFINITY; int key = 0x7fffffff;
         for (int cc = threadIdx.x; cc < mt; cc += NT) {
-            if (C.st[cc] != 0) continue;
+            if (C.st[cc] != 0 || C.anorm[cc] == 0.0) continue;
             double adx = C.Adx[cc];
             const double rz = EPS_ROW * C.anorm[cc] * dn;
             if (adx < -rz && !isinf(C.lbc[cc])) {
@@ -505,7 +507,7 @@ __device__ int resolve_pending(Ctx& C, int c_out, int side_out, unsigned long lo
         if (threadIdx.x == 0) { if (jside < 0) C.lbc[j] = C.Ax[j]; else C.ubc[j] = C.Ax[j]; }
         get_row(C, j, C.t2);
         givens_add(C, j, jside, C.t2, kpd + 1, kpd, false);
-        if (threadIdx.x == 0) C.yW[kpd] = 0.0;
+        if (threadIdx.x == 0) { C.yW[kpd] = 0.0; if (zero_step) C.tabu[j] = 1; }
         __syncthreads();
         n_exch++;
         first = false; moved = true;
@@ -553,6 +555,7 @@ __global__ void __launch_bounds__(NT) k3_qp_kernel(eep_qp_io io)
         C.ired = reinterpret_cast<int*>(p); p += 4;
         C.widx = reinterpret_cast<short*>(p); p += (n + 3) / 4 + 1;
         C.st = reinterpret_cast<signed char*>(p);
+        C.tabu = C.st + mt;
     }
     for (long long veh = blockIdx.x; veh < io.B; veh += gridDim.x) {
         __syncthreads();
@@ -581,6 +584,7 @@ __global__ void __launch_bounds__(NT) k3_qp_kernel(eep_qp_io io)
                 C.anorm[r] = s;
             }
             for (int j = threadIdx.x; j < n; j += NT) C.anorm[m + j] = 1.0;
+            for (int c = threadIdx.x; c < mt; c += NT) C.tabu[c] = 0;
             __syncthreads();
         }
 
@@ -645,15 +649,16 @@ __global__ void __launch_bounds__(NT) k3_qp_kernel(eep_qp_io io)
             dxmax = block_max(C, dxmax);
             double tau = 1.0; int key = 0x7fffffff;
             for (int c = threadIdx.x; c < mt; c += NT) {
-                if (C.st[c] != 0) continue;
+                if (C.st[c] != 0 || C.anorm[c] == 0.0) continue;      // all-zero rows can never be added
                 double adx = C.Adx[c];
                 const double rz = EPS_ROW * C.anorm[c] * dxmax;
                 if (!isinf(C.lbc[c])) {
                     double ln = lb_new(C, c);
                     double dlb = isinf(ln) ? 0.0 : ln - C.lbc[c];
                     double rate = adx - dlb;
-                    if (rate < -(EPS_RATE * (1.0 + fabs(adx) + fabs(dlb)) + rz)) {
-                        double sl = C.Ax[c] - C.lbc[c]; if (sl < 0) sl = 0;
+                    double sl = C.Ax[c] - C.lbc[c]; if (sl < 0) sl = 0;
+                    if (rate < -(EPS_RATE * (1.0 + fabs(adx) + fabs(dlb)) + rz) &&
+                        -rate - sl > FEAS_TOL * (1.0 + fabs(ln))) {
                         double t = sl / (-rate);
                         int k = 2 * c;
                         if (t < tau || (t == tau && k < key && t < 1.0)) { tau = t; key = k; }
@@ -663,8 +668,9 @@ __global__ void __launch_bounds__(NT) k3_qp_kernel(eep_qp_io io)
                     double un = ub_new(C, c);
                     double dub = isinf(un) ? 0.0 : un - C.ubc[c];
                     double rate = dub - adx;
-                    if (rate < -(EPS_RATE * (1.0 + fabs(adx) + fabs(dub)) + rz)) {
-                        double sl = C.ubc[c] - C.Ax[c]; if (sl < 0) sl = 0;
+                    double sl = C.ubc[c] - C.Ax[c]; if (sl < 0) sl = 0;
+                    if (rate < -(EPS_RATE * (1.0 + fabs(adx) + fabs(dub)) + rz) &&
+                        -rate - sl > FEAS_TOL * (1.0 + fabs(un))) {
                         double t = sl / (-rate);
                         int k = 2 * c + 1;
                         if (t < tau || (t == tau && k < key && t < 1.0)) { tau = t; key = k; }
@@ -678,6 +684,7 @@ __global__ void __launch_bounds__(NT) k3_qp_kernel(eep_qp_io io)
             for (int r = nZ + threadIdx.x; r < n; r += NT) {
                 int c = C.widx[r];
                 if (lb_new(C, c) == ub_new(C, c)) continue;
+                if (C.tabu[c]) continue;                 // no reversal inside a run of zero-length steps
                 double yc = C.yW[r], dy = C.dyW[r];
                 int k = 2 * mt + (n - 1 - r);
                 if (C.st[c] < 0 && dy < -thr) {
@@ -691,6 +698,10 @@ __global__ void __launch_bounds__(NT) k3_qp_kernel(eep_qp_io io)
             block_argmin(C, tau, key);
             const bool full = !(tau < 1.0) || key == 0x7fffffff;
             if (full) tau = 1.0;
+            // anti-cycling (see oracle/qp_oracle.c): constraints that enter while the homotopy makes no
+            // progress may not leave through the dual test until it does
+            const bool zero_step = !(tau > 1e-14);
+            if (!zero_step) for (int c = threadIdx.x; c < mt; c += NT) C.tabu[c] = 0;
 
             // take the step
             for (int i = threadIdx.x; i < n; i += NT) {
@@ -715,7 +726,10 @@ __global__ void __launch_bounds__(NT) k3_qp_kernel(eep_qp_io io)
             if (key < 2 * mt) {
                 // ---------- primal blocking: add constraint ----------
                 const int blk = key >> 1, side = (key & 1) ? 1 : -1;
-                if (threadIdx.x == 0) { if (side < 0) C.lbc[blk] = C.Ax[blk]; else C.ubc[blk] = C.Ax[blk]; }
+                if (threadIdx.x == 0) {
+                    if (side < 0) C.lbc[blk] = C.Ax[blk]; else C.ubc[blk] = C.Ax[blk];
+                    if (zero_step) C.tabu[blk] = 1;
+                }
                 get_row(C, blk, C.t4);
                 const int nZc = n - C.nA;
                 if (givens_add(C, blk, side, C.t4, nZc, nZc, true) == 0) {
@@ -772,7 +786,7 @@ __global__ void __launch_bounds__(NT) k3_qp_kernel(eep_qp_io io)
                 const int side = C.st[c];
                 __syncthreads();
                 remove_constraint(C, rp);
-                int rc = resolve_pending(C, c, side, n_exch);
+                int rc = resolve_pending(C, c, side, n_exch, zero_step);
                 if (rc) { status = rc; break; }
             }
         }
@@ -819,6 +833,10 @@ __global__ void __launch_bounds__(NT) k3_qp_kernel(eep_qp_io io)
                 int far = 0;
                 for (int r = nZ + threadIdx.x; r < n; r += NT) { int c = C.widx[r]; if (c >= m && fabs(C.x[c - m]) >= FARB) far = 1; }
                 if (block_max(C, (double)far) > 0) status = EEPACC_QP_UNBOUNDED;
+                int zr = 0;         // an all-zero row with inconsistent bounds: infeasible QP
+                for (int c = threadIdx.x; c < m; c += NT)
+                    if (C.anorm[c] == 0.0 && (lb_new(C, c) > 1e-8 || ub_new(C, c) < -1e-8)) zr = 1;
+                if (block_max(C, (double)zr) > 0) status = EEPACC_QP_INFEASIBLE;
             }
             for (int i = threadIdx.x; i < n; i += NT) {
                 io.x[veh * (size_t)n + i] = C.x[i];
@@ -858,7 +876,7 @@ extern "C" size_t eep_qp_smem_bytes(int n, int m)
     const int mt = n + m, ldq = n | 1;
     size_t d = (size_t)n * ldq + (size_t)n * (n + 1) / 2 + (n + 1) + 12 * (size_t)n + 2 * (size_t)(n + 1)
              + 5 * (size_t)mt + 8 + 4 + ((n + 3) / 4 + 1);
-    return d * 8 + (size_t)mt + 16;
+    return d * 8 + 2 * (size_t)mt + 16;
 }
 
 extern "C" int eep_launch_qp(const eep_qp_io* io, cudaStream_t st)

@@ -129,15 +129,16 @@ def _uniform(rng, lo, hi, size=None):
 
 
 def perturbed_scenarios(B, base_v_2hz, seed=0xEE9ACC, highway_v_2hz=None, mass=False,
-                        full_route=False, n_steps=871, ts=0.5):
-    """Synthetic scenario batch.  Scenario 0 is the unperturbed
-    golden case.  Returns (routes: Route*B ctypes array, lead: float64[n_steps, B, 2]).
+                        full_route=False, n_steps=871, ts=0.5, first=0):
+    """Synthetic scenario batch: global scenarios first..first+B-1.
+    Global scenario 0 is the unperturbed golden case.  Returns (routes: Route*B ctypes array, lead: float64[n_steps, B, 2]).
 
     base_v_2hz / highway_v_2hz: 2 Hz lead speed samples (after resample + threshold)."""
     routes = (Route * B)()
     lead = np.zeros((n_steps, B, 2))
     t = np.arange(n_steps) * ts
-    for b in range(B):
+    for bl in range(B):
+        b = first + bl
         rng = np.random.Generator(np.random.Philox(key=seed, counter=[b, 0, 0, 0]))
         hw = highway_v_2hz is not None and (b % 2 == 1)
         y = np.array(highway_v_2hz if hw else base_v_2hz, dtype=np.float64)[:n_steps].copy()
@@ -183,10 +184,10 @@ def perturbed_scenarios(B, base_v_2hz, seed=0xEE9ACC, highway_v_2hz=None, mass=F
                 slopes.append([_uniform(rng, 0, 8), int(pos), int(pos + ln)])
                 pos += ln
         try:
-            routes[b] = generate_use_case(zones, curves, slopes, stops, tls, ms)
+            routes[bl] = generate_use_case(zones, curves, slopes, stops, tls, ms)
         except ValueError:
-            routes[b] = generate_use_case(zones, None, None, stops, tls, ms)
+            routes[bl] = generate_use_case(zones, None, None, stops, tls, ms)
         s_tv, v_tv = lead_from_half_hz(y, t_sim=(n_steps - 1) * ts, ts=ts, init_dist=gap)
-        lead[:, b, 0] = s_tv
-        lead[:, b, 1] = v_tv
+        lead[:, bl, 0] = s_tv
+        lead[:, bl, 1] = v_tv
     return routes, lead

@@ -34,6 +34,7 @@
 #define EPS_PD    1.0e-9     /* projected-Hessian pivot test, relative to max|diag H|     */
 #define EPS_RATE  1.0e-12
 #define EPS_ROW   1.0e-12    /* |a'dx| below EPS_ROW*|a|_1*|dx|_inf is numerically zero      */
+#define FEAS_TOL  1.0e-10    /* a bound violated by less than this at the full step is not blocking (cf. qpOASES boundTolerance) */
 #define LP_REG    1.0e-6
 
 struct orc_qpws {
@@ -42,6 +43,7 @@ struct orc_qpws {
     int nA;
     int* widx;        /* [n]  constraint index per working-set position */
     int* st;          /* [mt] -1 lower, 0 inactive, +1 upper            */
+    char* tabu;       /* [mt] anti-cycling: added during the current run of zero-length steps */
     double *x, *y, *Ax;
     double *g_cur, *lb_cur, *ub_cur, *lb_new, *ub_new;
     double *Q, *T, *R;                 /* n x n each */
@@ -62,6 +64,7 @@ orc_qpws* orc_qpws_new(int n, int m)
     w->n = n; w->m = m; w->mt = m + n;
     w->widx = (int*)calloc((size_t)n, sizeof(int));
     w->st = (int*)calloc((size_t)w->mt, sizeof(int));
+    w->tabu = (char*)calloc((size_t)w->mt, 1);
     w->x = dalloc(n); w->y = dalloc(w->mt); w->Ax = dalloc(w->mt);
     w->g_cur = dalloc(n); w->lb_cur = dalloc(w->mt); w->ub_cur = dalloc(w->mt);
     w->lb_new = dalloc(w->mt); w->ub_new = dalloc(w->mt);
@@ -76,7 +79,7 @@ orc_qpws* orc_qpws_new(int n, int m)
 void orc_qpws_free(orc_qpws* w)
 {
     if (!w) return;
-    free(w->widx); free(w->st); free(w->x); free(w->y); free(w->Ax); free(w->g_cur);
+    free(w->widx); free(w->st); free(w->tabu); free(w->x); free(w->y); free(w->Ax); free(w->g_cur);
     free(w->lb_cur); free(w->ub_cur); free(w->lb_new); free(w->ub_new); free(w->Q); free(w->T);
     free(w->R); free(w->dx); free(w->dyW); free(w->Adx); free(w->tmp1); free(w->tmp2);
     free(w->tmp3); free(w->tmp4); free(w->dg); free(w->dlb); free(w->dub); free(w->anorm);
@@ -419,7 +422,7 @@ static void reanchor(orc_qpws* w, int recompute_y);
  * the pending column to R (projected Hessian stays positive definite) or move along the
  * direction of non-positive curvature to the next blocking constraint, add it and repeat.
  * (c_out, side_out) = the constraint whose removal created the pending column. */
-static int resolve_pending(orc_qpws* w, int c_out, int side_out, int dbg)
+static int resolve_pending(orc_qpws* w, int c_out, int side_out, int dbg, int zero_step)
 {
     const int n = w->n, mt = w->mt;
     double* Qm = w->Q; double* Rm = w->R;
@@ -466,7 +469,7 @@ static int resolve_pending(orc_qpws* w, int c_out, int side_out, int dbg)
         double tmin = INFINITY; int j = -1, jside = 0;
         double dn = 0; for (int i = 0; i < n; ++i) dn += d[i] * d[i]; dn = sqrt(dn);
         for (int cc = 0; cc < mt; ++cc) {
-            if (w->st[cc] != 0) continue;
+            if (w->st[cc] != 0 || w->anorm[cc] == 0.0) continue;
             double adx = w->Adx[cc];
             const double rz = EPS_ROW * w->anorm[cc] * dn;
             if (adx < -rz && !isinf(w->lb_cur[cc])) {
@@ -488,6 +491,7 @@ static int resolve_pending(orc_qpws* w, int c_out, int side_out, int dbg)
         get_row(w, j, a_j);
         add_constraint_pending(w, j, jside, a_j, kpd);
         w->y[j] = 0.0;
+        if (zero_step) w->tabu[j] = 1;
         w->n_exch++;
         first = 0; moved = 1;
     }
@@ -524,6 +528,7 @@ int orc_qpsolve(orc_qpws* w, const double* H, const double* g, const double* A,
     const int max_iter = 5 * (n + m);
     w->H = H; w->A = A; w->g_new = g;
     w->n_exch = 0; w->n_refac = 0;
+    memset(w->tabu, 0, (size_t)w->mt);
     const int dbg = getenv("ORC_QP_DEBUG") != 0;
     for (int i = 0; i < m; ++i) {
         w->lb_new[i] = (lba[i] <= -BIG) ? -INFINITY : lba[i];
@@ -622,21 +627,23 @@ int orc_qpsolve(orc_qpws* w, const double* H, const double* g, const double* A,
         double dxmax = 0;
         for (int i = 0; i < n; ++i) if (fabs(w->dx[i]) > dxmax) dxmax = fabs(w->dx[i]);
         for (int c = 0; c < mt; ++c) {
-            if (w->st[c] != 0) continue;
+            if (w->st[c] != 0 || w->anorm[c] == 0.0) continue;     /* all-zero rows can never be added */
             double adx = w->Adx[c];
             const double rz = EPS_ROW * w->anorm[c] * dxmax;
             if (!isinf(w->lb_cur[c])) {
                 double rate = adx - w->dlb[c];
-                if (rate < -(EPS_RATE * (1.0 + fabs(adx) + fabs(w->dlb[c])) + rz)) {
-                    double sl = w->Ax[c] - w->lb_cur[c]; if (sl < 0) sl = 0;
+                double sl = w->Ax[c] - w->lb_cur[c]; if (sl < 0) sl = 0;
+                if (rate < -(EPS_RATE * (1.0 + fabs(adx) + fabs(w->dlb[c])) + rz) &&
+                    -rate - sl > FEAS_TOL * (1.0 + fabs(w->lb_new[c]))) {
                     double t = sl / (-rate);
                     if (t < tau) { tau = t; blk = c; blk_side = -1; }
                 }
             }
             if (!isinf(w->ub_cur[c])) {
                 double rate = w->dub[c] - adx;
-                if (rate < -(EPS_RATE * (1.0 + fabs(adx) + fabs(w->dub[c])) + rz)) {
-                    double sl = w->ub_cur[c] - w->Ax[c]; if (sl < 0) sl = 0;
+                double sl = w->ub_cur[c] - w->Ax[c]; if (sl < 0) sl = 0;
+                if (rate < -(EPS_RATE * (1.0 + fabs(adx) + fabs(w->dub[c])) + rz) &&
+                    -rate - sl > FEAS_TOL * (1.0 + fabs(w->ub_new[c]))) {
                     double t = sl / (-rate);
                     if (t < tau) { tau = t; blk = c; blk_side = 1; }
                 }
@@ -647,6 +654,7 @@ int orc_qpsolve(orc_qpws* w, const double* H, const double* g, const double* A,
         for (int k = 0; k < nA; ++k) {
             int c = w->widx[k];
             if (w->lb_new[c] == w->ub_new[c]) continue;          /* equality: never leaves */
+            if (w->tabu[c]) continue;                            /* no reversal inside a run of zero steps */
             double yc = w->y[c], dy = w->dyW[k];
             double thr = EPS_RATE * (1.0 + dys);
             if (w->st[c] < 0 && dy < -thr) {
@@ -658,6 +666,11 @@ int orc_qpsolve(orc_qpws* w, const double* H, const double* g, const double* A,
             }
         }
         if (blk >= 0) blk_dual = -1;
+        /* anti-cycling: constraints that enter while the homotopy makes no progress may not leave
+         * again through the dual test until it does (flat edges at degenerate vertices otherwise
+         * ping-pong between two equally optimal vertices) */
+        const int zero_step = !(tau > 1e-14);
+        if (!zero_step) memset(w->tabu, 0, (size_t)mt);
 
         /* take the step */
         for (int i = 0; i < n; ++i) { w->x[i] += tau * w->dx[i]; }
@@ -674,7 +687,7 @@ int orc_qpsolve(orc_qpws* w, const double* H, const double* g, const double* A,
         for (int i = 0; i < n; ++i) w->g_cur[i] += tau * w->dg[i];
         for (int c = 0; c < mt; ++c) { w->lb_cur[c] += tau * w->dlb[c]; w->ub_cur[c] += tau * w->dub[c]; }
         if (++iter > max_iter) { status = EEPACC_QP_MAXITER; break; }
-        if (dbg) fprintf(stderr, "it %d tau %.3e blk %d side %d dual %d (c=%d) nA %d\n", iter, tau, blk, blk_side, blk_dual, blk_dual >= 0 ? w->widx[blk_dual] : -1, w->nA);
+        if (dbg) fprintf(stderr, "it %d tau %.3e blk %d side %d dual %d (c=%d) nA %d dy %.3e dys %.3e y %.3e dxmax %.3e\n", iter, tau, blk, blk_side, blk_dual, blk_dual >= 0 ? w->widx[blk_dual] : -1, w->nA, blk_dual >= 0 ? w->dyW[blk_dual] : 0.0, dys, blk_dual >= 0 ? w->y[w->widx[blk_dual]] : 0.0, dxmax);
 
         if (blk >= 0) {
             /* ---------- primal blocking: add constraint blk ---------- */
@@ -682,6 +695,7 @@ int orc_qpsolve(orc_qpws* w, const double* H, const double* g, const double* A,
             get_row(w, blk, a);
             /* snap the value to the bound it hit */
             if (blk_side < 0) w->lb_cur[blk] = w->Ax[blk]; else w->ub_cur[blk] = w->Ax[blk];
+            if (zero_step) w->tabu[blk] = 1;
             if (add_constraint(w, blk, blk_side, a, 1) == 0) {
                 w->y[blk] = 0.0;
             } else {
@@ -739,7 +753,7 @@ int orc_qpsolve(orc_qpws* w, const double* H, const double* g, const double* A,
             const int side = w->st[c];
             w->y[c] = 0.0;
             remove_constraint(w, blk_dual);
-            int rc = resolve_pending(w, c, side, dbg);
+            int rc = resolve_pending(w, c, side, dbg, zero_step);
             if (rc) { status = rc; break; }
         }
     }
@@ -781,6 +795,8 @@ int orc_qpsolve(orc_qpws* w, const double* H, const double* g, const double* A,
     if (status == EEPACC_QP_OK) {
         for (int j = 0; j < n; ++j)
             if (w->st[m + j] != 0 && fabs(w->x[j]) >= FARB) status = EEPACC_QP_UNBOUNDED;
+        for (int c = 0; c < m; ++c)       /* an all-zero row with inconsistent bounds: infeasible QP */
+            if (w->anorm[c] == 0.0 && (w->lb_new[c] > 1e-8 || w->ub_new[c] < -1e-8)) status = EEPACC_QP_INFEASIBLE;
     }
     if (status != EEPACC_QP_OK) w->warm = 0;
     return status;
