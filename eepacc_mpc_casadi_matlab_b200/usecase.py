@@ -151,7 +151,7 @@ def perturbed_scenarios(B, base_v_2hz, seed=0xEE9ACC, highway_v_2hz=None, mass=F
             y *= _uniform(rng, 0.85, 1.15)
             delay = int(rng.integers(0, 21))
             if delay:
-                y = np.concatenate([np.zeros(delay), y[:-delay]])
+                y = np.concatenate([np.zeros(delay), y])[:n_steps]
             gap = _uniform(rng, 6.0, 30.0)
             for _ in range(3):
                 A, f, ph = _uniform(rng, 0, 0.3), _uniform(rng, 0.01, 0.1), _uniform(rng, 0, 2 * math.pi)
