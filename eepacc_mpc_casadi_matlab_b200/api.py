@@ -37,7 +37,7 @@ PLAIN_SYMBOLS = ["eepacc_qp_nvar", "eepacc_qp_ncon", "eepacc_mem_setup", "eepacc
                  "eepacc_mem_launch_count", "eepacc_mem_get_counters", "eepacc_mem_kpi_device_ptr",
                  "eepacc_sizeof_params", "eepacc_sizeof_route", "eepacc_last_error",
                  "eepacc_measure_dfma_peak", "eepacc_mem_debug_trace", "eepacc_mem_enable_timing",
-                 "eepacc_mem_get_timing"]
+                 "eepacc_mem_get_timing", "eepacc_mem_debug_phases"]
 
 
 class EepaccError(RuntimeError):
@@ -71,6 +71,7 @@ def load_library():
     L.eepacc_qp_ncon.argtypes = [C.c_int, C.POINTER(S.Params)]
     L.eepacc_mem_debug_trace.argtypes = [C.c_int, _dp, C.c_int]
     L.eepacc_mem_enable_timing.argtypes = [C.c_int, C.c_int]
+    L.eepacc_mem_debug_phases.argtypes = [C.c_int, _dp]
     L.eepacc_mem_get_timing.argtypes = [C.c_int, _dp, _dp, C.c_longlong]
     for f in FAMILIES:
         getattr(L, f).argtypes = [_dpp, _dpp, C.POINTER(C.c_longlong), _dp, C.c_int]
@@ -325,6 +326,11 @@ class Engine:
         out = np.zeros((cap, 4))
         self.L.eepacc_mem_debug_trace(self.mem, out.ctypes.data_as(_dp), cap)
         return out[out[:, 2] > 0]
+
+    def debug_phases(self):
+        out = np.zeros(8)
+        self.L.eepacc_mem_debug_phases(self.mem, out.ctypes.data_as(_dp))
+        return out
 
     def kpi_device_ptr(self):
         return self.L.eepacc_mem_kpi_device_ptr(self.mem)

@@ -57,7 +57,7 @@ struct Mem {
     double t0 = 0.0;
     long long n_lead = 0;
     DBuf routes, s_prev, v_prev, Fm_prev, Fb_prev, a_minus1, v_tv_meas, fbA, fbD, prev_sol, x0, dyn;
-    DBuf H, g, A, lba, uba;
+    DBuf g, lba, uba, sblk;     // closed loop is matrix-free: no dense H / A is ever stored
     DBuf wx, wy, widx, wside, wnA, warm, xsol, cost, status, iter, counters;
     DBuf kpi_acc, kpi, lead, lead_step, logrow, dbg;
     DBuf in[12], out[8];        // staging for host-pointer calls
@@ -67,7 +67,7 @@ struct Mem {
     void release_all()
     {
         DBuf* all[] = { &routes, &s_prev, &v_prev, &Fm_prev, &Fb_prev, &a_minus1, &v_tv_meas, &fbA, &fbD, &prev_sol,
-                        &x0, &dyn, &H, &g, &A, &lba, &uba, &wx, &wy, &widx, &wside, &wnA, &warm, &xsol, &cost,
+                        &x0, &dyn, &g, &lba, &uba, &sblk, &wx, &wy, &widx, &wside, &wnA, &warm, &xsol, &cost,
                         &status, &iter, &counters, &kpi_acc, &kpi, &lead, &lead_step, &logrow, &dbg };
         for (DBuf* b : all) b->release();
         for (auto& b : in) b.release();
@@ -114,7 +114,6 @@ int reset_state(Mem* M)
     CK(cudaMemsetAsync(M->wnA.p, 0, B * sizeof(int), M->stream));
     CK(cudaMemsetAsync(M->counters.p, 0, B * 4 * sizeof(unsigned long long), M->stream));
     CK(cudaMemsetAsync(M->kpi_acc.p, 0, B * ACC_W * 8, M->stream));
-    CK(cudaMemsetAsync(M->A.p, 0, (size_t)B * M->m * M->n * 8, M->stream));   // K2 writes structural non-zeros only
     // a_minus1 and the FB A/D rows start from their Settings.m / RunOpt_FBMPC.m:78-90 values
     std::vector<double> am1((size_t)B, M->p.a_minus1_init);
     CK(cudaMemcpyAsync(M->a_minus1.p, am1.data(), B * 8, cudaMemcpyHostToDevice, M->stream));
@@ -179,8 +178,9 @@ eep_build_io make_build_io(Mem* M, int mode)
     io.fbA = M->fbA.as<double>(); io.fbD = M->fbD.as<double>();
     io.prev_sol = M->prev_sol.as<double>();
     io.x0 = M->x0.as<double>();
-    io.H = M->H.as<double>(); io.g = M->g.as<double>(); io.A = M->A.as<double>();
+    io.H = nullptr; io.g = M->g.as<double>(); io.A = nullptr;
     io.lba = M->lba.as<double>(); io.uba = M->uba.as<double>();
+    io.sblk = M->sblk.as<double>();
     io.dyn = M->dyn.as<double>();
     return io;
 }
@@ -188,9 +188,10 @@ eep_qp_io make_qp_io(Mem* M)
 {
     eep_qp_io io;
     memset(&io, 0, sizeof io);
-    io.B = M->B; io.n = M->n; io.m = M->m;
-    io.H = M->H.as<double>(); io.g = M->g.as<double>(); io.A = M->A.as<double>();
+    io.B = M->B; io.n = M->n; io.m = M->m; io.ctrl = M->ctrl;
+    io.H = nullptr; io.g = M->g.as<double>(); io.A = nullptr;
     io.lba = M->lba.as<double>(); io.uba = M->uba.as<double>();
+    io.sblk = M->sblk.as<double>();
     io.wx = M->wx.as<double>(); io.wy = M->wy.as<double>();
     io.widx = M->widx.as<short>(); io.wside = M->wside.as<signed char>();
     io.wnA = M->wnA.as<int>(); io.warm = M->warm.as<int>();
@@ -218,7 +219,7 @@ int device_step(Mem* M, const double* lead_dev, double* log_dev)
     if (ev) CK(cudaEventRecord(ev[1], M->stream));
     if (rc) return fail(EEPACC_ERR_CUDA, "k2_build launch", (cudaError_t)rc);
     eep_qp_io qio = make_qp_io(M);
-    rc = eep_launch_qp(&qio, M->stream);
+    rc = eep_launch_qp(&M->p, &qio, M->stream);
     if (rc) return fail(EEPACC_ERR_CUDA, "k3_qp launch", (cudaError_t)rc);
     if (ev) CK(cudaEventRecord(ev[2], M->stream));
     eep_post_io pio;
@@ -318,7 +319,7 @@ int eepacc_mem_setup(int mem, int ctrl, const eepacc_params* p, const eepacc_rou
         { &M->Fb_prev, (size_t)B * 8 }, { &M->a_minus1, (size_t)B * 8 }, { &M->v_tv_meas, (size_t)B * 8 },
         { &M->fbA, (size_t)B * NH * 8 }, { &M->fbD, (size_t)B * NH * 8 },
         { &M->prev_sol, (size_t)B * 2 * (NH + 1) * 8 }, { &M->x0, (size_t)B * 2 * 8 }, { &M->dyn, (size_t)B * 2 * NH * 8 },
-        { &M->H, (size_t)B * n * n * 8 }, { &M->g, (size_t)B * n * 8 }, { &M->A, (size_t)B * m * n * 8 },
+        { &M->g, (size_t)B * n * 8 }, { &M->sblk, (size_t)B * EEP_SBLK * 8 },
         { &M->lba, (size_t)B * m * 8 }, { &M->uba, (size_t)B * m * 8 },
         { &M->wx, (size_t)B * n * 8 }, { &M->wy, (size_t)B * n * 8 }, { &M->widx, (size_t)B * n * 2 },
         { &M->wside, (size_t)B * n }, { &M->wnA, (size_t)B * 4 }, { &M->warm, (size_t)B * 4 },
@@ -412,6 +413,18 @@ void* eepacc_mem_kpi_device_ptr(int mem)
 
 double eepacc_measure_dfma_peak(int device) { return eep_dfma_peak(device); }
 
+/* Developer aid: clock64() cycles of vehicle 0's last solve by phase (needs eepacc_mem_debug_trace enabled):
+ * 0 load/norms, 1 warm QR, 2 refactor R, 3 aux-QP setup, 4 KKT step, 5 A*dx + ratio tests + step,
+ * 6 working-set change, 7 refinement + outputs. */
+int eepacc_mem_debug_phases(int mem, double* out)
+{
+    Mem* M = get_mem(mem);
+    if (!M || !M->ready || !M->dbg.p || !out) return fail(EEPACC_ERR_ARG, "tracing not enabled");
+    CK(cudaSetDevice(M->device));
+    CK(cudaMemcpy(out, (double*)M->dbg.p + 4096 * 4, 8 * 8, cudaMemcpyDeviceToHost));
+    return EEPACC_OK;
+}
+
 /* CUDA-event timing of the closed-loop kernels on the mem's stream.  enable: on = 1.
  * get: tot[4] = summed ms of k2_build, k3_qp, k4_post over the steps since the last reset and the
  * number of steps; step_ms[cap] = per-step latency (build start -> post end). */
@@ -449,8 +462,8 @@ int eepacc_mem_debug_trace(int mem, double* out, int cap)
     if (!M || !M->ready) return fail(EEPACC_ERR_ARG, "mem not set up");
     CK(cudaSetDevice(M->device));
     if (!M->dbg.p) {
-        if (M->dbg.ensure(4096 * 4 * 8)) return EEPACC_ERR_MEM;
-        CK(cudaMemset(M->dbg.p, 0, 4096 * 4 * 8));
+        if (M->dbg.ensure((4096 * 4 + 8) * 8)) return EEPACC_ERR_MEM;
+        CK(cudaMemset(M->dbg.p, 0, (4096 * 4 + 8) * 8));
         return EEPACC_OK;
     }
     if (out && cap > 0) {
@@ -609,6 +622,7 @@ static int eval_qpbuild(int ctrl, const double** arg, double** res, long long* i
         if (!o[k]) return fail(EEPACC_ERR_ARG, "missing output buffer");
     }
     io.H = o[0]; io.g = o[1]; io.A = o[2]; io.lba = o[3]; io.uba = o[4];
+    io.sblk = nullptr; io.dyn = nullptr;
     CK(cudaMemsetAsync(io.A, 0, cnt[2] * 8, M->stream));
     rc = eep_launch_build(&M->p, &io, M->stream);
     if (rc) return fail(EEPACC_ERR_CUDA, "k2_build launch", (cudaError_t)rc);
@@ -636,6 +650,7 @@ int eepacc_qpsolve(const double** arg, double** res, long long* iw, double*, int
     for (int k = 0; k < 7; ++k) if ((rc = stage_in(M, k, arg[k], icnt[k], c.dev, &in[k]))) return rc;
     for (int k = 0; k < 5; ++k) if (!in[k]) return fail(EEPACC_ERR_ARG, "h, g, a, lba, uba are required");
     io.H = in[0]; io.g = in[1]; io.A = in[2]; io.lba = in[3]; io.uba = in[4]; io.lbx = in[5]; io.ubx = in[6];
+    io.sblk = nullptr;          // dense conic operands: the generic operators
     /* arg[7..9] (x0, lam_x0, lam_a0) are accepted for scheme compatibility; the hot start lives in mem,
        exactly like the plugin's implicit qpOASES hot start. */
     const size_t ocnt[6] = { B * n, B, B * m, B * n, B, B };
@@ -647,7 +662,7 @@ int eepacc_qpsolve(const double** arg, double** res, long long* iw, double*, int
     io.lam_a = o[2]; io.lam_x = o[3];
     if (o[4]) io.status = o[4];
     if (o[5]) io.iter = o[5];
-    rc = eep_launch_qp(&io, M->stream);
+    rc = eep_launch_qp(&M->p, &io, M->stream);
     if (rc) return fail(EEPACC_ERR_CUDA, "k3_qp launch", (cudaError_t)rc);
     M->launches += 1;
     for (int k = 0; k < 6; ++k) if ((rc = copy_out(M, k, res[k], ocnt[k], c.dev))) return rc;

@@ -7,6 +7,22 @@
 #define EEPACC_MAX_NCON 522     // FB: 26*20+2
 #define EEPACC_LOG_W    12      // z1[8], a, status, iter, cost
 
+// Structured per-vehicle QP block written by K2 for K3's matrix-free path (doubles):
+//   PS/PV [(N+1) x N]  d s_k, v_k / d (driven control of stage i);  VEST [N] v_est(k);
+//   DC/CC [N x 3 x 3]  stage Hessian blocks on the core [v, driven controls] (D_k) and the coupling
+//                      with stage k-1 (C_k: rows stage k, cols stage k-1);  DG [N x 4] diagonal
+//                      curvature of the non-driven controls;  HMAX max|Hs|, HSCALE max|diag H|, MASS.
+#define EEP_SB_PS     0
+#define EEP_SB_PV     420
+#define EEP_SB_VEST   840
+#define EEP_SB_DC     860
+#define EEP_SB_CC     1040
+#define EEP_SB_DG     1220
+#define EEP_SB_HMAX   1300
+#define EEP_SB_HSCALE 1301
+#define EEP_SB_MASS   1302
+#define EEP_SBLK      1304
+
 // K2 (k2_build.cu)
 struct eep_build_io {
     long long B;
@@ -22,7 +38,8 @@ struct eep_build_io {
     const double *in_x0, *in_am1, *in_lead, *in_t0;
     // outputs
     double *x0;                 // [B][2] measured state
-    double *H, *g, *A, *lba, *uba;
+    double *H, *g, *A, *lba, *uba;   // H, A may be null (matrix-free closed loop)
+    double *sblk;               // [B][EEP_SBLK] structured block (may be null)
     double *dyn;                // [B][2][N] alpha_k, Dv_k for the post kernel (may be null)
 };
 
@@ -30,7 +47,9 @@ struct eep_build_io {
 struct eep_qp_io {
     long long B;
     int n, m;
-    const double *H, *g, *A, *lba, *uba, *lbx, *ubx;   // lbx/ubx may be null (= +-inf)
+    int ctrl;
+    const double *H, *g, *A, *lba, *uba, *lbx, *ubx;   // lbx/ubx may be null (= +-inf); H, A null in matrix-free mode
+    const double *sblk;         // [B][EEP_SBLK] structured block from K2: non-null selects the matrix-free operators
     // warm-start state (device, owned by the mem object)
     double *wx, *wy;            // [B][n]
     short *widx;                // [B][n]   constraint index per Q column
@@ -64,8 +83,8 @@ void eep_launch_power(const eepacc_params* p, long long B, int fifth, const doub
 void eep_launch_plant(const eepacc_params* p, long long B, const eepacc_route* routes, long long route_stride,
                       const double* x, const double* u, double* xn, cudaStream_t st);
 int eep_launch_build(const eepacc_params* p, const eep_build_io* io, cudaStream_t st);
-int eep_launch_qp(const eep_qp_io* io, cudaStream_t st);
-size_t eep_qp_smem_bytes(int n, int m);
+int eep_launch_qp(const eepacc_params* p, const eep_qp_io* io, cudaStream_t st);
+size_t eep_qp_smem_bytes(int n, int m, int smode);
 int eep_launch_post(const eepacc_params* p, const eep_post_io* io, cudaStream_t st);
 int eep_launch_kpi_final(const eepacc_params* p, long long B, int n_steps, const double* kpi_acc, double* kpi, cudaStream_t st);
 double eep_dfma_peak(int device);

@@ -14,19 +14,12 @@
 // g n, lba/uba m; closed-loop scalars as SoA arrays of length B.
 #include "eepacc_dev.cuh"
 #include "eepacc_kernels.h"
+#include "eepacc_rows.cuh"
 
 #define N EEP_N
 #define MAXW 7          // 1 + n_u (FB)
 #define NT_BUILD 128
 
-struct RowDesc {
-    double cS, cV;      // coefficients on s_k, v_k
-    int kst;            // stage of the state entries (-1: none)
-    int nctl;
-    int cj[4];          // dense column index of control entries
-    double cv[4];
-    double lb, ub;
-};
 
 struct BuildSmem {
     double s_est[N + 1], v_est[N + 1], s_tv_est[N + 1], v_tv_est[N + 1];
@@ -176,173 +169,6 @@ __device__ void bl_stage_cost(const eepacc_params& p, int tv, BuildSmem& S, int 
     }
     if (k + 1 < N) D[1 * W + 1] += 2 * w_j / (Ts * Ts);
     c[2] += w_f;                // :148
-}
-
-// ---- constraint rows ----
-__device__ __forceinline__ void rd_clear(RowDesc& r) { r.cS = 0; r.cV = 0; r.kst = -1; r.nctl = 0; r.lb = -INFINITY; r.ub = INFINITY; }
-__device__ __forceinline__ void rd_ctl(RowDesc& r, int j, double v) { r.cj[r.nctl] = j; r.cv[r.nctl] = v; r.nctl++; }
-
-// CreateQP_FB.m:310-473 (26 rows / stage) and :478-489 (2 terminal rows)
-__device__ void fb_row(const eepacc_params& p, double m, const BuildSmem& S, int c, RowDesc& r)
-{
-    rd_clear(r);
-    const double INF = INFINITY;
-    if (c >= 26 * N) {
-        r.kst = N; r.cS = 1;
-        if (c == 26 * N) { r.ub = S.s_tv_est[N - 1] - p.h_min; }
-        else { r.cV = p.tau_min; r.ub = S.s_tv_est[N - 1]; }
-        return;
-    }
-    const int k = c / 26, t = c % 26;
-    const int jFm = k * 6, jFb = jFm + 1, jxv = jFm + 2, jxh = jFm + 3, jxs = jFm + 4, jxf = jFm + 5;
-    const eep_stage_bounds& B = S.bnd[k];
-    const double lm = p.lambda * m, za = p.zeta_a, Tp = p.Ts;
-    const double zrg = S.zrg[k], ve = S.v_est[k], vv = ve * ve;
-    double sn, cn; sincos(B.slope, &sn, &cn);
-    switch (t) {
-    case 0: r.kst = k; r.cS = 1; r.lb = S.s_meas; r.ub = p.s_goal; break;                // s  (:311)
-    case 1: r.kst = k; r.cV = 1; r.lb = 0; r.ub = p.v_max; break;                        // v
-    case 2: rd_ctl(r, jFm, 1); r.lb = -1e4; r.ub = 1e4; break;                           // Fm
-    case 3: rd_ctl(r, jFb, 1); r.lb = -1e4; r.ub = 0; break;                             // Fb
-    case 4: rd_ctl(r, jxv, 1); r.lb = 0; break;
-    case 5: rd_ctl(r, jxh, 1); r.lb = 0; break;
-    case 6: rd_ctl(r, jxs, 1); r.lb = 0; break;
-    case 7: rd_ctl(r, jxf, 1); r.lb = 0; break;
-    case 8:  // torque limit, min (:359)
-        r.kst = k; r.cV = -p.phi * p.T_m_max * p.T_m_max / 4 / p.P_m_max;
-        rd_ctl(r, jFm, p.eta_TF / p.phi); rd_ctl(r, jxf, 1); r.lb = -p.T_m_max; break;
-    case 9:  // torque limit, max (:363)
-        r.kst = k; r.cV = p.phi * p.T_m_max * p.T_m_max / 4 / p.P_m_max;
-        rd_ctl(r, jFm, 1 / p.eta_TF / p.phi); rd_ctl(r, jxf, -1); r.ub = p.T_m_max; break;
-    case 10: { // rear wheel traction (:369-372)
-        double zw = m * p.g * (p.L_f * cn + p.h_g * sn);
-        rd_ctl(r, jFm, p.L / p.mu + p.h_g); rd_ctl(r, jFb, p.h_g); rd_ctl(r, jxf, 1);
-        r.lb = -zw + p.h_g * zrg; break; }
-    case 11: { // (:374-376)
-        double zw = m * p.g * (p.L_f * cn + p.h_g * sn);
-        rd_ctl(r, jFm, p.L / p.mu - p.h_g); rd_ctl(r, jFb, -p.h_g); rd_ctl(r, jxf, -1);
-        r.ub = zw - p.h_g * zrg; break; }
-    case 12: rd_ctl(r, jFm, 1); rd_ctl(r, jFb, 1); rd_ctl(r, jxf, -1); r.ub = p.mu * m * p.g * cn; break;   // (:380)
-    case 13: rd_ctl(r, jFm, 1); rd_ctl(r, jFb, 1); rd_ctl(r, jxf, 1); r.lb = -p.mu * m * p.g * cn; break;   // (:384)
-    case 14: rd_ctl(r, jFm, 1); rd_ctl(r, jFb, 1); rd_ctl(r, jxf, -1); r.ub = lm * B.a_max + za * vv + zrg; break;  // ISO a (:390)
-    case 15: rd_ctl(r, jFm, 1); rd_ctl(r, jFb, 1); rd_ctl(r, jxf, 1); r.lb = lm * B.a_min + za * vv + zrg; break;
-    case 16: case 17: {   // ISO jerk (:400-418)
-        double sg = (t == 16) ? -1.0 : 1.0;
-        if (k == 0) {
-            rd_ctl(r, jFm, 1); rd_ctl(r, jFb, 1); rd_ctl(r, jxf, sg);
-            double jb = (t == 16) ? B.j_max : B.j_min;
-            double val = lm * (Tp * jb + S.a_minus1) + za * vv + zrg;
-            if (t == 16) r.ub = val; else r.lb = val;
-        } else {
-            // 5 control entries: the previous-stage pair shares one coefficient, folded below
-            double dv2 = za * (vv - S.v_est[k - 1] * S.v_est[k - 1]);
-            double Dz = zrg - S.zrg[k - 1];
-            double jb = (t == 16) ? B.j_max : B.j_min;
-            double val = lm * Tp * jb + dv2 + Dz;
-            r.kst = -2;                       // marker: add -1 on (Fm,Fb) of stage k-1
-            rd_ctl(r, jFm, 1); rd_ctl(r, jFb, 1); rd_ctl(r, jxf, sg);
-            if (t == 16) r.ub = val; else r.lb = val;
-        }
-        break; }
-    case 18: r.kst = k; r.cV = 1; rd_ctl(r, jxf, -1); r.ub = B.v_lim; break;             // (:421)
-    case 19: r.kst = k; r.cV = 1; rd_ctl(r, jxf, -1); r.ub = B.v_curv; break;
-    case 20: r.kst = k; r.cV = 1; rd_ctl(r, jxs, -1); r.ub = B.v_stop; break;
-    case 21: r.kst = k; r.cV = 1; rd_ctl(r, jxs, -1); r.ub = B.v_tl; break;
-    case 22: r.kst = k; r.cV = 1; rd_ctl(r, jxv, 1); r.lb = fmin(B.v_lim, B.v_curv); break;   // (:445)
-    case 23: r.kst = k; r.cS = 1; rd_ctl(r, jxs, -1); r.ub = S.s_tv_est[k] - p.h_min; break;  // (:451)
-    case 24: r.kst = k; r.cS = 1; r.cV = p.tau_min; rd_ctl(r, jxs, -1); r.ub = S.s_tv_est[k]; break;
-    default: // 25: desired headway, Taylor form (:464-467)
-        r.kst = k; r.cS = 1; r.cV = p.T_hwp + 2 * p.G_hwp * ve; rd_ctl(r, jxh, -1);
-        r.ub = S.s_tv_est[k] - p.A_hwp + p.G_hwp * vv; break;
-    }
-    (void)INF;
-}
-
-// CreateQP_AB.m:237-371 (MC: 18 rows / stage, ABO: 14)
-__device__ void ab_row(const eepacc_params& p, const BuildSmem& S, int c, RowDesc& r)
-{
-    rd_clear(r);
-    const int rps = p.ab_route_rows ? 18 : 14;
-    if (c >= rps * N) {
-        r.kst = N; r.cS = 1;
-        if (c == rps * N) r.ub = S.s_tv_est[N - 1] - p.h_min;
-        else { r.cV = p.tau_min; r.ub = S.s_tv_est[N - 1]; }
-        return;
-    }
-    const int k = c / rps;
-    int t = c % rps;
-    if (!p.ab_route_rows && t >= 10) t += 4;       // skip the four route rows
-    const int ja = k * 5, jxv = ja + 1, jxh = ja + 2, jxs = ja + 3, jxf = ja + 4;
-    const eep_stage_bounds& B = S.bnd[k];
-    const double T = p.Ts;
-    switch (t) {
-    case 0: r.kst = k; r.cS = 1; r.lb = 0; r.ub = p.s_goal; break;
-    case 1: r.kst = k; r.cV = 1; r.lb = 0; r.ub = p.v_max; break;
-    case 2: rd_ctl(r, jxv, 1); r.lb = 0; break;
-    case 3: rd_ctl(r, jxh, 1); r.lb = 0; break;
-    case 4: rd_ctl(r, jxs, 1); r.lb = 0; break;
-    case 5: rd_ctl(r, jxf, 1); r.lb = 0; break;
-    case 6: rd_ctl(r, ja, 1); rd_ctl(r, jxf, -1); r.ub = B.a_max; break;                 // (:275)
-    case 7: rd_ctl(r, ja, 1); rd_ctl(r, jxf, 1); r.lb = B.a_min; break;
-    case 8: case 9: {                                                                    // (:285-305)
-        double sg = (t == 8) ? -1.0 : 1.0;
-        double jb = (t == 8) ? B.j_max : B.j_min;
-        rd_ctl(r, ja, 1); rd_ctl(r, jxf, sg);
-        double val;
-        if (k > 0) { r.kst = -2; val = T * jb; }
-        else val = T * jb + S.a_minus1;
-        if (t == 8) r.ub = val; else r.lb = val;
-        break; }
-    case 10: r.kst = k; r.cV = 1; rd_ctl(r, jxf, -1); r.ub = B.v_lim; break;             // MC :307-329
-    case 11: r.kst = k; r.cV = 1; rd_ctl(r, jxf, -1); r.ub = B.v_curv; break;
-    case 12: r.kst = k; r.cV = 1; rd_ctl(r, jxs, -1); r.ub = B.v_stop; break;
-    case 13: r.kst = k; r.cV = 1; rd_ctl(r, jxs, -1); r.ub = B.v_tl; break;
-    case 14: r.kst = k; r.cV = 1; rd_ctl(r, jxv, 1); r.lb = fmin(B.v_lim, B.v_curv); break;   // (:332)
-    case 15: r.kst = k; r.cS = 1; rd_ctl(r, jxs, -1); r.ub = S.s_tv_est[k] - p.h_min; break;
-    case 16: r.kst = k; r.cS = 1; r.cV = p.tau_min; rd_ctl(r, jxs, -1); r.ub = S.s_tv_est[k]; break;
-    default: // 17 (:348-354)
-        r.kst = k; r.cS = 1; r.cV = p.T_hwp + p.G_hwp * S.v_est[k]; rd_ctl(r, jxh, -1);
-        r.ub = S.s_tv_est[k] - p.A_hwp; break;
-    }
-}
-
-// CreateQP_BL.m:215-314 (13 rows / stage + 2) ; CreateQP_TV.m (11 rows / stage, 0.8x limits)
-__device__ void bl_row(const eepacc_params& p, int tv, const BuildSmem& S, int c, RowDesc& r)
-{
-    rd_clear(r);
-    const int rps = tv ? 11 : 13;
-    if (c >= rps * N) {
-        r.kst = N; r.cS = 1;
-        if (c == rps * N) r.ub = S.s_tv_est[N - 1] - p.h_min;
-        else { r.cV = p.tau_min; r.ub = S.s_tv_est[N - 1]; }
-        return;
-    }
-    const int k = c / rps, t = c % rps;
-    const int ja = k * 2, jxf = ja + 1;
-    const eep_stage_bounds& B = S.bnd[k];
-    const double Ts = p.Ts, sf = tv ? 0.8 : 1.0;
-    switch (t) {
-    case 0: r.kst = k; r.cS = 1; r.lb = 0; r.ub = p.s_goal; break;
-    case 1: r.kst = k; r.cV = 1; r.lb = 0; r.ub = p.v_max; break;
-    case 2: rd_ctl(r, jxf, 1); r.lb = 0; break;
-    case 3: rd_ctl(r, ja, 1); rd_ctl(r, jxf, 1); r.lb = B.a_min; break;                  // (:232)
-    case 4: rd_ctl(r, ja, 1); rd_ctl(r, jxf, -1); r.ub = B.a_max; break;
-    case 5: case 6: {                                                                    // (:242-262)
-        double sg = (t == 5) ? 1.0 : -1.0;
-        double jb = (t == 5) ? B.j_min : B.j_max;
-        rd_ctl(r, ja, 1); rd_ctl(r, jxf, sg);
-        double val;
-        if (k > 0) { r.kst = -2; val = Ts * jb; }
-        else val = Ts * jb + S.a_minus1;
-        if (t == 5) r.lb = val; else r.ub = val;
-        break; }
-    case 7: r.kst = k; r.cV = 1; rd_ctl(r, jxf, -1); r.ub = sf * B.v_lim; break;         // (:265)
-    case 8: r.kst = k; r.cV = 1; rd_ctl(r, jxf, -1); r.ub = sf * B.v_curv; break;
-    case 9: r.kst = k; r.cV = 1; rd_ctl(r, jxf, -1); r.ub = B.v_stop; break;
-    case 10: r.kst = k; r.cV = 1; rd_ctl(r, jxf, -1); r.ub = B.v_tl; break;
-    case 11: r.kst = k; r.cS = 1; rd_ctl(r, jxf, -1); r.ub = S.s_tv_est[k] - p.h_min; break;   // (:289)
-    default: r.kst = k; r.cS = 1; r.cV = p.tau_min; rd_ctl(r, jxf, -1); r.ub = S.s_tv_est[k]; break;
-    }
 }
 
 __global__ void __launch_bounds__(NT_BUILD) k2_build_kernel(eepacc_params p, eep_build_io io)
@@ -495,10 +321,8 @@ __global__ void __launch_bounds__(NT_BUILD) k2_build_kernel(eepacc_params p, eep
             S.MV[k][j] = v;
         }
         __syncthreads();
-        // ---------- H (n x n, column-major) and g ----------
-        double* Hout = io.H + veh * (long long)n * n;
-        for (int idx = tid; idx < n * n; idx += NT_BUILD) {
-            const int a = idx % n, j = idx / n;           // row a fastest: coalesced column-major store
+        // ---------- H (n x n, column-major; only when the dense conic operands are asked for) ----------
+        auto Hentry = [&](int a, int j) -> double {
             const int ka = a / nu, ca = a % nu;
             const int i = j / nu, cj = j % nu;
             const bool drvj = cj < nb;
@@ -518,7 +342,46 @@ __global__ void __launch_bounds__(NT_BUILD) k2_build_kernel(eepacc_params p, eep
                 for (int k = ka + 1; k < N; ++k) acc += S.PV[k][ka] * S.MV[k][j];
                 v += acc;
             }
-            Hout[idx] = v;
+            return v;
+        };
+        if (io.H) {
+            double* Hout = io.H + veh * (long long)n * n;
+            for (int idx = tid; idx < n * n; idx += NT_BUILD) Hout[idx] = Hentry(idx % n, idx / n);   // row fastest: coalesced
+        }
+        // ---------- structured block for the matrix-free solver path ----------
+        if (io.sblk) {
+            double* sb = io.sblk + veh * (long long)EEP_SBLK;
+            for (int e = tid; e < (N + 1) * N; e += NT_BUILD) {
+                sb[EEP_SB_PS + e] = S.PS[e / N][e % N];
+                sb[EEP_SB_PV + e] = S.PV[e / N][e % N];
+            }
+            const int nc = 1 + nb;                          // core = [v, driven controls]
+            for (int e = tid; e < N * 9; e += NT_BUILD) {
+                const int k = e / 9, a = (e % 9) / 3, b = e % 3;
+                const bool in = a < nc && b < nc;
+                sb[EEP_SB_DC + e] = in ? S.Dk[k][a * W + b] : 0.0;
+                sb[EEP_SB_CC + e] = in ? S.Ck[k][a * W + b] : 0.0;
+            }
+            for (int e = tid; e < N * 4; e += NT_BUILD) {
+                const int k = e / 4, c = nb + e % 4;        // non-driven control c: diagonal curvature only
+                sb[EEP_SB_DG + e] = (c < nu) ? S.Dk[k][(1 + c) * W + (1 + c)] : 0.0;
+            }
+            for (int k = tid; k < N; k += NT_BUILD) sb[EEP_SB_VEST + k] = (ctrl == EEPACC_TV) ? 0.0 : S.v_est[k];
+            // scale of H: max |diag(H)| and max |Hs| (zero Hessian <=> LP)
+            double hd = 0.0, hm = 0.0;
+            for (int a = tid; a < n; a += NT_BUILD) hd = fmax(hd, fabs(Hentry(a, a)));
+            for (int e = tid; e < N * W * W; e += NT_BUILD) {
+                const int k = e / (W * W), q = e % (W * W);
+                hm = fmax(hm, fmax(fabs(S.Dk[k][q]), fabs(S.Ck[k][q])));
+            }
+            __shared__ double red_hd[NT_BUILD / 32], red_hm[NT_BUILD / 32];
+            for (int o = 16; o > 0; o >>= 1) { hd = fmax(hd, __shfl_xor_sync(0xffffffffu, hd, o)); hm = fmax(hm, __shfl_xor_sync(0xffffffffu, hm, o)); }
+            if ((tid & 31) == 0) { red_hd[tid >> 5] = hd; red_hm[tid >> 5] = hm; }
+            __syncthreads();
+            if (tid == 0) {
+                for (int w = 1; w < NT_BUILD / 32; ++w) { hd = fmax(hd, red_hd[w]); hm = fmax(hm, red_hm[w]); }
+                sb[EEP_SB_HSCALE] = hd; sb[EEP_SB_HMAX] = hm; sb[EEP_SB_MASS] = mass;
+            }
         }
         double* gout = io.g + veh * (long long)n;
         for (int a = tid; a < n; a += NT_BUILD) {
@@ -534,27 +397,27 @@ __global__ void __launch_bounds__(NT_BUILD) k2_build_kernel(eepacc_params p, eep
             gout[a] = v;
         }
         // ---------- A (structural non-zeros only) and shifted bounds ----------
-        double* Aout = io.A + veh * (long long)m * n;
+        double* Aout = io.A ? io.A + veh * (long long)m * n : nullptr;
         double* lbo = io.lba + veh * (long long)m;
         double* ubo = io.uba + veh * (long long)m;
         for (int c = tid; c < m; c += NT_BUILD) {
             RowDesc rd;
-            if (ctrl == EEPACC_FB) fb_row(p, mass, S, c, rd);
-            else if (ctrl == EEPACC_AB) ab_row(p, S, c, rd);
-            else bl_row(p, ctrl == EEPACC_TV, S, c, rd);
+            eep_row<true>(ctrl, p, mass, S, c, rd);
             double gd = 0.0;
             if (rd.kst >= 0) {
                 const int k = rd.kst;
                 gd = rd.cS * S.ds[k] + rd.cV * S.dv[k];
-                for (int i = 0; i < k && i < N; ++i) {
+                if (Aout) for (int i = 0; i < k && i < N; ++i) {
                     double v = rd.cS * S.PS[k][i] + rd.cV * S.PV[k][i];
                     for (int cj = 0; cj < nb; ++cj) Aout[c + (long long)(i * nu + cj) * m] = v;
                 }
             }
-            for (int e = 0; e < rd.nctl; ++e) Aout[c + (long long)rd.cj[e] * m] = rd.cv[e];
-            if (rd.kst == -2) {      // jerk rows: -1 on the driven controls of the previous stage
-                const int kprev = rd.cj[0] / nu - 1;
-                for (int cj = 0; cj < nb; ++cj) Aout[c + (long long)(kprev * nu + cj) * m] = -1.0;
+            if (Aout) {
+                for (int e = 0; e < rd.nctl; ++e) Aout[c + (long long)rd.cj[e] * m] = rd.cv[e];
+                if (rd.kst == -2) {      // jerk rows: -1 on the driven controls of the previous stage
+                    const int kprev = rd.cj[0] / nu - 1;
+                    for (int cj = 0; cj < nb; ++cj) Aout[c + (long long)(kprev * nu + cj) * m] = -1.0;
+                }
             }
             lbo[c] = rd.lb - gd;
             ubo[c] = rd.ub - gd;

@@ -24,6 +24,7 @@
 // row per thread.  Working-set position arrays are indexed by the Q column r they own.
 #include "eepacc_dev.cuh"
 #include "eepacc_kernels.h"
+#include "eepacc_rows.cuh"
 
 #define NT 128
 #define FARB      1.0e6
@@ -45,7 +46,13 @@ struct Ctx {
     // shared
     double *Q, *M, *sub;
     double *x, *gcur, *dx, *dg, *t1, *t2, *t3, *t4, *yW, *dyW, *dbw, *wv, *csA, *snA;
-    double *Ax, *lbc, *ubc, *Adx, *anorm;
+    double *Ax, *lbc, *ubc, *Adx;
+    float* anorm;           // [mt] L1 norm of every row (only scales a noise threshold)
+    // matrix-free mode (closed loop): K2's structured block staged in shared memory
+    int smode, ctrl, nu, nb;
+    const eepacc_params* p;
+    double mass;
+    double *PS, *PV, *vest, *Dc, *Cc, *Dg, *sv, *vv, *drv, *yc;
     short* widx;            // [n] by Q column r
     signed char* st;        // [mt]
     signed char* tabu;      // [mt] anti-cycling flags
@@ -109,17 +116,102 @@ __device__ __forceinline__ void block_argmin(Ctx& C, double& t, int& key)
     }
 }
 
+struct VestSrc { const double* v_est; };
+
+// ---- matrix-free operators (closed loop): H = Psi' Hs Psi and A = Gs Psi are never formed ----
+// state sensitivities of a direction v: drv[i] = sum of the driven controls of stage i,
+// sv[k] = d s_k, vv[k] = d v_k  (k = 0..N)
+__device__ void s_prep(Ctx& C, const double* v)
+{
+    const int NH = EEP_N;
+    for (int i = threadIdx.x; i < NH; i += NT) {
+        double d = v[i * C.nu];
+        if (C.nb == 2) d += v[i * C.nu + 1];
+        C.drv[i] = d;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k <= NH; k += NT) {
+        double a = 0, b = 0;
+        for (int i = 0; i < k && i < NH; ++i) { a += C.PS[k * NH + i] * C.drv[i]; b += C.PV[k * NH + i] * C.drv[i]; }
+        C.sv[k] = a; C.vv[k] = b;
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void s_rowdesc(const Ctx& C, int c, RowDesc& rd)
+{
+    VestSrc src{ C.vest };
+    eep_row<false>(C.ctrl, *C.p, C.mass, src, c, rd);
+}
+// one entry A(c, j) of the dense constraint matrix
+__device__ __forceinline__ double s_entry(const Ctx& C, const RowDesc& rd, int j)
+{
+    const int NH = EEP_N;
+    const int i = j / C.nu, cj = j % C.nu;
+    double val = 0.0;
+    if (rd.kst >= 0 && cj < C.nb && i < rd.kst) val = rd.cS * C.PS[rd.kst * NH + i] + rd.cV * C.PV[rd.kst * NH + i];
+    for (int e = 0; e < rd.nctl; ++e) if (rd.cj[e] == j) val += rd.cv[e];
+    if (rd.kst == -2 && cj < C.nb && i == rd.cj[0] / C.nu - 1) val -= 1.0;
+    return val;
+}
+__device__ __forceinline__ double A_entry(const Ctx& C, int c, int j)
+{
+    if (!C.smode) return C.A[c + (size_t)j * C.m];
+    RowDesc rd;
+    s_rowdesc(C, c, rd);
+    return s_entry(C, rd, j);
+}
+
 // ---- dense primitives; every routine ends with data visible after a __syncthreads() ----
 __device__ void get_row(Ctx& C, int c, double* a)
 {
     const int n = C.n, m = C.m;
-    if (c < m) { for (int j = threadIdx.x; j < n; j += NT) a[j] = C.A[c + (size_t)j * m]; }
-    else { for (int j = threadIdx.x; j < n; j += NT) a[j] = (j == c - m) ? 1.0 : 0.0; }
+    if (c >= m) { for (int j = threadIdx.x; j < n; j += NT) a[j] = (j == c - m) ? 1.0 : 0.0; }
+    else if (C.smode) {
+        RowDesc rd;
+        s_rowdesc(C, c, rd);
+        for (int j = threadIdx.x; j < n; j += NT) a[j] = s_entry(C, rd, j);
+    } else { for (int j = threadIdx.x; j < n; j += NT) a[j] = C.A[c + (size_t)j * m]; }
     __syncthreads();
 }
 __device__ void Hmul(Ctx& C, const double* v, double* out)
 {
     const int n = C.n;
+    if (C.smode) {
+        const int NH = EEP_N, nu = C.nu, nb = C.nb;
+        s_prep(C, v);
+        // y_k on the core [v, driven]: D_k w_k + C_k w_{k-1} + C_{k+1}' w_{k+1}
+        for (int k = threadIdx.x; k < NH; k += NT) {
+            double w0[3] = { C.vv[k], v[k * nu], nb == 2 ? v[k * nu + 1] : 0.0 };
+            double y[3] = { 0, 0, 0 };
+            const double* D = C.Dc + k * 9;
+            for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) y[a] += D[a * 3 + b] * w0[b];
+            if (k > 0) {
+                double w1[3] = { C.vv[k - 1], v[(k - 1) * nu], nb == 2 ? v[(k - 1) * nu + 1] : 0.0 };
+                const double* Cm = C.Cc + k * 9;
+                for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) y[a] += Cm[a * 3 + b] * w1[b];
+            }
+            if (k + 1 < NH) {
+                double w2[3] = { C.vv[k + 1], v[(k + 1) * nu], nb == 2 ? v[(k + 1) * nu + 1] : 0.0 };
+                const double* Cp = C.Cc + (k + 1) * 9;
+                for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) y[a] += Cp[b * 3 + a] * w2[b];
+            }
+            C.yc[k * 3] = y[0]; C.yc[k * 3 + 1] = y[1]; C.yc[k * 3 + 2] = y[2];
+        }
+        __syncthreads();
+        for (int j = threadIdx.x; j < n; j += NT) {
+            const int i = j / nu, cj = j % nu;
+            double val;
+            if (cj < nb) {
+                val = C.yc[i * 3 + 1 + cj];
+                double acc = 0.0;
+                for (int k = i + 1; k < NH; ++k) acc += C.PV[k * NH + i] * C.yc[k * 3];
+                val += acc;
+            } else val = C.Dg[i * 4 + (cj - nb)] * v[j];
+            out[j] = val + C.reg * v[j];
+        }
+        __syncthreads();
+        return;
+    }
     for (int i = threadIdx.x; i < n; i += NT) {
         double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
         int j = 0;
@@ -137,6 +229,21 @@ __device__ void Hmul(Ctx& C, const double* v, double* out)
 __device__ void Amul(Ctx& C, const double* v, double* out)
 {
     const int n = C.n, m = C.m;
+    if (C.smode) {
+        s_prep(C, v);
+        for (int r = threadIdx.x; r < m; r += NT) {
+            RowDesc rd;
+            s_rowdesc(C, r, rd);
+            double val = 0.0;
+            if (rd.kst >= 0) val = rd.cS * C.sv[rd.kst] + rd.cV * C.vv[rd.kst];
+            for (int e = 0; e < rd.nctl; ++e) val += rd.cv[e] * v[rd.cj[e]];
+            if (rd.kst == -2) val -= C.drv[rd.cj[0] / C.nu - 1];
+            out[r] = val;
+        }
+        for (int j = threadIdx.x; j < n; j += NT) out[m + j] = v[j];
+        __syncthreads();
+        return;
+    }
     for (int r = threadIdx.x; r < m; r += NT) {
         double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
         int j = 0;
@@ -178,25 +285,61 @@ __device__ void Qmul(Ctx& C, const double* p, int c0, int c1, double* out, bool 
     }
     __syncthreads();
 }
-// solve M[lo:hi,lo:hi] x = b (back substitution); b is destroyed, x may not alias b
+// solve M[lo:hi,lo:hi] x = b (back substitution); b is destroyed, x may not alias b.
+// Blocks of 32 rows: one warp solves the diagonal block with shuffles (no block barrier inside),
+// then all threads fold the solved block into the remaining right-hand side.
 __device__ void usolve(Ctx& C, int lo, int hi, double* b, double* x)
 {
-    for (int r = hi - 1; r >= lo; --r) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int b1 = hi; b1 > lo; b1 -= 32) {
+        const int b0 = (b1 - 32 > lo) ? b1 - 32 : lo, nbk = b1 - b0;
         __syncthreads();
-        double xr = b[r] / MM(r, r);
-        for (int i = lo + threadIdx.x; i < r; i += NT) b[i] -= MM(i, r) * xr;
-        if (threadIdx.x == 0) x[r] = xr;
+        if (warp == 0) {
+            const int r = b0 + lane;
+            double acc = (lane < nbk) ? b[r] : 0.0;
+            const double inv = (lane < nbk) ? 1.0 / MM(r, r) : 0.0;
+            for (int t = nbk - 1; t >= 0; --t) {
+                const double xt = __shfl_sync(0xffffffffu, acc * inv, t);
+                if (lane < t) acc -= MM(r, b0 + t) * xt;
+                if (lane == t) x[r] = xt;
+            }
+        }
+        __syncthreads();
+        for (int i = lo + threadIdx.x; i < b0; i += NT) {
+            double s0 = 0, s1 = 0;
+            int c = b0;
+            for (; c + 1 < b1; c += 2) { s0 += MM(i, c) * x[c]; s1 += MM(i, c + 1) * x[c + 1]; }
+            if (c < b1) s0 += MM(i, c) * x[c];
+            b[i] -= s0 + s1;
+        }
     }
     __syncthreads();
 }
 // solve M[lo:hi,lo:hi]' y = v (forward substitution); v destroyed
 __device__ void tsolve(Ctx& C, int lo, int hi, double* v, double* y)
 {
-    for (int r = lo; r < hi; ++r) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int b0 = lo; b0 < hi; b0 += 32) {
+        const int b1 = (b0 + 32 < hi) ? b0 + 32 : hi, nbk = b1 - b0;
         __syncthreads();
-        double yr = v[r] / MM(r, r);
-        for (int i = r + 1 + threadIdx.x; i < hi; i += NT) v[i] -= MM(r, i) * yr;
-        if (threadIdx.x == 0) y[r] = yr;
+        if (warp == 0) {
+            const int r = b0 + lane;
+            double acc = (lane < nbk) ? v[r] : 0.0;
+            const double inv = (lane < nbk) ? 1.0 / MM(r, r) : 0.0;
+            for (int t = 0; t < nbk; ++t) {
+                const double yt = __shfl_sync(0xffffffffu, acc * inv, t);
+                if (lane > t && lane < nbk) acc -= MM(b0 + t, r) * yt;
+                if (lane == t) y[r] = yt;
+            }
+        }
+        __syncthreads();
+        for (int i = b1 + threadIdx.x; i < hi; i += NT) {
+            double s0 = 0, s1 = 0;
+            int c = b0;
+            for (; c + 1 < b1; c += 2) { s0 += MM(c, i) * y[c]; s1 += MM(c + 1, i) * y[c + 1]; }
+            if (c < b1) s0 += MM(c, i) * y[c];
+            v[i] -= s0 + s1;
+        }
     }
     __syncthreads();
 }
@@ -425,7 +568,7 @@ __device__ void reanchor(Ctx& C, bool recompute_y)
             double yc = C.yW[r];
             if (yc == 0.0) continue;
             int c = C.widx[r];
-            if (c < m) s += C.A[c + (size_t)j * m] * yc;
+            if (c < m) s += A_entry(C, c, j) * yc;
             else if (c - m == j) s += yc;
         }
         C.gcur[j] = s;
@@ -483,7 +626,7 @@ __device__ int resolve_pending(Ctx& C, int c_out, int side_out, unsigned long lo
         dn = sqrt(block_sum(C, dn));
         double tmin = INFINITY; int key = 0x7fffffff;
         for (int cc = threadIdx.x; cc < mt; cc += NT) {
-            if (C.st[cc] != 0 || C.anorm[cc] == 0.0) continue;
+            if (C.st[cc] != 0 || C.anorm[cc] == 0.0f) continue;
             double adx = C.Adx[cc];
             const double rz = EPS_ROW * C.anorm[cc] * dn;
             if (adx < -rz && !isinf(C.lbc[cc])) {
@@ -516,6 +659,182 @@ __device__ int resolve_pending(Ctx& C, int c_out, int side_out, unsigned long lo
     return 0;
 }
 
+// Warm start: rebuild  A_W Q = [0 T]  for the kept working set under the NEW constraint matrix.
+//   A_W' = Qh [Rh; 0]  =>  Q = Qh with reversed columns,  T(i, c) = Rh(n-1-c, i).
+// Most active rows are unit rows (slack / variable bounds, one entry): they are ordered first and
+// eliminated by coordinate swaps (Qh = P_0 .. P_{nU-1} diag(I, G2)), so the Householder QR and the
+// explicit formation of Qh only run on the few general rows in the remaining n - nU coordinates.
+// Rows whose new bound is infinite, or that became linearly dependent, are dropped (y = 0).
+__device__ void warm_setup(Ctx& C, int old_nA, const short* gidx, const signed char* gside, const double* gy)
+{
+    const int n = C.n, mt = C.mt, m = C.m;
+    for (int c = threadIdx.x; c < mt; c += NT) C.st[c] = 0;
+    short* cand = reinterpret_cast<short*>(C.wv);        // [n] constraint index per QR column
+    short* ucol = cand + n;                              // [n] unit rows: variable index (else -1)   (wv holds 4n shorts)
+    short* swp = cand + 2 * n;                           // [n] swap partner of unit column k
+    short* pos = cand + 3 * n;                           // [n] current row of coordinate j
+    double* ycand = C.dyW;                               // [n]
+    double* uval = C.t3;                                 // [n] coefficient of a unit row
+    double* v0a = C.csA;                                 // v0 of every reflector
+    double* beta = C.snA;                                // 2 / v'v
+    double* rdiag = C.sub;                               // Rh(k,k)
+    double* cn2 = C.dbw;                                 // squared norm of the original row
+    short* tmpc = reinterpret_cast<short*>(C.t1);        // classification scratch: [3n] shorts
+    double* tmpv = C.t2;
+    __syncthreads();
+    // 1. classify the stored working set in parallel (position k was stored at Q column n-1-k)
+    for (int k = threadIdx.x; k < old_nA; k += NT) {
+        const int r = n - 1 - k;
+        const int c = gidx[r], sd = gside[r];
+        const double bnd = sd < 0 ? lb_new(C, c) : ub_new(C, c);
+        int jv = -1; double cv = 0.0; int ok = !isinf(bnd);
+        if (ok) {
+            if (c >= m) { jv = c - m; cv = 1.0; }
+            else if (C.smode) {
+                RowDesc rd; s_rowdesc(C, c, rd);
+                if (rd.kst == -1 && rd.nctl == 1) { jv = rd.cj[0]; cv = rd.cv[0]; }
+            } else {
+                int nnz = 0, jl = -1; double vl = 0;
+                for (int j = 0; j < n; ++j) { double v = C.A[c + (size_t)j * m]; if (v != 0.0) { ++nnz; jl = j; vl = v; } }
+                if (nnz == 1) { jv = jl; cv = vl; }
+            }
+        }
+        tmpc[3 * k] = (short)(ok ? c : -1); tmpc[3 * k + 1] = (short)jv; tmpc[3 * k + 2] = (short)sd;
+        tmpv[k] = cv;
+    }
+    __syncthreads();
+    // thread 0: ordered list (unit rows first, relative order kept) and the swap plan
+    if (threadIdx.x == 0) {
+        int cnt = 0;
+        for (int j = 0; j < n; ++j) pos[j] = (short)j;
+        short* inv = reinterpret_cast<short*>(C.t4);      // row -> coordinate
+        for (int j = 0; j < n; ++j) inv[j] = (short)j;
+        for (int k = 0; k < old_nA; ++k) {
+            const int c = tmpc[3 * k], jv = tmpc[3 * k + 1];
+            if (c < 0 || jv < 0) continue;
+            const int a = pos[jv];
+            if (a < cnt) continue;                        // coordinate already pinned: dependent, drop
+            // swap rows a and cnt
+            const int jo = inv[cnt];
+            pos[jv] = (short)cnt; pos[jo] = (short)a; inv[cnt] = (short)jv; inv[a] = (short)jo;
+            cand[cnt] = (short)c; ucol[cnt] = (short)jv; swp[cnt] = (short)a; uval[cnt] = tmpv[k];
+            ycand[cnt] = gy[n - 1 - k]; C.st[c] = (signed char)tmpc[3 * k + 2];
+            ++cnt;
+        }
+        C.ired[5] = cnt;                                  // nU
+        for (int k = 0; k < old_nA; ++k) {
+            const int c = tmpc[3 * k], jv = tmpc[3 * k + 1];
+            if (c < 0 || jv >= 0) continue;
+            cand[cnt] = (short)c; ucol[cnt] = -1; ycand[cnt] = gy[n - 1 - k]; C.st[c] = (signed char)tmpc[3 * k + 2];
+            ++cnt;
+        }
+        C.ired[4] = cnt;
+    }
+    __syncthreads();
+    int cnt = C.ired[4];
+    const int nU = C.ired[5];
+    // 2. stage the general rows as columns nU.. of W (= Q storage), apply the coordinate swaps
+    for (int k = nU + threadIdx.x; k < cnt; k += NT) {
+        const int c = cand[k];
+        double s2 = 0;
+        if (C.smode) {
+            RowDesc rd;
+            s_rowdesc(C, c, rd);
+            for (int j = 0; j < n; ++j) { double v = s_entry(C, rd, j); MQ(j, k) = v; s2 += v * v; }
+        } else {
+            for (int j = 0; j < n; ++j) { double v = C.A[c + (size_t)j * m]; MQ(j, k) = v; s2 += v * v; }
+        }
+        cn2[k] = s2;
+        for (int u = 0; u < nU; ++u) { const int a = swp[u]; if (a != u) { double t = MQ(u, k); MQ(u, k) = MQ(a, k); MQ(a, k) = t; } }
+    }
+    for (int k = threadIdx.x; k < nU; k += NT) rdiag[k] = uval[k];
+    __syncthreads();
+    // 3. Householder QR of the general columns on rows >= nU; a dependent column is swapped with the last and dropped
+    int k = nU;
+    while (k < cnt) {
+        double s2 = 0;
+        for (int i = k + threadIdx.x; i < n; i += NT) s2 += MQ(i, k) * MQ(i, k);
+        s2 = block_sum(C, s2);
+        const double ref = cn2[k] > 1.0 ? cn2[k] : 1.0;
+        if (!(s2 > EPS_LI * EPS_LI * ref)) {
+            const int last = cnt - 1;
+            __syncthreads();
+            if (threadIdx.x == 0) C.st[cand[k]] = 0;
+            __syncthreads();
+            if (k != last) {
+                for (int i = threadIdx.x; i < n; i += NT) MQ(i, k) = MQ(i, last);
+                if (threadIdx.x == 0) { cand[k] = cand[last]; ycand[k] = ycand[last]; cn2[k] = cn2[last]; }
+            }
+            cnt = last;
+            __syncthreads();
+            continue;
+        }
+        const double sigma = sqrt(s2), x0 = MQ(k, k);
+        const double alpha = (x0 >= 0.0) ? -sigma : sigma;
+        const double v0 = x0 - alpha;
+        const double bt = 1.0 / (s2 - x0 * alpha);
+        for (int j = k + 1 + threadIdx.x; j < cnt; j += NT) {
+            double d = v0 * MQ(k, j), d1 = 0, d2 = 0, d3 = 0;
+            int i = k + 1;
+            for (; i + 3 < n; i += 4) {
+                d += MQ(i, k) * MQ(i, j); d1 += MQ(i + 1, k) * MQ(i + 1, j);
+                d2 += MQ(i + 2, k) * MQ(i + 2, j); d3 += MQ(i + 3, k) * MQ(i + 3, j);
+            }
+            for (; i < n; ++i) d += MQ(i, k) * MQ(i, j);
+            d = ((d + d1) + (d2 + d3)) * bt;
+            MQ(k, j) -= d * v0;
+            for (int i2 = k + 1; i2 < n; ++i2) MQ(i2, j) -= d * MQ(i2, k);
+        }
+        if (threadIdx.x == 0) { v0a[k] = v0; beta[k] = bt; rdiag[k] = alpha; }
+        __syncthreads();
+        ++k;
+    }
+    const int nA = cnt, nZ = n - nA;
+    // 4. T block of M from Rh:  M(r, c) = Rh(n-1-c, n-1-r),  c >= r >= nZ  (unit columns: diagonal only)
+    for (int r = nZ + threadIdx.x; r < n; r += NT) {
+        const int b = n - 1 - r;
+        for (int c = r; c < n; ++c) {
+            const int a = n - 1 - c;
+            MM(r, c) = (a == b) ? rdiag[a] : (b < nU ? 0.0 : MQ(a, b));
+        }
+    }
+    __syncthreads();
+    // 5. form Qh = P_0 .. P_{nU-1} diag(I, G2): backward accumulation of the reflectors, then the swaps
+    for (int j = threadIdx.x; j < n; j += NT)
+        if (j < nU || j >= nA) { for (int i = 0; i < n; ++i) MQ(i, j) = (i == j) ? 1.0 : 0.0; }
+    __syncthreads();
+    for (int kk = nA - 1; kk >= nU; --kk) {
+        const double v0 = v0a[kk], bt = beta[kk];
+        for (int j = kk + 1 + threadIdx.x; j < n; j += NT) {
+            double d = v0 * MQ(kk, j), d1 = 0, d2 = 0, d3 = 0;
+            int i = kk + 1;
+            for (; i + 3 < n; i += 4) {
+                d += MQ(i, kk) * MQ(i, j); d1 += MQ(i + 1, kk) * MQ(i + 1, j);
+                d2 += MQ(i + 2, kk) * MQ(i + 2, j); d3 += MQ(i + 3, kk) * MQ(i + 3, j);
+            }
+            for (; i < n; ++i) d += MQ(i, kk) * MQ(i, j);
+            d = ((d + d1) + (d2 + d3)) * bt;
+            MQ(kk, j) -= d * v0;
+            for (int i2 = kk + 1; i2 < n; ++i2) MQ(i2, j) -= d * MQ(i2, kk);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += NT) {
+            double vi = MQ(i, kk);
+            MQ(i, kk) = (i < kk) ? 0.0 : (i == kk) ? 1.0 - bt * v0 * v0 : -bt * v0 * vi;
+        }
+        __syncthreads();
+    }
+    for (int j = threadIdx.x; j < n; j += NT)
+        for (int u = nU - 1; u >= 0; --u) { const int a = swp[u]; if (a != u) { double t = MQ(u, j); MQ(u, j) = MQ(a, j); MQ(a, j) = t; } }
+    __syncthreads();
+    // 6. reverse the columns, 7. working-set bookkeeping by Q column
+    for (int i = threadIdx.x; i < n; i += NT)
+        for (int c = 0; c < n / 2; ++c) { double a = MQ(i, c), b = MQ(i, n - 1 - c); MQ(i, c) = b; MQ(i, n - 1 - c) = a; }
+    for (int kq = threadIdx.x; kq < nA; kq += NT) { C.yW[n - 1 - kq] = ycand[kq]; C.widx[n - 1 - kq] = cand[kq]; }
+    C.nA = nA;
+    __syncthreads();
+}
+
 __device__ void cold_ws(Ctx& C)
 {
     const int n = C.n, m = C.m, mt = C.mt;
@@ -536,7 +855,7 @@ __device__ void cold_ws(Ctx& C)
 
 extern __shared__ __align__(16) unsigned char k3_smem[];
 
-__global__ void __launch_bounds__(NT) k3_qp_kernel(eep_qp_io io)
+__global__ void __launch_bounds__(NT) k3_qp_kernel(const __grid_constant__ eepacc_params prm, eep_qp_io io)
 {
     Ctx C;
     const int n = io.n, m = io.m, mt = n + m;
@@ -550,28 +869,60 @@ __global__ void __launch_bounds__(NT) k3_qp_kernel(eep_qp_io io)
         C.t1 = p; p += n; C.t2 = p; p += n; C.t3 = p; p += n; C.t4 = p; p += n;
         C.yW = p; p += n; C.dyW = p; p += n; C.dbw = p; p += n; C.wv = p; p += n;
         C.csA = p; p += n + 1; C.snA = p; p += n + 1;
-        C.Ax = p; p += mt; C.lbc = p; p += mt; C.ubc = p; p += mt; C.Adx = p; p += mt; C.anorm = p; p += mt;
+        C.Ax = p; p += mt; C.lbc = p; p += mt; C.ubc = p; p += mt; C.Adx = p; p += mt;
+        C.anorm = reinterpret_cast<float*>(p); p += (mt + 1) / 2;
+        C.smode = io.sblk != nullptr; C.ctrl = io.ctrl; C.p = &prm;
+        C.nu = n / EEP_N; C.nb = (io.ctrl == EEPACC_FB) ? 2 : 1;
+        if (C.smode) {
+            const int NH = EEP_N;
+            C.PS = p; p += (NH + 1) * NH; C.PV = p; p += (NH + 1) * NH; C.vest = p; p += NH;
+            C.Dc = p; p += NH * 9; C.Cc = p; p += NH * 9; C.Dg = p; p += NH * 4;
+            C.sv = p; p += NH + 1; C.vv = p; p += NH + 1; C.drv = p; p += NH; C.yc = p; p += NH * 3;
+        }
         C.red = p; p += 8;
-        C.ired = reinterpret_cast<int*>(p); p += 4;
+        C.ired = reinterpret_cast<int*>(p); p += 4;      // 8 ints
         C.widx = reinterpret_cast<short*>(p); p += (n + 3) / 4 + 1;
         C.st = reinterpret_cast<signed char*>(p);
         C.tabu = C.st + mt;
     }
     for (long long veh = blockIdx.x; veh < io.B; veh += gridDim.x) {
         __syncthreads();
-        C.H = io.H + veh * (size_t)n * n;
+        C.H = io.H ? io.H + veh * (size_t)n * n : nullptr;
         C.g = io.g + veh * (size_t)n;
-        C.A = io.A + veh * (size_t)m * n;
+        C.A = io.A ? io.A + veh * (size_t)m * n : nullptr;
         C.lba = io.lba + veh * (size_t)m;
         C.uba = io.uba + veh * (size_t)m;
         C.lbx = io.lbx ? io.lbx + veh * (size_t)n : nullptr;
         C.ubx = io.ubx ? io.ubx + veh * (size_t)n : nullptr;
         int status = EEPACC_QP_OK, iter = 0;
         const int max_iter = 5 * (n + m);
+        long long ph[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }, tck = clock64();
+#define PHASE(i) do { long long t_ = clock64(); ph[i] += t_ - tck; tck = t_; } while (0)
         unsigned long long n_exch = 0, n_refac = 0;
 
-        // Hessian scale and LP regularisation
-        {
+        // Hessian scale, LP regularisation, row norms
+        if (C.smode) {
+            const double* sb = io.sblk + veh * (size_t)EEP_SBLK;
+            for (int e = threadIdx.x; e < (EEP_N + 1) * EEP_N; e += NT) { C.PS[e] = sb[EEP_SB_PS + e]; C.PV[e] = sb[EEP_SB_PV + e]; }
+            for (int e = threadIdx.x; e < EEP_N * 9; e += NT) { C.Dc[e] = sb[EEP_SB_DC + e]; C.Cc[e] = sb[EEP_SB_CC + e]; }
+            for (int e = threadIdx.x; e < EEP_N * 4; e += NT) C.Dg[e] = sb[EEP_SB_DG + e];
+            for (int e = threadIdx.x; e < EEP_N; e += NT) C.vest[e] = sb[EEP_SB_VEST + e];
+            C.reg = (sb[EEP_SB_HMAX] == 0.0) ? LP_REG : 0.0;
+            C.hscale = fmax(sb[EEP_SB_HSCALE], LP_REG);
+            C.mass = sb[EEP_SB_MASS];
+            __syncthreads();
+            for (int r = threadIdx.x; r < m; r += NT) {
+                RowDesc rd;
+                s_rowdesc(C, r, rd);
+                double sa = 0;
+                if (rd.kst >= 0)
+                    for (int i = 0; i < rd.kst && i < EEP_N; ++i)
+                        sa += C.nb * fabs(rd.cS * C.PS[rd.kst * EEP_N + i] + rd.cV * C.PV[rd.kst * EEP_N + i]);
+                for (int e = 0; e < rd.nctl; ++e) sa += fabs(rd.cv[e]);
+                if (rd.kst == -2) sa += C.nb;
+                C.anorm[r] = (float)sa;
+            }
+        } else {
             double hd = 0, hm = 0;
             for (int e = threadIdx.x; e < n * n; e += NT) { double v = fabs(C.H[e]); hm = fmax(hm, v); if (e % (n + 1) == 0) hd = fmax(hd, v); }
             hd = block_max(C, hd);
@@ -579,43 +930,26 @@ __global__ void __launch_bounds__(NT) k3_qp_kernel(eep_qp_io io)
             C.reg = (hm == 0.0) ? LP_REG : 0.0;
             C.hscale = fmax(hd, LP_REG);
             for (int r = threadIdx.x; r < m; r += NT) {
-                double s = 0;
-                for (int j = 0; j < n; ++j) s += fabs(C.A[r + (size_t)j * m]);
-                C.anorm[r] = s;
+                double sa = 0;
+                for (int j = 0; j < n; ++j) sa += fabs(C.A[r + (size_t)j * m]);
+                C.anorm[r] = (sa > 0.0 && sa < 1e-30) ? 1e-30f : (float)sa;
             }
-            for (int j = threadIdx.x; j < n; j += NT) C.anorm[m + j] = 1.0;
-            for (int c = threadIdx.x; c < mt; c += NT) C.tabu[c] = 0;
-            __syncthreads();
         }
+        for (int j = threadIdx.x; j < n; j += NT) C.anorm[m + j] = 1.0f;
+        for (int c = threadIdx.x; c < mt; c += NT) C.tabu[c] = 0;
+        __syncthreads();
 
+        PHASE(0);
         // ---------------- set-up ----------------
         const int was_warm = io.warm[veh];
         bool need_cold = !was_warm;
         for (int i = threadIdx.x; i < n; i += NT) C.x[i] = was_warm ? io.wx[veh * (size_t)n + i] : 0.0;
         if (!need_cold) {
-            const int old_nA = io.wnA[veh];
-            for (int c = threadIdx.x; c < mt; c += NT) C.st[c] = 0;
-            for (int e = threadIdx.x; e < n * C.ldq; e += NT) C.Q[e] = 0.0;
-            __syncthreads();
-            for (int v = threadIdx.x; v < n; v += NT) MQ(v, v) = 1.0;
-            C.nA = 0;
-            __syncthreads();
-            for (int k = 0; k < old_nA; ++k) {          // oldest first: stored column n-1-k
-                const int rold = n - 1 - k;
-                const int c = io.widx[veh * (size_t)n + rold];
-                const int s = io.wside[veh * (size_t)n + rold];
-                const double yv = io.wy[veh * (size_t)n + rold];
-                double bnd = s < 0 ? lb_new(C, c) : ub_new(C, c);
-                if (isinf(bnd)) continue;
-                get_row(C, c, C.t2);
-                const int nZ = n - C.nA;
-                if (givens_add(C, c, s, C.t2, nZ, 0, true) == 0) {
-                    if (threadIdx.x == 0) C.yW[nZ - 1] = yv;
-                }
-                __syncthreads();
-            }
+            warm_setup(C, io.wnA[veh], io.widx + veh * (size_t)n, io.wside + veh * (size_t)n, io.wy + veh * (size_t)n);
+            PHASE(1);
             n_refac++;
             if (refactor_R(C)) need_cold = true;
+            PHASE(2);
         }
         if (need_cold) cold_ws(C);
         Amul(C, C.x, C.Ax);
@@ -629,6 +963,7 @@ __global__ void __launch_bounds__(NT) k3_qp_kernel(eep_qp_io io)
         }
         __syncthreads();
         reanchor(C, false);
+        PHASE(3);
 
         // ---------------- homotopy ----------------
         for (;;) {
@@ -642,6 +977,7 @@ __global__ void __launch_bounds__(NT) k3_qp_kernel(eep_qp_io io)
             }
             __syncthreads();
             kkt_step(C, C.dg, C.dbw, C.dx, C.dyW);
+            PHASE(4);
             Amul(C, C.dx, C.Adx);
 
             double dxmax = 0;
@@ -649,7 +985,8 @@ __global__ void __launch_bounds__(NT) k3_qp_kernel(eep_qp_io io)
             dxmax = block_max(C, dxmax);
             double tau = 1.0; int key = 0x7fffffff;
             for (int c = threadIdx.x; c < mt; c += NT) {
-                if (C.st[c] != 0 || C.anorm[c] == 0.0) continue;      // all-zero rows can never be added
+                if (C.st[c] != 0 || C.anorm[c] == 0.0f) continue;      // all-zero rows can never be added
+                if (C.tabu[c] == 2) continue;                          // left during this run of zero steps: no re-entry
                 double adx = C.Adx[c];
                 const double rz = EPS_ROW * C.anorm[c] * dxmax;
                 if (!isinf(C.lbc[c])) {
@@ -684,7 +1021,7 @@ __global__ void __launch_bounds__(NT) k3_qp_kernel(eep_qp_io io)
             for (int r = nZ + threadIdx.x; r < n; r += NT) {
                 int c = C.widx[r];
                 if (lb_new(C, c) == ub_new(C, c)) continue;
-                if (C.tabu[c]) continue;                 // no reversal inside a run of zero-length steps
+                if (C.tabu[c] == 1) continue;            // entered during this run of zero steps: stays
                 double yc = C.yW[r], dy = C.dyW[r];
                 int k = 2 * mt + (n - 1 - r);
                 if (C.st[c] < 0 && dy < -thr) {
@@ -716,6 +1053,7 @@ __global__ void __launch_bounds__(NT) k3_qp_kernel(eep_qp_io io)
                 if (!isinf(un)) C.ubc[c] = full ? un : C.ubc[c] + tau * (un - C.ubc[c]);
             }
             __syncthreads();
+            PHASE(5);
             if (full) break;
             if (++iter > max_iter) { status = EEPACC_QP_MAXITER; break; }
             if (io.dbg && veh == 0 && threadIdx.x == 0 && iter <= io.dbg_cap) {
@@ -764,6 +1102,7 @@ __global__ void __launch_bounds__(NT) k3_qp_kernel(eep_qp_io io)
                         double l = (side < 0) ? C.t2[r] : -C.t2[r];
                         C.yW[r] -= theta * l;
                     }
+                    if (threadIdx.x == 0 && zero_step) C.tabu[C.widx[n - 1 - kk]] = 2;
                     __syncthreads();
                     remove_constraint(C, n - 1 - kk);
                     // new T row over the (unchanged-size) range space; R untouched
@@ -785,16 +1124,20 @@ __global__ void __launch_bounds__(NT) k3_qp_kernel(eep_qp_io io)
                 const int c = C.widx[rp];
                 const int side = C.st[c];
                 __syncthreads();
+                if (threadIdx.x == 0 && zero_step) C.tabu[c] = 2;
                 remove_constraint(C, rp);
                 int rc = resolve_pending(C, c, side, n_exch, zero_step);
                 if (rc) { status = rc; break; }
             }
+            PHASE(6);
         }
 
+        PHASE(6);
         // ---------------- iterative refinement on the final working set ----------------
         if (status == EEPACC_QP_OK) {
-            for (int pass = 0; pass < 2; ++pass) {
+            for (int pass = 0; pass < 1; ++pass) {
                 const int nZ = n - C.nA;
+                Amul(C, C.x, C.Adx);
                 Hmul(C, C.x, C.t4);
                 // rg = Hx + g - A_W' y ; rb = bound - a'x
                 for (int j = threadIdx.x; j < n; j += NT) {
@@ -802,17 +1145,14 @@ __global__ void __launch_bounds__(NT) k3_qp_kernel(eep_qp_io io)
                     for (int r = n - 1; r >= nZ; --r) {
                         double yc = C.yW[r];
                         int c = C.widx[r];
-                        if (c < m) s -= C.A[c + (size_t)j * m] * yc;
+                        if (c < m) s -= A_entry(C, c, j) * yc;
                         else if (c - m == j) s -= yc;
                     }
                     C.dg[j] = s;
                 }
                 for (int r = nZ + threadIdx.x; r < n; r += NT) {
-                    int c = C.widx[r];
-                    double ax = 0;
-                    if (c < m) { for (int j = 0; j < n; ++j) ax += C.A[c + (size_t)j * m] * C.x[j]; }
-                    else ax = C.x[c - m];
-                    C.dbw[r] = (C.st[c] < 0 ? C.lbc[c] : C.ubc[c]) - ax;
+                    const int c = C.widx[r];
+                    C.dbw[r] = (C.st[c] < 0 ? C.lbc[c] : C.ubc[c]) - C.Adx[c];
                 }
                 __syncthreads();
                 kkt_step(C, C.dg, C.dbw, C.dx, C.dyW);
@@ -860,6 +1200,8 @@ __global__ void __launch_bounds__(NT) k3_qp_kernel(eep_qp_io io)
                 io.iter[veh] = (double)iter;
                 io.wnA[veh] = C.nA;
                 io.warm[veh] = (status == EEPACC_QP_OK) ? 1 : 0;
+                PHASE(7);
+                if (io.dbg && veh == 0) for (int q = 0; q < 8; ++q) io.dbg[(size_t)io.dbg_cap * 4 + q] = (double)ph[q];
                 if (io.counters) {
                     io.counters[veh * 4 + 0] += (unsigned long long)iter;
                     io.counters[veh * 4 + 1] += (status != EEPACC_QP_OK);
@@ -871,27 +1213,27 @@ __global__ void __launch_bounds__(NT) k3_qp_kernel(eep_qp_io io)
     }
 }
 
-extern "C" size_t eep_qp_smem_bytes(int n, int m)
+extern "C" size_t eep_qp_smem_bytes(int n, int m, int smode)
 {
-    const int mt = n + m, ldq = n | 1;
+    const int mt = n + m, ldq = n | 1, NH = EEP_N;
     size_t d = (size_t)n * ldq + (size_t)n * (n + 1) / 2 + (n + 1) + 12 * (size_t)n + 2 * (size_t)(n + 1)
-             + 5 * (size_t)mt + 8 + 4 + ((n + 3) / 4 + 1);
+             + 4 * (size_t)mt + (mt + 1) / 2 + 8 + 4 + ((n + 3) / 4 + 1);
+    if (smode) d += 2 * (size_t)(NH + 1) * NH + NH + 2 * NH * 9 + NH * 4 + 2 * (NH + 1) + NH + NH * 3;
     return d * 8 + 2 * (size_t)mt + 16;
 }
 
-extern "C" int eep_launch_qp(const eep_qp_io* io, cudaStream_t st)
+extern "C" int eep_launch_qp(const eepacc_params* p, const eep_qp_io* io, cudaStream_t st)
 {
-    size_t sm = eep_qp_smem_bytes(io->n, io->m);
+    size_t sm = eep_qp_smem_bytes(io->n, io->m, io->sblk != nullptr);
     static size_t attr_for = 0;
     if (sm > attr_for) {
         cudaError_t e = cudaFuncSetAttribute(k3_qp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         if (e != cudaSuccess) return (int)e;
         attr_for = sm;
     }
-    long long g = io->B;
-    const long long cap = 148LL * 4;
-    if (g > cap) g = cap;
+    long long g = io->B;               // one CTA per vehicle: the hardware scheduler balances uneven solves
     if (g < 1) g = 1;
-    k3_qp_kernel<<<(int)g, NT, sm, st>>>(*io);
+    if (g > 2147483647LL) g = 2147483647LL;
+    k3_qp_kernel<<<(int)g, NT, sm, st>>>(*p, *io);
     return (int)cudaGetLastError();
 }

@@ -148,6 +148,8 @@ int eepacc_mem_get_timing(int mem, double* tot, double* step_ms, long long cap);
 /* Developer aid: first call enables a per-iteration solver trace for vehicle 0; later calls fetch
  * out[cap][4] = step length, ratio-test key, |working set|, exchanges of the last solve. */
 int eepacc_mem_debug_trace(int mem, double* out, int cap);
+/* clock64() cycles of vehicle 0's last solve by solver phase, out[8] (tracing must be enabled). */
+int eepacc_mem_debug_phases(int mem, double* out);
 /* FP64-FMA peak microbenchmark (register-resident DFMA chains); returns GFLOP/s or <0. */
 double eepacc_measure_dfma_peak(int device);
 

@@ -628,6 +628,7 @@ int orc_qpsolve(orc_qpws* w, const double* H, const double* g, const double* A,
         for (int i = 0; i < n; ++i) if (fabs(w->dx[i]) > dxmax) dxmax = fabs(w->dx[i]);
         for (int c = 0; c < mt; ++c) {
             if (w->st[c] != 0 || w->anorm[c] == 0.0) continue;     /* all-zero rows can never be added */
+            if (w->tabu[c] == 2) continue;                         /* left during this run of zero steps: no re-entry */
             double adx = w->Adx[c];
             const double rz = EPS_ROW * w->anorm[c] * dxmax;
             if (!isinf(w->lb_cur[c])) {
@@ -654,7 +655,7 @@ int orc_qpsolve(orc_qpws* w, const double* H, const double* g, const double* A,
         for (int k = 0; k < nA; ++k) {
             int c = w->widx[k];
             if (w->lb_new[c] == w->ub_new[c]) continue;          /* equality: never leaves */
-            if (w->tabu[c]) continue;                            /* no reversal inside a run of zero steps */
+            if (w->tabu[c] == 1) continue;                       /* entered during this run of zero steps: stays */
             double yc = w->y[c], dy = w->dyW[k];
             double thr = EPS_RATE * (1.0 + dys);
             if (w->st[c] < 0 && dy < -thr) {
@@ -733,6 +734,7 @@ int orc_qpsolve(orc_qpws* w, const double* H, const double* g, const double* A,
                 }
                 int cout_ = w->widx[kout];
                 w->y[cout_] = 0.0;
+                if (zero_step) w->tabu[cout_] = 2;
                 remove_constraint(w, kout);
                 {   /* new T row for blk over the (unchanged-size) range space; R untouched */
                     double* Tm = w->T;
@@ -752,6 +754,7 @@ int orc_qpsolve(orc_qpws* w, const double* H, const double* g, const double* A,
             const int c = w->widx[blk_dual];
             const int side = w->st[c];
             w->y[c] = 0.0;
+            if (zero_step) w->tabu[c] = 2;
             remove_constraint(w, blk_dual);
             int rc = resolve_pending(w, c, side, dbg, zero_step);
             if (rc) { status = rc; break; }
@@ -760,7 +763,7 @@ int orc_qpsolve(orc_qpws* w, const double* H, const double* g, const double* A,
 
     /* ---------------- iterative refinement on the final working set ---------------- */
     if (status == EEPACC_QP_OK) {
-        for (int pass = 0; pass < 2; ++pass) {
+        for (int pass = 0; pass < 1; ++pass) {
             const int nA = w->nA;
             double* hx = w->tmp1; double* a = w->tmp3;
             double rg[ORC_NMAX], rb[ORC_NMAX];
