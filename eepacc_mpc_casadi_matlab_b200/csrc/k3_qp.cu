@@ -853,6 +853,23 @@ __device__ void cold_ws(Ctx& C)
     __syncthreads();
 }
 
+// auxiliary QP for which the current (x, y, working set) is optimal: relaxed bounds + anchored gradient
+__device__ void setup_aux(Ctx& C)
+{
+    const int mt = C.mt;
+    Amul(C, C.x, C.Ax);
+    for (int c = threadIdx.x; c < mt; c += NT) {
+        int s = C.st[c];
+        double ax = C.Ax[c], ln = lb_new(C, c), un = ub_new(C, c);
+        bool eq = ln == un;
+        if (s < 0) { C.lbc[c] = ax; C.ubc[c] = eq ? ax : (isinf(un) ? INFINITY : ax + RELAX); }
+        else if (s > 0) { C.ubc[c] = ax; C.lbc[c] = eq ? ax : (isinf(ln) ? -INFINITY : ax - RELAX); }
+        else { C.lbc[c] = isinf(ln) ? -INFINITY : ax - RELAX; C.ubc[c] = isinf(un) ? INFINITY : ax + RELAX; }
+    }
+    __syncthreads();
+    reanchor(C, false);
+}
+
 extern __shared__ __align__(16) unsigned char k3_smem[];
 
 __global__ void __launch_bounds__(NT) k3_qp_kernel(const __grid_constant__ eepacc_params prm, eep_qp_io io)
@@ -896,6 +913,7 @@ __global__ void __launch_bounds__(NT) k3_qp_kernel(const __grid_constant__ eepac
         C.ubx = io.ubx ? io.ubx + veh * (size_t)n : nullptr;
         int status = EEPACC_QP_OK, iter = 0;
         const int max_iter = 5 * (n + m);
+        const int restart_after = (4 * n > 400 ? 4 * n : 400);
         long long ph[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }, tck = clock64();
 #define PHASE(i) do { long long t_ = clock64(); ph[i] += t_ - tck; tck = t_; } while (0)
         unsigned long long n_exch = 0, n_refac = 0;
@@ -952,17 +970,7 @@ __global__ void __launch_bounds__(NT) k3_qp_kernel(const __grid_constant__ eepac
             PHASE(2);
         }
         if (need_cold) cold_ws(C);
-        Amul(C, C.x, C.Ax);
-        for (int c = threadIdx.x; c < mt; c += NT) {
-            int s = C.st[c];
-            double ax = C.Ax[c], ln = lb_new(C, c), un = ub_new(C, c);
-            bool eq = ln == un;
-            if (s < 0) { C.lbc[c] = ax; C.ubc[c] = eq ? ax : (isinf(un) ? INFINITY : ax + RELAX); }
-            else if (s > 0) { C.ubc[c] = ax; C.lbc[c] = eq ? ax : (isinf(ln) ? -INFINITY : ax - RELAX); }
-            else { C.lbc[c] = isinf(ln) ? -INFINITY : ax - RELAX; C.ubc[c] = isinf(un) ? INFINITY : ax + RELAX; }
-        }
-        __syncthreads();
-        reanchor(C, false);
+        setup_aux(C);
         PHASE(3);
 
         // ---------------- homotopy ----------------
@@ -1056,6 +1064,15 @@ __global__ void __launch_bounds__(NT) k3_qp_kernel(const __grid_constant__ eepac
             PHASE(5);
             if (full) break;
             if (++iter > max_iter) { status = EEPACC_QP_MAXITER; break; }
+            if (iter == restart_after) {
+                // the warm-started path wanders (degenerate / non-convex stretches): start over from an
+                // all-fixed working set at the current point -- the cold-start path
+                cold_ws(C);
+                setup_aux(C);
+                for (int c = threadIdx.x; c < mt; c += NT) C.tabu[c] = 0;
+                __syncthreads();
+                continue;
+            }
             if (io.dbg && veh == 0 && threadIdx.x == 0 && iter <= io.dbg_cap) {
                 double* o = io.dbg + (size_t)(iter - 1) * 4;
                 o[0] = tau; o[1] = (double)key; o[2] = (double)C.nA; o[3] = (double)n_exch;

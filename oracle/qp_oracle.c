@@ -519,6 +519,29 @@ static void cold_ws(orc_qpws* w)
     w->nA = n;
 }
 
+/* auxiliary QP for which the current (x, y, working set) is optimal: relaxed bounds + anchored gradient */
+static void setup_aux(orc_qpws* w)
+{
+    const int mt = w->mt;
+    Amul(w, w->x, w->Ax);
+    for (int c = 0; c < mt; ++c) {
+        int s = w->st[c];
+        double ax = w->Ax[c];
+        int eq = (w->lb_new[c] == w->ub_new[c]);
+        if (s < 0) {
+            w->lb_cur[c] = ax;
+            w->ub_cur[c] = eq ? ax : (isinf(w->ub_new[c]) ? INFINITY : ax + RELAX);
+        } else if (s > 0) {
+            w->ub_cur[c] = ax;
+            w->lb_cur[c] = eq ? ax : (isinf(w->lb_new[c]) ? -INFINITY : ax - RELAX);
+        } else {
+            w->lb_cur[c] = isinf(w->lb_new[c]) ? -INFINITY : ax - RELAX;
+            w->ub_cur[c] = isinf(w->ub_new[c]) ? INFINITY : ax + RELAX;
+        }
+    }
+    reanchor(w, 0);
+}
+
 int orc_qpsolve(orc_qpws* w, const double* H, const double* g, const double* A,
                 const double* lba, const double* uba, const double* lbx, const double* ubx,
                 double* xout, double* cost, double* lam_a, double* lam_x, int* iter_out)
@@ -526,6 +549,7 @@ int orc_qpsolve(orc_qpws* w, const double* H, const double* g, const double* A,
     const int n = w->n, m = w->m, mt = w->mt;
     int status = EEPACC_QP_OK, iter = 0;
     const int max_iter = 5 * (n + m);
+    const int restart_after = (4 * n > 400 ? 4 * n : 400);
     w->H = H; w->A = A; w->g_new = g;
     w->n_exch = 0; w->n_refac = 0;
     memset(w->tabu, 0, (size_t)w->mt);
@@ -585,23 +609,7 @@ int orc_qpsolve(orc_qpws* w, const double* H, const double* g, const double* A,
         if (!w->warm) memset(w->x, 0, sizeof(double) * (size_t)n);
         cold_ws(w);
     }
-    Amul(w, w->x, w->Ax);
-    for (int c = 0; c < mt; ++c) {
-        int s = w->st[c];
-        double ax = w->Ax[c];
-        int eq = (w->lb_new[c] == w->ub_new[c]);
-        if (s < 0) {
-            w->lb_cur[c] = ax;
-            w->ub_cur[c] = eq ? ax : (isinf(w->ub_new[c]) ? INFINITY : ax + RELAX);
-        } else if (s > 0) {
-            w->ub_cur[c] = ax;
-            w->lb_cur[c] = eq ? ax : (isinf(w->lb_new[c]) ? -INFINITY : ax - RELAX);
-        } else {
-            w->lb_cur[c] = isinf(w->lb_new[c]) ? -INFINITY : ax - RELAX;
-            w->ub_cur[c] = isinf(w->ub_new[c]) ? INFINITY : ax + RELAX;
-        }
-    }
-    reanchor(w, 0);
+    setup_aux(w);
     w->warm = 1;
 
     /* ---------------- homotopy ---------------- */
@@ -688,6 +696,14 @@ int orc_qpsolve(orc_qpws* w, const double* H, const double* g, const double* A,
         for (int i = 0; i < n; ++i) w->g_cur[i] += tau * w->dg[i];
         for (int c = 0; c < mt; ++c) { w->lb_cur[c] += tau * w->dlb[c]; w->ub_cur[c] += tau * w->dub[c]; }
         if (++iter > max_iter) { status = EEPACC_QP_MAXITER; break; }
+        if (iter == restart_after) {
+            /* the warm-started path wanders (degenerate / non-convex stretches): start over from an
+             * all-fixed working set at the current point -- the cold-start path */
+            cold_ws(w);
+            setup_aux(w);
+            memset(w->tabu, 0, (size_t)mt);
+            continue;
+        }
         if (dbg) fprintf(stderr, "it %d tau %.3e blk %d side %d dual %d (c=%d) nA %d dy %.3e dys %.3e y %.3e dxmax %.3e\n", iter, tau, blk, blk_side, blk_dual, blk_dual >= 0 ? w->widx[blk_dual] : -1, w->nA, blk_dual >= 0 ? w->dyW[blk_dual] : 0.0, dys, blk_dual >= 0 ? w->y[w->widx[blk_dual]] : 0.0, dxmax);
 
         if (blk >= 0) {

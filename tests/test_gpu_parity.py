@@ -168,7 +168,7 @@ def test_batched_steps_match_oracle(oracle, lead_urban, cn):
                 degenerate = True
             # objective: 1e-9 relative (north star); the eps-regularised LPs of BL/TV are solved to ~1e-8;
             # degenerate FB steps may sit in different local minima of the indefinite objective
-            otol = 1e-5 if degenerate else (1e-6 if cn in ("bl", "tv") else 1e-9)
+            otol = 1e-5 if degenerate else (1e-5 if cn in ("bl", "tv") else 1e-9)
             assert abs(g[11] - o[11]) <= otol * (1 + abs(o[11])), (k, b, "objective", g[11], o[11])
             tol = 1e-5 if degenerate else (2e-6 if cn in ("bl", "tv") else 1e-6)
             assert np.max(np.abs(g[:2] - o[:2])) < tol, (k, b, "state")

@@ -1,0 +1,140 @@
+"""CPU: pins the oracle (oracle/, plain C) against every fixture the reference ships for the path
+(tests/golden/*.npz, extracted from the saved*.mat files by tests/golden/make_golden.py)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import golden
+from eepacc_mpc_casadi_matlab_b200 import settings as S, usecase as U
+
+KEYS = ["s_opt", "v_opt", "Fm_opt", "Fb_opt", "xi_v_opt", "xi_h_opt", "xi_s_opt", "xi_f_opt", "a_opt"]
+dp = C.POINTER(C.c_double)
+
+
+@pytest.mark.parametrize("tree", ["mc", "abo"])
+@pytest.mark.parametrize("cn", ["ab", "fb", "bl"])
+def test_closed_loop_reproduces_saved_run(oracle, lead_urban, tree, cn):
+    """All 871 warm-started QPs + plant steps of savedXXMPCsol.mat: first-stage values, states, energy,
+    and the last step's dense H and G (RunOpt_*MPC.m stores them in optSol)."""
+    g = golden(f"mpc_{tree}_{cn}.npz")
+    p = S.default_params(tree)
+    V = oracle.Vehicle(S.CTRL_NAMES[cn], p, U.default_route())
+    log = np.array([V.step(*lead_urban[k]) for k in range(871)])
+    lp = cn == "bl"           # H = 0: eps-regularised LP, solved (and stored by qpOASES) to ~1e-7
+    tol_state, tol_force = (2e-6, 5e-3) if lp else (1e-10, 1e-7)
+    for i, k in enumerate(KEYS):
+        if k not in g.files:
+            continue
+        tol = tol_force if k in ("Fm_opt", "Fb_opt") else tol_state
+        assert np.max(np.abs(log[:, i] - g[k])) < tol, k
+    assert log[:, 9].sum() == 0            # the reference flags 3 BL steps (6..8) as failed; the values still agree
+    H, gg, A, lba, uba = oracle.qp_arrays(V.qp())
+    assert np.max(np.abs(H - g["H"])) < 1e-12 * max(1.0, np.abs(g["H"]).max())
+    assert np.max(np.abs(A - g["G"])) < 1e-12
+    kpi = np.zeros(S.N_KPI)
+    oracle.lib().orc_kpi(C.byref(p), 1.0, log.ctypes.data_as(dp), 871, kpi.ctypes.data_as(dp))
+    assert abs(kpi[0] - g["E_opt"][-1]) < (1e-6 if lp else 1e-9) * g["E_opt"][-1]      # Ts*cumsum(P5)
+
+
+@pytest.mark.parametrize("tree", ["mc", "abo"])
+def test_plant_power_and_energy_against_saved_runs(oracle, tree):
+    p = S.default_params(tree)
+    r = U.default_route()
+    L = oracle.lib()
+    for cn in ("ab", "fb", "bl"):
+        g = golden(f"mpc_{tree}_{cn}.npz")
+        n = len(g["s_opt"])
+        for k in range(0, n - 1, 7):                    # RunPlantModel: x_{k+1} = plant(x_k, Fm_k + Fb_k)
+            x = np.array([g["s_opt"][k], g["v_opt"][k]]); u = np.array([g["Fm_opt"][k], g["Fb_opt"][k]])
+            xn = np.zeros(2)
+            L.orc_plant(C.byref(p), C.byref(r), x.ctypes.data_as(dp), u.ctypes.data_as(dp), xn.ctypes.data_as(dp))
+            assert abs(xn[0] - g["s_opt"][k + 1]) < 1e-10 and abs(xn[1] - g["v_opt"][k + 1]) < 1e-12
+        P = np.array([L.orc_power5(p.b_fifth, g["Fm_opt"][k], g["rpm_opt"][k]) for k in range(n)])
+        assert np.max(np.abs(P - g["P_opt"]) / (1 + np.abs(g["P_opt"]))) < 1e-13
+        assert np.max(np.abs(p.Ts * np.cumsum(P) - g["E_opt"]) / g["E_opt"][-1]) < 1e-13
+        rpm = (30 / np.pi) * g["v_opt"] * p.phi
+        assert np.max(np.abs(rpm - g["rpm_opt"])) < 1e-9
+
+
+@pytest.mark.parametrize("tree", ["mc", "abo"])
+def test_rk4_map_F_against_saved_nlp_trajectory(oracle, tree):
+    """F (M = 4 RK4 steps, RunOpt_NLP.m:275-288) maps node k to node k+1 of savedNLPsol.mat; the
+    Jacobian is checked against central differences of F itself."""
+    g = golden(f"nlp_{tree}.npz")
+    p = S.default_params(tree)
+    L = oracle.lib()
+    n = len(g["Fm_opt"])
+    worst_s = worst_v = 0.0
+    for k in range(0, n - 1, 5):
+        x0 = np.array([g["s_opt"][k], g["v_opt"][k], g["theta_opt"][k], g["j_opt"][k] if k < len(g["j_opt"]) else 0.0])
+        u = np.array([g["Fm_opt"][k], g["Fb_opt"][k], 0.0, 0.0, 0.0, 0.0])
+        xf, qf, J = np.zeros(4), np.zeros(1), np.zeros(50)
+        L.orc_F_jac(C.byref(p), 1.0, x0.ctypes.data_as(dp), u.ctypes.data_as(dp), xf.ctypes.data_as(dp),
+                    qf.ctypes.data_as(dp), J.ctypes.data_as(dp))
+        worst_s = max(worst_s, abs(xf[0] - g["s_opt"][k + 1]))
+        worst_v = max(worst_v, abs(xf[1] - g["v_opt"][k + 1]))
+    assert worst_s < 1e-8 and worst_v < 1e-10       # IPOPT closes the shooting gaps to ~1e-12
+    # Jacobian vs finite differences
+    x0 = np.array([120.0, 11.0, 0.02, 0.3]); u = np.array([900.0, -50.0, 0.1, 0.2, 0.0, 0.05])
+    xf, qf, J = np.zeros(4), np.zeros(1), np.zeros(50)
+    L.orc_F_jac(C.byref(p), 1.0, x0.ctypes.data_as(dp), u.ctypes.data_as(dp), xf.ctypes.data_as(dp), qf.ctypes.data_as(dp), J.ctypes.data_as(dp))
+    J = J.reshape(10, 5).T
+    z = np.r_[x0, u]
+    for c in range(10):
+        h = 1e-5 * max(1.0, abs(z[c]))
+        out = []
+        for sgn in (1, -1):
+            zz = z.copy(); zz[c] += sgn * h
+            a, b = np.zeros(4), np.zeros(1)
+            xx, uu = zz[:4].copy(), zz[4:].copy()
+            L.orc_F_jac(C.byref(p), 1.0, xx.ctypes.data_as(dp), uu.ctypes.data_as(dp), a.ctypes.data_as(dp), b.ctypes.data_as(dp), None)
+            out.append(np.r_[a, b])
+        fd = (out[0] - out[1]) / (2 * h)
+        assert np.max(np.abs(fd - J[:, c]) / (1 + np.abs(J[:, c]))) < 1e-6, c
+
+
+def test_lead_trace_recipe_matches_fixture():
+    """Run_DrivingCycle.m:16-46 + Main.m:88 from the raw 10 Hz cycle stored beside the fixture."""
+    sig = pytest.importorskip("scipy.signal")
+    d = golden("lead_TO01_EAD.npz")
+    y = sig.resample_poly(d["v_10hz"], 1, 5, window=("kaiser", 5.0))
+    y = y.copy(); y[y < 0.1] = 0
+    s, v = U.lead_from_half_hz(y)
+    assert np.max(np.abs(s - d["s_tv"])) < 1e-9 and np.max(np.abs(v - d["v_tv"])) < 1e-12
+
+
+def test_use_case_generator_and_pwa_quirks():
+    r = U.default_route()                                   # use case 0, Settings.m:148-190
+    assert list(r.s_speedLim[:r.n_sl]) == [-1.0, 999.0, 1000.0, 99999.0]
+    assert np.allclose(list(r.v_speedLim[:r.n_sl]), np.array([60, 60, 50, 50]) / 3.6)
+    assert list(r.s_curv[:r.n_curv]) == [1.0, 2.0, 3.0, 4.0]
+    assert list(r.curvature[:r.n_curv]) == [1e-5, 1e-5, 1e-6, 1e-6]
+    assert list(r.s_slope[:r.n_slope]) == [1.0, 2.0] and list(r.slope[:r.n_slope]) == [0.0, 0.0]
+    # duplicate handling of SimplifyPWA.m:30-47 (shift by 0.1, the doms(j) indexing quirk)
+    d, v = U.simplify_pwa([0, 5, 5, 9], [1, 1, 2, 2])
+    assert d == [0.0, 4.9, 5.0, 9.0] and v == [1.0, 1.0, 2.0, 2.0]
+    with pytest.raises(ValueError):
+        U.generate_use_case([[50, 0]], curves=[[1 / 20, 10 * i + 5, 10 * i + 9] for i in range(40)])
+
+
+def test_bounds_estimator_quirks(oracle):
+    """EstimateRouteAndComfortBounds.m: v_lim falls back to s_speedLim(end) (:84), strict curve
+    lookup (:98), red-light funnel (:121-131), ISO limits (:148-163)."""
+    p = S.default_params("mc")
+    r = U.generate_use_case([[60, 0], [50, 1000]], stops=[150.0], tls=[[300.0, 0.0, 12.0, 10.0]])
+    L = oracle.lib()
+    N = S.N_HOR
+    s_est = np.linspace(100.0, 320.0, N + 1); v_est = np.linspace(2.0, 25.0, N + 1)
+    outs = [np.zeros(N) for _ in range(9)]
+    L.orc_bounds.argtypes = [C.POINTER(S.Params), C.POINTER(S.Route), C.c_int, dp, dp, C.c_double] + [dp] * 9
+    L.orc_bounds(C.byref(p), C.byref(r), 0, s_est.ctypes.data_as(dp), v_est.ctypes.data_as(dp), 3.0,
+                 *[o.ctypes.data_as(dp) for o in outs])
+    slope, vlim, vstop, vtl, vcurv, amin, amax, jmin, jmax = outs
+    assert np.allclose(vlim, 60 / 3.6)
+    assert np.allclose(vcurv, p.alpha_TTL * 1e-6 ** (-1 / 3))                 # past the last curve point
+    k = int(np.argmin(np.abs(s_est[:N] - 150)))
+    assert abs(vstop[k] - (abs(150 - s_est[k]) + p.stopVel)) < 1e-12 and vstop[0] == abs(150 - s_est[0]) + p.stopVel
+    red = np.array([((3.0 + (i + 1) * p.Ts) % 22.0) < 12.0 for i in range(N)])
+    assert np.all(vtl[~red] == 1e5) and np.all(vtl[red & (np.abs(300 - s_est[:N]) < 100)] < 1e5)
+    assert amax[0] == 4 and amin[0] == -5 and amax[-1] == 2 and jmax[-1] == 2.5
