@@ -29,7 +29,7 @@ def build_library(force=False, verbose=False):
         src = os.path.join(CSRC, s)
         obj = os.path.join(objdir, s.replace(".cu", ".o"))
         if force or _stale(obj, [src] + hdrs):
-            cmd = [nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj]
+            cmd = [nvcc] + NVCC_FLAGS + (["-DEEP_K3_TIMERS"] if os.environ.get("EEP_K3_TIMERS") else []) + ["-c", src, "-o", obj]
             if verbose:
                 print(" ".join(cmd))
             subprocess.check_call(cmd)

@@ -415,13 +415,13 @@ double eepacc_measure_dfma_peak(int device) { return eep_dfma_peak(device); }
 
 /* Developer aid: clock64() cycles of vehicle 0's last solve by phase (needs eepacc_mem_debug_trace enabled):
  * 0 load/norms, 1 warm QR, 2 refactor R, 3 aux-QP setup, 4 KKT step, 5 A*dx + ratio tests + step,
- * 6 working-set change, 7 refinement + outputs. */
+ * 6 working-set change, 7 refinement + outputs; out[8..15] KKT-step sub-phases, out[16..19] ratio-test sub-phases. out[20]. */
 int eepacc_mem_debug_phases(int mem, double* out)
 {
     Mem* M = get_mem(mem);
     if (!M || !M->ready || !M->dbg.p || !out) return fail(EEPACC_ERR_ARG, "tracing not enabled");
     CK(cudaSetDevice(M->device));
-    CK(cudaMemcpy(out, (double*)M->dbg.p + 4096 * 4, 8 * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out, (double*)M->dbg.p + 4096 * 4, 20 * 8, cudaMemcpyDeviceToHost));
     return EEPACC_OK;
 }
 
@@ -462,8 +462,8 @@ int eepacc_mem_debug_trace(int mem, double* out, int cap)
     if (!M || !M->ready) return fail(EEPACC_ERR_ARG, "mem not set up");
     CK(cudaSetDevice(M->device));
     if (!M->dbg.p) {
-        if (M->dbg.ensure((4096 * 4 + 8) * 8)) return EEPACC_ERR_MEM;
-        CK(cudaMemset(M->dbg.p, 0, (4096 * 4 + 8) * 8));
+        if (M->dbg.ensure((4096 * 4 + 24) * 8)) return EEPACC_ERR_MEM;
+        CK(cudaMemset(M->dbg.p, 0, (4096 * 4 + 24) * 8));
         return EEPACC_OK;
     }
     if (out && cap > 0) {

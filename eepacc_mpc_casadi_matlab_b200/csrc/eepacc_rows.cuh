@@ -10,17 +10,28 @@
 #pragma once
 #include "eepacc_dev.cuh"
 
+// Plain scalar slots (no indexed arrays): the descriptor must live in registers -- K3 runs with the
+// maximum shared-memory carve-out, so anything that lands in local memory pays an L2 round trip.
 struct RowDesc {
     double cS, cV;      // coefficients on s_k, v_k
     int kst;            // stage of the state entries (-1: none, -2: none + "-1 on the driven controls of stage k-1")
-    int nctl;
-    int cj[4];          // dense column index of control entries
-    double cv[4];
+    int nctl;           // 1..3 control entries
+    int cj0, cj1, cj2;  // dense column index of control entries
+    double cv0, cv1, cv2;
     double lb, ub;
 };
 
-__device__ __forceinline__ void rd_clear(RowDesc& r) { r.cS = 0; r.cV = 0; r.kst = -1; r.nctl = 0; r.lb = -INFINITY; r.ub = INFINITY; }
-__device__ __forceinline__ void rd_ctl(RowDesc& r, int j, double v) { r.cj[r.nctl] = j; r.cv[r.nctl] = v; r.nctl++; }
+__device__ __forceinline__ void rd_clear(RowDesc& r)
+{
+    r.cS = 0; r.cV = 0; r.kst = -1; r.nctl = 0; r.lb = -INFINITY; r.ub = INFINITY;
+    r.cj0 = r.cj1 = r.cj2 = -1; r.cv0 = r.cv1 = r.cv2 = 0.0;
+}
+__device__ __forceinline__ void rd_ctl(RowDesc& r, int j, double v)          // first entry
+{ r.cj0 = j; r.cv0 = v; r.nctl = 1; }
+__device__ __forceinline__ void rd_ctl2(RowDesc& r, int j, double v)         // second entry
+{ r.cj1 = j; r.cv1 = v; r.nctl = 2; }
+__device__ __forceinline__ void rd_ctl3(RowDesc& r, int j, double v)         // third entry
+{ r.cj2 = j; r.cv2 = v; r.nctl = 3; }
 
 // CreateQP_FB.m:310-473 (26 rows / stage) and :478-489 (2 terminal rows)
 template <bool BOUNDS, class SRC>
@@ -48,16 +59,16 @@ __device__ void fb_row(const eepacc_params& p, double m, const SRC& S, int c, Ro
     case 7: rd_ctl(r, jxf, 1); if constexpr (BOUNDS) r.lb = 0; break;
     case 8:  // torque limit, min (:359)
         r.kst = k; r.cV = -p.phi * p.T_m_max * p.T_m_max / 4 / p.P_m_max;
-        rd_ctl(r, jFm, p.eta_TF / p.phi); rd_ctl(r, jxf, 1);
+        rd_ctl(r, jFm, p.eta_TF / p.phi); rd_ctl2(r, jxf, 1);
         if constexpr (BOUNDS) r.lb = -p.T_m_max;
         break;
     case 9:  // torque limit, max (:363)
         r.kst = k; r.cV = p.phi * p.T_m_max * p.T_m_max / 4 / p.P_m_max;
-        rd_ctl(r, jFm, 1 / p.eta_TF / p.phi); rd_ctl(r, jxf, -1);
+        rd_ctl(r, jFm, 1 / p.eta_TF / p.phi); rd_ctl2(r, jxf, -1);
         if constexpr (BOUNDS) r.ub = p.T_m_max;
         break;
     case 10: // rear wheel traction (:369-372)
-        rd_ctl(r, jFm, p.L / p.mu + p.h_g); rd_ctl(r, jFb, p.h_g); rd_ctl(r, jxf, 1);
+        rd_ctl(r, jFm, p.L / p.mu + p.h_g); rd_ctl2(r, jFb, p.h_g); rd_ctl3(r, jxf, 1);
         if constexpr (BOUNDS) {
             double sn, cn; sincos(S.bnd[k].slope, &sn, &cn);
             double zw = m * p.g * (p.L_f * cn + p.h_g * sn);
@@ -65,28 +76,28 @@ __device__ void fb_row(const eepacc_params& p, double m, const SRC& S, int c, Ro
         }
         break;
     case 11: // (:374-376)
-        rd_ctl(r, jFm, p.L / p.mu - p.h_g); rd_ctl(r, jFb, -p.h_g); rd_ctl(r, jxf, -1);
+        rd_ctl(r, jFm, p.L / p.mu - p.h_g); rd_ctl2(r, jFb, -p.h_g); rd_ctl3(r, jxf, -1);
         if constexpr (BOUNDS) {
             double sn, cn; sincos(S.bnd[k].slope, &sn, &cn);
             double zw = m * p.g * (p.L_f * cn + p.h_g * sn);
             r.ub = zw - p.h_g * S.zrg[k];
         }
         break;
-    case 12: rd_ctl(r, jFm, 1); rd_ctl(r, jFb, 1); rd_ctl(r, jxf, -1);                                         // (:380)
+    case 12: rd_ctl(r, jFm, 1); rd_ctl2(r, jFb, 1); rd_ctl3(r, jxf, -1);                                         // (:380)
         if constexpr (BOUNDS) { double sn, cn; sincos(S.bnd[k].slope, &sn, &cn); r.ub = p.mu * m * p.g * cn; }
         break;
-    case 13: rd_ctl(r, jFm, 1); rd_ctl(r, jFb, 1); rd_ctl(r, jxf, 1);                                          // (:384)
+    case 13: rd_ctl(r, jFm, 1); rd_ctl2(r, jFb, 1); rd_ctl3(r, jxf, 1);                                          // (:384)
         if constexpr (BOUNDS) { double sn, cn; sincos(S.bnd[k].slope, &sn, &cn); r.lb = -p.mu * m * p.g * cn; }
         break;
-    case 14: rd_ctl(r, jFm, 1); rd_ctl(r, jFb, 1); rd_ctl(r, jxf, -1);                                         // ISO a (:390)
+    case 14: rd_ctl(r, jFm, 1); rd_ctl2(r, jFb, 1); rd_ctl3(r, jxf, -1);                                         // ISO a (:390)
         if constexpr (BOUNDS) r.ub = p.lambda * m * S.bnd[k].a_max + p.zeta_a * ve * ve + S.zrg[k];
         break;
-    case 15: rd_ctl(r, jFm, 1); rd_ctl(r, jFb, 1); rd_ctl(r, jxf, 1);
+    case 15: rd_ctl(r, jFm, 1); rd_ctl2(r, jFb, 1); rd_ctl3(r, jxf, 1);
         if constexpr (BOUNDS) r.lb = p.lambda * m * S.bnd[k].a_min + p.zeta_a * ve * ve + S.zrg[k];
         break;
     case 16: case 17: {   // ISO jerk (:400-418)
         const double sg = (t == 16) ? -1.0 : 1.0;
-        rd_ctl(r, jFm, 1); rd_ctl(r, jFb, 1); rd_ctl(r, jxf, sg);
+        rd_ctl(r, jFm, 1); rd_ctl2(r, jFb, 1); rd_ctl3(r, jxf, sg);
         if (k > 0) r.kst = -2;                  // -1 on (Fm, Fb) of stage k-1
         if constexpr (BOUNDS) {
             const double lm = p.lambda * m, za = p.zeta_a, Tp = p.Ts, vv = ve * ve;
@@ -138,11 +149,11 @@ __device__ void ab_row(const eepacc_params& p, const SRC& S, int c, RowDesc& r)
     case 3: rd_ctl(r, jxh, 1); if constexpr (BOUNDS) r.lb = 0; break;
     case 4: rd_ctl(r, jxs, 1); if constexpr (BOUNDS) r.lb = 0; break;
     case 5: rd_ctl(r, jxf, 1); if constexpr (BOUNDS) r.lb = 0; break;
-    case 6: rd_ctl(r, ja, 1); rd_ctl(r, jxf, -1); if constexpr (BOUNDS) r.ub = S.bnd[k].a_max; break;          // (:275)
-    case 7: rd_ctl(r, ja, 1); rd_ctl(r, jxf, 1); if constexpr (BOUNDS) r.lb = S.bnd[k].a_min; break;
+    case 6: rd_ctl(r, ja, 1); rd_ctl2(r, jxf, -1); if constexpr (BOUNDS) r.ub = S.bnd[k].a_max; break;          // (:275)
+    case 7: rd_ctl(r, ja, 1); rd_ctl2(r, jxf, 1); if constexpr (BOUNDS) r.lb = S.bnd[k].a_min; break;
     case 8: case 9: {                                                                                          // (:285-305)
         const double sg = (t == 8) ? -1.0 : 1.0;
-        rd_ctl(r, ja, 1); rd_ctl(r, jxf, sg);
+        rd_ctl(r, ja, 1); rd_ctl2(r, jxf, sg);
         if (k > 0) r.kst = -2;
         if constexpr (BOUNDS) {
             const double jb = (t == 8) ? S.bnd[k].j_max : S.bnd[k].j_min;
@@ -186,11 +197,11 @@ __device__ void bl_row(const eepacc_params& p, int tv, const SRC& S, int c, RowD
     case 0: r.kst = k; r.cS = 1; if constexpr (BOUNDS) { r.lb = 0; r.ub = p.s_goal; } break;
     case 1: r.kst = k; r.cV = 1; if constexpr (BOUNDS) { r.lb = 0; r.ub = p.v_max; } break;
     case 2: rd_ctl(r, jxf, 1); if constexpr (BOUNDS) r.lb = 0; break;
-    case 3: rd_ctl(r, ja, 1); rd_ctl(r, jxf, 1); if constexpr (BOUNDS) r.lb = S.bnd[k].a_min; break;           // (:232)
-    case 4: rd_ctl(r, ja, 1); rd_ctl(r, jxf, -1); if constexpr (BOUNDS) r.ub = S.bnd[k].a_max; break;
+    case 3: rd_ctl(r, ja, 1); rd_ctl2(r, jxf, 1); if constexpr (BOUNDS) r.lb = S.bnd[k].a_min; break;           // (:232)
+    case 4: rd_ctl(r, ja, 1); rd_ctl2(r, jxf, -1); if constexpr (BOUNDS) r.ub = S.bnd[k].a_max; break;
     case 5: case 6: {                                                                                          // (:242-262)
         const double sg = (t == 5) ? 1.0 : -1.0;
-        rd_ctl(r, ja, 1); rd_ctl(r, jxf, sg);
+        rd_ctl(r, ja, 1); rd_ctl2(r, jxf, sg);
         if (k > 0) r.kst = -2;
         if constexpr (BOUNDS) {
             const double jb = (t == 5) ? S.bnd[k].j_min : S.bnd[k].j_max;

@@ -413,9 +413,11 @@ __global__ void __launch_bounds__(NT_BUILD) k2_build_kernel(eepacc_params p, eep
                 }
             }
             if (Aout) {
-                for (int e = 0; e < rd.nctl; ++e) Aout[c + (long long)rd.cj[e] * m] = rd.cv[e];
+                if (rd.nctl > 0) Aout[c + (long long)rd.cj0 * m] = rd.cv0;
+                if (rd.nctl > 1) Aout[c + (long long)rd.cj1 * m] = rd.cv1;
+                if (rd.nctl > 2) Aout[c + (long long)rd.cj2 * m] = rd.cv2;
                 if (rd.kst == -2) {      // jerk rows: -1 on the driven controls of the previous stage
-                    const int kprev = rd.cj[0] / nu - 1;
+                    const int kprev = rd.cj0 / nu - 1;
                     for (int cj = 0; cj < nb; ++cj) Aout[c + (long long)(kprev * nu + cj) * m] = -1.0;
                 }
             }

@@ -149,8 +149,10 @@ __device__ __forceinline__ double s_entry(const Ctx& C, const RowDesc& rd, int j
     const int i = j / C.nu, cj = j % C.nu;
     double val = 0.0;
     if (rd.kst >= 0 && cj < C.nb && i < rd.kst) val = rd.cS * C.PS[rd.kst * NH + i] + rd.cV * C.PV[rd.kst * NH + i];
-    for (int e = 0; e < rd.nctl; ++e) if (rd.cj[e] == j) val += rd.cv[e];
-    if (rd.kst == -2 && cj < C.nb && i == rd.cj[0] / C.nu - 1) val -= 1.0;
+    if (rd.cj0 == j) val += rd.cv0;
+    if (rd.cj1 == j) val += rd.cv1;
+    if (rd.cj2 == j) val += rd.cv2;
+    if (rd.kst == -2 && cj < C.nb && i == rd.cj0 / C.nu - 1) val -= 1.0;
     return val;
 }
 __device__ __forceinline__ double A_entry(const Ctx& C, int c, int j)
@@ -236,8 +238,10 @@ __device__ void Amul(Ctx& C, const double* v, double* out)
             s_rowdesc(C, r, rd);
             double val = 0.0;
             if (rd.kst >= 0) val = rd.cS * C.sv[rd.kst] + rd.cV * C.vv[rd.kst];
-            for (int e = 0; e < rd.nctl; ++e) val += rd.cv[e] * v[rd.cj[e]];
-            if (rd.kst == -2) val -= C.drv[rd.cj[0] / C.nu - 1];
+            if (rd.nctl > 0) val += rd.cv0 * v[rd.cj0];
+            if (rd.nctl > 1) val += rd.cv1 * v[rd.cj1];
+            if (rd.nctl > 2) val += rd.cv2 * v[rd.cj2];
+            if (rd.kst == -2) val -= C.drv[rd.cj0 / C.nu - 1];
             out[r] = val;
         }
         for (int j = threadIdx.x; j < n; j += NT) out[m + j] = v[j];
@@ -507,15 +511,19 @@ __device__ int refactor_R(Ctx& C)
 }
 
 // KKT step: H dx + dg = A_W' dy,  A_W dx = db   (db, dy indexed by Q column)
-__device__ void kkt_step(Ctx& C, const double* dg, const double* dbw, double* dx, double* dyW)
+__device__ void kkt_step(Ctx& C, const double* dg, const double* dbw, double* dx, double* dyW, long long* kp = nullptr)
 {
+    long long tk = clock64();
+#define KPH(i) do { if (kp) { long long t_ = clock64(); kp[i] += t_ - tk; tk = t_; } } while (0)
     const int n = C.n, nZ = n - C.nA;
     double *p = C.t1, *u = C.t2, *t = C.t3;
     if (C.nA > 0) {
         for (int r = nZ + threadIdx.x; r < n; r += NT) t[r] = dbw[r];
         __syncthreads();
         usolve(C, nZ, n, t, p);
+        KPH(0);
         Qmul(C, p, nZ, n, dx, false);
+        KPH(1);
     } else {
         for (int i = threadIdx.x; i < n; i += NT) dx[i] = 0.0;
         __syncthreads();
@@ -523,22 +531,29 @@ __device__ void kkt_step(Ctx& C, const double* dg, const double* dbw, double* dx
     Hmul(C, dx, u);
     for (int i = threadIdx.x; i < n; i += NT) u[i] += dg[i];
     __syncthreads();
+    KPH(2);
     if (nZ > 0) {
         Qtmul(C, u, t, 0, nZ);
         for (int j = threadIdx.x; j < nZ; j += NT) t[j] = -t[j];
         __syncthreads();
+        KPH(3);
         tsolve(C, 0, nZ, t, p);
         usolve(C, 0, nZ, p, t);
+        KPH(4);
         Qmul(C, t, 0, nZ, p, false);            // p = Z q
         for (int i = threadIdx.x; i < n; i += NT) dx[i] += p[i];
         __syncthreads();
+        KPH(5);
         Hmul(C, p, t);
         for (int i = threadIdx.x; i < n; i += NT) u[i] += t[i];
         __syncthreads();
+        KPH(2);
     }
     if (C.nA > 0) {
         Qtmul(C, u, t, nZ, n);
+        KPH(6);
         tsolve(C, nZ, n, t, dyW);
+        KPH(7);
     }
 }
 
@@ -692,7 +707,7 @@ __device__ void warm_setup(Ctx& C, int old_nA, const short* gidx, const signed c
             if (c >= m) { jv = c - m; cv = 1.0; }
             else if (C.smode) {
                 RowDesc rd; s_rowdesc(C, c, rd);
-                if (rd.kst == -1 && rd.nctl == 1) { jv = rd.cj[0]; cv = rd.cv[0]; }
+                if (rd.kst == -1 && rd.nctl == 1) { jv = rd.cj0; cv = rd.cv0; }
             } else {
                 int nnz = 0, jl = -1; double vl = 0;
                 for (int j = 0; j < n; ++j) { double v = C.A[c + (size_t)j * m]; if (v != 0.0) { ++nnz; jl = j; vl = v; } }
@@ -872,7 +887,7 @@ __device__ void setup_aux(Ctx& C)
 
 extern __shared__ __align__(16) unsigned char k3_smem[];
 
-__global__ void __launch_bounds__(NT) k3_qp_kernel(const __grid_constant__ eepacc_params prm, eep_qp_io io)
+__global__ void __launch_bounds__(NT, 1) k3_qp_kernel(const __grid_constant__ eepacc_params prm, eep_qp_io io)
 {
     Ctx C;
     const int n = io.n, m = io.m, mt = n + m;
@@ -914,8 +929,17 @@ __global__ void __launch_bounds__(NT) k3_qp_kernel(const __grid_constant__ eepac
         int status = EEPACC_QP_OK, iter = 0;
         const int max_iter = 5 * (n + m);
         const int restart_after = (4 * n > 400 ? 4 * n : 400);
+#ifdef EEP_K3_TIMERS
         long long ph[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }, tck = clock64();
+        long long kph[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }, rph[4] = { 0, 0, 0, 0 };
 #define PHASE(i) do { long long t_ = clock64(); ph[i] += t_ - tck; tck = t_; } while (0)
+#define KPHP kph
+#define RPH(i) do { rph[i] += clock64() - tr; tr = clock64(); } while (0)
+#else
+#define PHASE(i) do { } while (0)
+#define KPHP nullptr
+#define RPH(i) do { } while (0)
+#endif
         unsigned long long n_exch = 0, n_refac = 0;
 
         // Hessian scale, LP regularisation, row norms
@@ -936,7 +960,7 @@ __global__ void __launch_bounds__(NT) k3_qp_kernel(const __grid_constant__ eepac
                 if (rd.kst >= 0)
                     for (int i = 0; i < rd.kst && i < EEP_N; ++i)
                         sa += C.nb * fabs(rd.cS * C.PS[rd.kst * EEP_N + i] + rd.cV * C.PV[rd.kst * EEP_N + i]);
-                for (int e = 0; e < rd.nctl; ++e) sa += fabs(rd.cv[e]);
+                sa += fabs(rd.cv0) + fabs(rd.cv1) + fabs(rd.cv2);
                 if (rd.kst == -2) sa += C.nb;
                 C.anorm[r] = (float)sa;
             }
@@ -984,9 +1008,13 @@ __global__ void __launch_bounds__(NT) k3_qp_kernel(const __grid_constant__ eepac
                 C.dbw[r] = isinf(nb) ? 0.0 : nb - cb;
             }
             __syncthreads();
-            kkt_step(C, C.dg, C.dbw, C.dx, C.dyW);
+            kkt_step(C, C.dg, C.dbw, C.dx, C.dyW, KPHP);
             PHASE(4);
+#ifdef EEP_K3_TIMERS
+            long long tr = clock64();
+#endif
             Amul(C, C.dx, C.Adx);
+            RPH(0);
 
             double dxmax = 0;
             for (int i = threadIdx.x; i < n; i += NT) dxmax = fmax(dxmax, fabs(C.dx[i]));
@@ -1041,6 +1069,7 @@ __global__ void __launch_bounds__(NT) k3_qp_kernel(const __grid_constant__ eepac
                 }
             }
             block_argmin(C, tau, key);
+            RPH(1);
             const bool full = !(tau < 1.0) || key == 0x7fffffff;
             if (full) tau = 1.0;
             // anti-cycling (see oracle/qp_oracle.c): constraints that enter while the homotopy makes no
@@ -1061,6 +1090,7 @@ __global__ void __launch_bounds__(NT) k3_qp_kernel(const __grid_constant__ eepac
                 if (!isinf(un)) C.ubc[c] = full ? un : C.ubc[c] + tau * (un - C.ubc[c]);
             }
             __syncthreads();
+            RPH(2);
             PHASE(5);
             if (full) break;
             if (++iter > max_iter) { status = EEPACC_QP_MAXITER; break; }
@@ -1218,7 +1248,13 @@ __global__ void __launch_bounds__(NT) k3_qp_kernel(const __grid_constant__ eepac
                 io.wnA[veh] = C.nA;
                 io.warm[veh] = (status == EEPACC_QP_OK) ? 1 : 0;
                 PHASE(7);
-                if (io.dbg && veh == 0) for (int q = 0; q < 8; ++q) io.dbg[(size_t)io.dbg_cap * 4 + q] = (double)ph[q];
+#ifdef EEP_K3_TIMERS
+                if (io.dbg && veh == 0) {
+                    for (int q = 0; q < 8; ++q) io.dbg[(size_t)io.dbg_cap * 4 + q] = (double)ph[q];
+                    for (int q = 0; q < 8; ++q) io.dbg[(size_t)io.dbg_cap * 4 + 8 + q] = (double)kph[q];
+                    for (int q = 0; q < 4; ++q) io.dbg[(size_t)io.dbg_cap * 4 + 16 + q] = (double)rph[q];
+                }
+#endif
                 if (io.counters) {
                     io.counters[veh * 4 + 0] += (unsigned long long)iter;
                     io.counters[veh * 4 + 1] += (status != EEPACC_QP_OK);

@@ -10,13 +10,15 @@ nst = int(sys.argv[3]) if len(sys.argv) > 3 else 30
 p, routes, lead = bench.make_workload(cn, B, 0, max(nst, 25))
 eng = api.Engine(cn, p, routes, B=B)
 eng.debug_trace()
-names = ["load", "warmQR", "refacR", "auxsetup", "kkt", "Adx+ratio", "wschange", "refine+out"]
-tot = np.zeros(8)
+names = ["load", "warmQR", "refacR", "auxsetup", "kkt", "Adx+ratio", "wschange", "refine+out",
+         "k:usolveT", "k:QmulY", "k:Hmul", "k:QtmulZ", "k:Rsolves", "k:QmulZ", "k:QtmulY", "k:tsolveT",
+         "r:Amul", "r:ratio", "r:update", "r:-"]
+tot = np.zeros(20)
 for k in range(nst):
     out = eng.step(lead[k])
     ph = eng.debug_phases()
     if k in (0, 1, 5, nst - 1):
-        print(k, "iter", out["iter"][0], {n_: int(v) for n_, v in zip(names, ph)}, "sum", int(ph.sum()))
+        print(k, "iter", out["iter"][0], {n_: int(v) for n_, v in zip(names, ph)}, "sum", int(ph[:8].sum()))
     if k > 0:
         tot += ph
-print("mean over warm steps:", {n_: int(v / (nst - 1)) for n_, v in zip(names, tot)}, "sum", int(tot.sum() / (nst - 1)))
+print("mean over warm steps:", {n_: int(v / (nst - 1)) for n_, v in zip(names, tot)}, "sum", int(tot[:8].sum() / (nst - 1)))
