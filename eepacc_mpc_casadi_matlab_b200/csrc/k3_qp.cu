@@ -26,7 +26,7 @@
 #include "eepacc_kernels.h"
 #include "eepacc_rows.cuh"
 
-#define NT 128
+#define NT 256
 #define FARB      1.0e6
 #define RELAX     1.0e4
 #define BIGB      1.0e19
