@@ -328,7 +328,7 @@ class Engine:
         return out[out[:, 2] > 0]
 
     def debug_phases(self):
-        out = np.zeros(20)
+        out = np.zeros(28)
         self.L.eepacc_mem_debug_phases(self.mem, out.ctypes.data_as(_dp))
         return out
 

@@ -421,7 +421,7 @@ int eepacc_mem_debug_phases(int mem, double* out)
     Mem* M = get_mem(mem);
     if (!M || !M->ready || !M->dbg.p || !out) return fail(EEPACC_ERR_ARG, "tracing not enabled");
     CK(cudaSetDevice(M->device));
-    CK(cudaMemcpy(out, (double*)M->dbg.p + 4096 * 4, 20 * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out, (double*)M->dbg.p + 4096 * 4, 28 * 8, cudaMemcpyDeviceToHost));
     return EEPACC_OK;
 }
 
@@ -462,8 +462,8 @@ int eepacc_mem_debug_trace(int mem, double* out, int cap)
     if (!M || !M->ready) return fail(EEPACC_ERR_ARG, "mem not set up");
     CK(cudaSetDevice(M->device));
     if (!M->dbg.p) {
-        if (M->dbg.ensure((4096 * 4 + 24) * 8)) return EEPACC_ERR_MEM;
-        CK(cudaMemset(M->dbg.p, 0, (4096 * 4 + 24) * 8));
+        if (M->dbg.ensure((4096 * 4 + 32) * 8)) return EEPACC_ERR_MEM;
+        CK(cudaMemset(M->dbg.p, 0, (4096 * 4 + 32) * 8));
         return EEPACC_OK;
     }
     if (out && cap > 0) {

@@ -680,8 +680,10 @@ __device__ int resolve_pending(Ctx& C, int c_out, int side_out, unsigned long lo
 // eliminated by coordinate swaps (Qh = P_0 .. P_{nU-1} diag(I, G2)), so the Householder QR and the
 // explicit formation of Qh only run on the few general rows in the remaining n - nU coordinates.
 // Rows whose new bound is infinite, or that became linearly dependent, are dropped (y = 0).
-__device__ void warm_setup(Ctx& C, int old_nA, const short* gidx, const signed char* gside, const double* gy)
+__device__ void warm_setup(Ctx& C, int old_nA, const short* gidx, const signed char* gside, const double* gy, long long* wp = nullptr)
 {
+    long long tw = clock64();
+#define WPH(i) do { if (wp) { long long t_ = clock64(); wp[i] += t_ - tw; tw = t_; } } while (0)
     const int n = C.n, mt = C.mt, m = C.m;
     for (int c = threadIdx.x; c < mt; c += NT) C.st[c] = 0;
     short* cand = reinterpret_cast<short*>(C.wv);        // [n] constraint index per QR column
@@ -718,6 +720,7 @@ __device__ void warm_setup(Ctx& C, int old_nA, const short* gidx, const signed c
         tmpv[k] = cv;
     }
     __syncthreads();
+    WPH(0);
     // thread 0: ordered list (unit rows first, relative order kept) and the swap plan
     if (threadIdx.x == 0) {
         int cnt = 0;
@@ -748,6 +751,7 @@ __device__ void warm_setup(Ctx& C, int old_nA, const short* gidx, const signed c
     __syncthreads();
     int cnt = C.ired[4];
     const int nU = C.ired[5];
+    WPH(1);
     // 2. stage the general rows as columns nU.. of W (= Q storage), apply the coordinate swaps
     for (int k = nU + threadIdx.x; k < cnt; k += NT) {
         const int c = cand[k];
@@ -764,6 +768,7 @@ __device__ void warm_setup(Ctx& C, int old_nA, const short* gidx, const signed c
     }
     for (int k = threadIdx.x; k < nU; k += NT) rdiag[k] = uval[k];
     __syncthreads();
+    WPH(2);
     // 3. Householder QR of the general columns on rows >= nU; a dependent column is swapped with the last and dropped
     int k = nU;
     while (k < cnt) {
@@ -804,6 +809,7 @@ __device__ void warm_setup(Ctx& C, int old_nA, const short* gidx, const signed c
         __syncthreads();
         ++k;
     }
+    WPH(3);
     const int nA = cnt, nZ = n - nA;
     // 4. T block of M from Rh:  M(r, c) = Rh(n-1-c, n-1-r),  c >= r >= nZ  (unit columns: diagonal only)
     for (int r = nZ + threadIdx.x; r < n; r += NT) {
@@ -814,6 +820,7 @@ __device__ void warm_setup(Ctx& C, int old_nA, const short* gidx, const signed c
         }
     }
     __syncthreads();
+    WPH(4);
     // 5. form Qh = P_0 .. P_{nU-1} diag(I, G2): backward accumulation of the reflectors, then the swaps
     for (int j = threadIdx.x; j < n; j += NT)
         if (j < nU || j >= nA) { for (int i = 0; i < n; ++i) MQ(i, j) = (i == j) ? 1.0 : 0.0; }
@@ -842,12 +849,14 @@ __device__ void warm_setup(Ctx& C, int old_nA, const short* gidx, const signed c
     for (int j = threadIdx.x; j < n; j += NT)
         for (int u = nU - 1; u >= 0; --u) { const int a = swp[u]; if (a != u) { double t = MQ(u, j); MQ(u, j) = MQ(a, j); MQ(a, j) = t; } }
     __syncthreads();
+    WPH(5);
     // 6. reverse the columns, 7. working-set bookkeeping by Q column
     for (int i = threadIdx.x; i < n; i += NT)
         for (int c = 0; c < n / 2; ++c) { double a = MQ(i, c), b = MQ(i, n - 1 - c); MQ(i, c) = b; MQ(i, n - 1 - c) = a; }
     for (int kq = threadIdx.x; kq < nA; kq += NT) { C.yW[n - 1 - kq] = ycand[kq]; C.widx[n - 1 - kq] = cand[kq]; }
     C.nA = nA;
     __syncthreads();
+    WPH(6);
 }
 
 __device__ void cold_ws(Ctx& C)
@@ -931,13 +940,15 @@ __global__ void __launch_bounds__(NT, 1) k3_qp_kernel(const __grid_constant__ ee
         const int restart_after = (4 * n > 400 ? 4 * n : 400);
 #ifdef EEP_K3_TIMERS
         long long ph[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }, tck = clock64();
-        long long kph[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }, rph[4] = { 0, 0, 0, 0 };
+        long long kph[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }, rph[4] = { 0, 0, 0, 0 }, rph2[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
 #define PHASE(i) do { long long t_ = clock64(); ph[i] += t_ - tck; tck = t_; } while (0)
 #define KPHP kph
+#define WPHP rph2
 #define RPH(i) do { rph[i] += clock64() - tr; tr = clock64(); } while (0)
 #else
 #define PHASE(i) do { } while (0)
 #define KPHP nullptr
+#define WPHP nullptr
 #define RPH(i) do { } while (0)
 #endif
         unsigned long long n_exch = 0, n_refac = 0;
@@ -987,7 +998,7 @@ __global__ void __launch_bounds__(NT, 1) k3_qp_kernel(const __grid_constant__ ee
         bool need_cold = !was_warm;
         for (int i = threadIdx.x; i < n; i += NT) C.x[i] = was_warm ? io.wx[veh * (size_t)n + i] : 0.0;
         if (!need_cold) {
-            warm_setup(C, io.wnA[veh], io.widx + veh * (size_t)n, io.wside + veh * (size_t)n, io.wy + veh * (size_t)n);
+            warm_setup(C, io.wnA[veh], io.widx + veh * (size_t)n, io.wside + veh * (size_t)n, io.wy + veh * (size_t)n, WPHP);
             PHASE(1);
             n_refac++;
             if (refactor_R(C)) need_cold = true;
@@ -1253,6 +1264,7 @@ __global__ void __launch_bounds__(NT, 1) k3_qp_kernel(const __grid_constant__ ee
                     for (int q = 0; q < 8; ++q) io.dbg[(size_t)io.dbg_cap * 4 + q] = (double)ph[q];
                     for (int q = 0; q < 8; ++q) io.dbg[(size_t)io.dbg_cap * 4 + 8 + q] = (double)kph[q];
                     for (int q = 0; q < 4; ++q) io.dbg[(size_t)io.dbg_cap * 4 + 16 + q] = (double)rph[q];
+                    for (int q = 0; q < 8; ++q) io.dbg[(size_t)io.dbg_cap * 4 + 20 + q] = (double)rph2[q];
                 }
 #endif
                 if (io.counters) {

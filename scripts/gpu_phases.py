@@ -12,8 +12,9 @@ eng = api.Engine(cn, p, routes, B=B)
 eng.debug_trace()
 names = ["load", "warmQR", "refacR", "auxsetup", "kkt", "Adx+ratio", "wschange", "refine+out",
          "k:usolveT", "k:QmulY", "k:Hmul", "k:QtmulZ", "k:Rsolves", "k:QmulZ", "k:QtmulY", "k:tsolveT",
-         "r:Amul", "r:ratio", "r:update", "r:-"]
-tot = np.zeros(20)
+         "r:Amul", "r:ratio", "r:update", "r:-",
+         "w:classify", "w:plan", "w:stage", "w:QR", "w:Tfill", "w:formQ", "w:reverse", "w:-"]
+tot = np.zeros(28)
 for k in range(nst):
     out = eng.step(lead[k])
     ph = eng.debug_phases()
