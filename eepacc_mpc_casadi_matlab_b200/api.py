@@ -332,6 +332,15 @@ class Engine:
         self.L.eepacc_mem_debug_phases(self.mem, out.ctypes.data_as(_dp))
         return out
 
+    def debug_fetch(self, what, count):
+        """developer aid: per-step device buffer -> host (0 sblk, 1 g, 2 lba, 3 uba, 4 x, 5 status, 6 iter, 7 cost)"""
+        out = np.zeros(int(count))
+        self.L.eepacc_mem_debug_fetch.restype = C.c_longlong
+        got = self.L.eepacc_mem_debug_fetch(self.mem, int(what), out.ctypes.data_as(_dp), C.c_longlong(out.size))
+        if got < 0:
+            self._err()
+        return out[:got]
+
     def kpi_device_ptr(self):
         return self.L.eepacc_mem_kpi_device_ptr(self.mem)
 

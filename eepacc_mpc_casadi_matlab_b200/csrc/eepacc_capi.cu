@@ -60,6 +60,11 @@ struct Mem {
     DBuf g, lba, uba, sblk;     // closed loop is matrix-free: no dense H / A is ever stored
     DBuf wx, wy, widx, wside, wnA, warm, xsol, cost, status, iter, counters;
     DBuf kpi_acc, kpi, lead, lead_step, logrow, dbg;
+    DBuf rowtab, rowc;          // packed constraint rows of the controller for the reduced-space QP kernel
+    DBuf defer_list, defer_cnt; // vehicles the reduced-space QP kernel hands to the full-space kernel
+    int qp_mode = 0;            // 0: reduced-space kernel + full-space fallback, 1: full-space kernel only
+    int qp_fc = 48;             // capacity (free variables) of the reduced factorisation
+    long long deferred_total = 0;
     DBuf in[12], out[8];        // staging for host-pointer calls
     bool timing = false;        // CUDA-event timing of every kernel launch (bench.py roofline leg)
     std::vector<cudaEvent_t> evs;
@@ -68,7 +73,7 @@ struct Mem {
     {
         DBuf* all[] = { &routes, &s_prev, &v_prev, &Fm_prev, &Fb_prev, &a_minus1, &v_tv_meas, &fbA, &fbD, &prev_sol,
                         &x0, &dyn, &g, &lba, &uba, &sblk, &wx, &wy, &widx, &wside, &wnA, &warm, &xsol, &cost,
-                        &status, &iter, &counters, &kpi_acc, &kpi, &lead, &lead_step, &logrow, &dbg };
+                        &status, &iter, &counters, &kpi_acc, &kpi, &lead, &lead_step, &logrow, &dbg, &defer_list, &defer_cnt, &rowtab, &rowc };
         for (DBuf* b : all) b->release();
         for (auto& b : in) b.release();
         for (auto& b : out) b.release();
@@ -219,6 +224,17 @@ int device_step(Mem* M, const double* lead_dev, double* log_dev)
     if (ev) CK(cudaEventRecord(ev[1], M->stream));
     if (rc) return fail(EEPACC_ERR_CUDA, "k2_build launch", (cudaError_t)rc);
     eep_qp_io qio = make_qp_io(M);
+    if (M->qp_mode == 0) {
+        // reduced-space kernel first; whatever it cannot hold goes to the full-space kernel
+        CK(cudaMemsetAsync(M->defer_cnt.p, 0, sizeof(int), M->stream));
+        qio.fc = M->qp_fc;
+        qio.defer_list = M->defer_list.as<int>(); qio.defer_cnt = M->defer_cnt.as<int>();
+        qio.rowtab = M->rowtab.as<unsigned long long>(); qio.rowc = M->rowc.as<double>();
+        rc = eep_launch_qpr(&M->p, &qio, M->stream);
+        if (rc) return fail(EEPACC_ERR_CUDA, "k3r_qp launch", (cudaError_t)rc);
+        qio.todo_list = M->defer_list.as<int>(); qio.todo_cnt = M->defer_cnt.as<int>();
+        M->launches += 1;
+    }
     rc = eep_launch_qp(&M->p, &qio, M->stream);
     if (rc) return fail(EEPACC_ERR_CUDA, "k3_qp launch", (cudaError_t)rc);
     if (ev) CK(cudaEventRecord(ev[2], M->stream));
@@ -327,6 +343,8 @@ int eepacc_mem_setup(int mem, int ctrl, const eepacc_params* p, const eepacc_rou
         { &M->iter, (size_t)B * 8 }, { &M->counters, (size_t)B * 4 * 8 },
         { &M->kpi_acc, (size_t)B * ACC_W * 8 }, { &M->kpi, (size_t)B * EEPACC_N_KPI * 8 },
         { &M->lead_step, (size_t)B * 2 * 8 }, { &M->logrow, (size_t)B * EEPACC_LOG_W * 8 },
+        { &M->defer_list, (size_t)(B + 1) * 4 }, { &M->defer_cnt, 16 },
+        { &M->rowtab, (size_t)(m + 1) * 8 }, { &M->rowc, 96 * 8 },
     };
     for (auto& e : plan) if (e.b->ensure(e.bytes)) return EEPACC_ERR_MEM;
     CK(cudaMemcpyAsync(M->routes.p, routes, (size_t)B * sizeof(eepacc_route), cudaMemcpyHostToDevice, M->stream));
@@ -344,8 +362,31 @@ int eepacc_mem_setup(int mem, int ctrl, const eepacc_params* p, const eepacc_rou
         CK(cudaMemcpyAsync(M->fbD.p, fd.data(), fd.size() * 8, cudaMemcpyHostToDevice, M->stream));
         CK(cudaStreamSynchronize(M->stream));
     }
+    {
+        int rc = eep_qpr_build_rowtab(ctrl, p, M->m, M->rowtab.as<unsigned long long>(), M->rowc.as<double>(), M->stream);
+        if (rc) return fail(EEPACC_ERR_CUDA, "constraint-row table of the reduced-space QP kernel", rc < 100000 ? (cudaError_t)rc : cudaSuccess);
+    }
+    // developer knobs (A/B runs): EEPACC_QP_MODE=1 forces the full-space kernel, EEPACC_QP_FC sets the capacity
+    M->qp_mode = 0; M->qp_fc = 48;
+    if (const char* e = getenv("EEPACC_QP_MODE")) M->qp_mode = atoi(e) ? 1 : 0;
+    if (const char* e = getenv("EEPACC_QP_FC")) { int v = atoi(e); if (v >= 8 && v <= EEPACC_MAX_NVAR) M->qp_fc = v; }
+    if (M->qp_fc > M->n) M->qp_fc = M->n;
     M->ready = true;
     return reset_state(M);
+}
+
+/* Closed-loop QP kernel selection: mode 0 = reduced-space kernel (capacity fc free variables, 8..n) with
+ * the full-space kernel as fallback for the vehicles that do not fit; mode 1 = full-space kernel only. */
+int eepacc_mem_set_qp_mode(int mem, int mode, int fc)
+{
+    Mem* M = get_mem(mem);
+    if (!M || !M->ready) return fail(EEPACC_ERR_ARG, "mem not set up");
+    if (mode < 0 || mode > 1) return fail(EEPACC_ERR_ARG, "mode must be 0 or 1");
+    if (fc <= 0) fc = 48;
+    if (fc < 8) fc = 8;
+    if (fc > M->n) fc = M->n;
+    M->qp_mode = mode; M->qp_fc = fc;
+    return EEPACC_OK;
 }
 
 int eepacc_mem_reset(int mem)
@@ -472,6 +513,33 @@ int eepacc_mem_debug_trace(int mem, double* out, int cap)
         CK(cudaMemset(M->dbg.p, 0, 4096 * 4 * 8));
     }
     return EEPACC_OK;
+}
+
+/* Developer aid: copy one of the mem's per-step device buffers to the host (after eepacc_step):
+ * what 0 sblk [B][EEP_SBLK], 1 g [B][n], 2 lba [B][m], 3 uba [B][m], 4 x [B][n], 5 status [B], 6 iter [B], 7 cost [B].
+ * Returns the number of doubles written (<= cap) or a negative error. */
+long long eepacc_mem_debug_fetch(int mem, int what, double* out, long long cap)
+{
+    Mem* M = get_mem(mem);
+    if (!M || !M->ready || !out) { fail(EEPACC_ERR_ARG, "bad arguments"); return -1; }
+    if (cudaSetDevice(M->device) != cudaSuccess) return -1;
+    const long long B = M->B;
+    const void* src = nullptr; long long cnt = 0;
+    switch (what) {
+    case 0: src = M->sblk.p; cnt = B * EEP_SBLK; break;
+    case 1: src = M->g.p; cnt = B * M->n; break;
+    case 2: src = M->lba.p; cnt = B * M->m; break;
+    case 3: src = M->uba.p; cnt = B * M->m; break;
+    case 4: src = M->xsol.p; cnt = B * M->n; break;
+    case 5: src = M->status.p; cnt = B; break;
+    case 6: src = M->iter.p; cnt = B; break;
+    case 7: src = M->cost.p; cnt = B; break;
+    default: fail(EEPACC_ERR_ARG, "unknown buffer"); return -1;
+    }
+    if (cnt > cap) cnt = cap;
+    if (cudaStreamSynchronize(M->stream) != cudaSuccess) return -1;
+    if (cudaMemcpy(out, src, (size_t)cnt * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return cnt;
 }
 
 // ---------------- CasADi-style families ----------------

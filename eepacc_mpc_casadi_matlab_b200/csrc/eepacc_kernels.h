@@ -59,6 +59,14 @@ struct eep_qp_io {
     double *x, *cost, *lam_a, *lam_x, *status, *iter;   // lam_* may be null
     unsigned long long *counters;   // [B][4] working-set changes, failed, exchanges, refactorisations
     double *dbg; int dbg_cap;       // optional per-iteration trace of vehicle 0: tau, key, nA, exchanges
+    // reduced-space kernel (k3r_qp.cu): capacity of the free-variable factorisation and the list of
+    // vehicles it hands over to the full-space kernel; the full-space kernel, when todo_list is
+    // non-null, only solves the vehicles todo_list[0 .. *todo_cnt)
+    int fc;
+    int *defer_list, *defer_cnt;
+    const int *todo_list, *todo_cnt;
+    const unsigned long long* rowtab;   // [m] packed constraint rows of the controller (eep_qpr_build_rowtab)
+    const double* rowc;                 // [96] their coefficient tables
 };
 
 // post kernel (k4_post.cu): z recovery, force allocation, logging, KPI accumulation
@@ -84,6 +92,9 @@ void eep_launch_plant(const eepacc_params* p, long long B, const eepacc_route* r
                       const double* x, const double* u, double* xn, cudaStream_t st);
 int eep_launch_build(const eepacc_params* p, const eep_build_io* io, cudaStream_t st);
 int eep_launch_qp(const eepacc_params* p, const eep_qp_io* io, cudaStream_t st);
+int eep_launch_qpr(const eepacc_params* p, const eep_qp_io* io, cudaStream_t st);
+size_t eep_qpr_smem_bytes(int n, int m, int fc);
+int eep_qpr_build_rowtab(int ctrl, const eepacc_params* p, int m, unsigned long long* tab_dev, double* consts_dev, cudaStream_t st);
 size_t eep_qp_smem_bytes(int n, int m, int smode);
 int eep_launch_post(const eepacc_params* p, const eep_post_io* io, cudaStream_t st);
 int eep_launch_kpi_final(const eepacc_params* p, long long B, int n_steps, const double* kpi_acc, double* kpi, cudaStream_t st);

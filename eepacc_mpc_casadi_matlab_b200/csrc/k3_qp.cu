@@ -926,7 +926,10 @@ __global__ void __launch_bounds__(NT, 1) k3_qp_kernel(const __grid_constant__ ee
         C.st = reinterpret_cast<signed char*>(p);
         C.tabu = C.st + mt;
     }
-    for (long long veh = blockIdx.x; veh < io.B; veh += gridDim.x) {
+    // fallback mode (closed loop): only the vehicles the reduced-space kernel (k3r_qp.cu) handed over
+    const long long n_work = io.todo_list ? (long long)*io.todo_cnt : io.B;
+    for (long long wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
+        const long long veh = io.todo_list ? (long long)io.todo_list[wi] : wi;
         __syncthreads();
         C.H = io.H ? io.H + veh * (size_t)n * n : nullptr;
         C.g = io.g + veh * (size_t)n;
@@ -1297,6 +1300,7 @@ extern "C" int eep_launch_qp(const eepacc_params* p, const eep_qp_io* io, cudaSt
         attr_for = sm;
     }
     long long g = io->B;               // one CTA per vehicle: the hardware scheduler balances uneven solves
+    if (io->todo_list && g > 148) g = 148;      // fallback mode: a few persistent CTAs walk the (short) hand-over list
     if (g < 1) g = 1;
     if (g > 2147483647LL) g = 2147483647LL;
     k3_qp_kernel<<<(int)g, NT, sm, st>>>(*p, *io);

@@ -1,0 +1,1588 @@
+// k3r_qp.cu -- K3 (closed-loop path): batched, warm-started parametric active-set QP solver in the
+// REDUCED space of the free variables, one vehicle per CTA, several CTAs per SM.
+//
+// Stands where the reference calls the CasADi conic plugin 'qpoases' once per MPC step
+//     sol = QPsolver('h',H,'g',c,'a',G,'lbx',..,'ubx',..,'lba',g_lb,'uba',g_ub)
+// (MC/RunOpt_ABMPC.m:252, RunOpt_FBMPC.m:278, RunOpt_BLMPC.m:230, RunOpt_TVMPC.m:208).
+// Same algorithm, tolerances and tie-break rules as k3_qp.cu / oracle/qp_oracle.c (homotopy, far
+// bounds, exchange steps, anti-cycling); what changes is the factorisation it is carried out on.
+//
+// Observation (measured on the perturbed urban/highway batches): of the ~90-105 active rows of a
+// 100/120-variable QP, ~3/4 are UNIT rows (slack >= 0, Fb <= 0, far bounds: one entry on one
+// variable).  A variable pinned by an active unit row is "fixed"; only nF ~ 40 variables are free,
+// the null space has nZ <= 20 columns.  As qpOASES does for its bounds, the factorisation
+//     A_gF Qf = [0 T],   Z' H_FF Z = R'R,     Qf = [Z Y]  (nF x nF)
+// only covers the free variables F and the active GENERAL rows g; the fixed block is implicit:
+//     full Q = diag(Qf, I_X),   full T = [T  A_gX; 0  diag(cv_X)].
+// Unit rows that become active during a solve are handled as general rows (no shrinking); the
+// compaction happens at the next MPC step's warm start, where everything is rebuilt anyway.
+// Freeing a fixed variable appends a row/column to Qf and removes the implicit last T row.
+// If nF would exceed the shared-memory capacity FC the vehicle is DEFERRED: its index goes to
+// io.defer_list and the full-space kernel (k3_qp.cu) solves it from the untouched warm state.
+//
+// Shared memory (FC = 48, FB n=120 m=522): Qf 18.4 KB, packed R/T 9.2 KB, homotopy state over the
+// m+n rows 21 KB, vectors 14 KB, K2's structured block 11 KB  ->  ~82 KB, 2 CTAs/SM (AB: 3).
+// H*v, A*v, A'*y and single rows are matrix-free (structured block, eepacc_rows.cuh).
+#include "eepacc_dev.cuh"
+#include "eepacc_kernels.h"
+#include "eepacc_rows.cuh"
+
+#ifndef EEP_HOST_EMU
+#define NT 128
+#define EMU_ONLY(...)
+#endif
+
+#define FARB      1.0e6
+#define RELAX     1.0e4
+#define BIGB      1.0e19
+#define EPS_LI    1.0e-10
+#define EPS_PD    1.0e-9
+#define EPS_RATE  1.0e-12
+#define EPS_ROW   1.0e-12
+#define FEAS_TOL  1.0e-10
+#define LP_REG    1.0e-6
+#define K3R_DEFER 1000          // internal status: hand the vehicle to the full-space kernel
+
+namespace k3r {
+
+template <int NU, int NB>
+struct CtxT {
+    static constexpr int nu = NU, nb = NB;     // controls per stage, driven controls per stage
+    int n, m, mt, fc, ldq;
+    int nF, nX, nZ;             // free variables, fixed variables (nF + nX = n), null-space columns
+    double reg, hscale;
+    const double *g, *lnw, *unw;               // shared copies: gradient [n], new bounds of all m+n rows
+    const unsigned long long* rtab;            // [m] packed constraint rows (k3r_build_rowtab)
+    const double *cvals, *cva, *cvb;           // [32] each: control coefficients, (a, b) of cV = a + b v_est(k)
+    // factorisation
+    double *Q, *M, *sub;
+    // full-space vectors [n]
+    double *x, *gcur, *dx, *dg, *t1, *t2, *t3, *t4;
+    // fixed block, by position k in the X list [n]
+    double *yX, *dyX, *xcv, *dbX;
+    // reduced vectors, by Qf column / row [fc + 1]
+    double *yW, *dyW, *dbw, *wv, *csA, *snA, *pF, *uF, *tF, *gF;
+    // homotopy state over all rows [mt]
+    double *Ax, *lbc, *ubc, *Adx;
+    float* anorm;
+    // structured block
+    double *PS, *PV, *vest, *Dc, *Cc, *Dg, *sv, *vv, *drv, *yc;
+    // adjoint scratch: per-stage accumulators and per-active-row descriptors
+    double *aS, *aV, *aD;       // [N+1], [N+1], [N]
+    double *rS, *rV, *rv0, *rv1, *rv2;   // [fc]
+    short *rk, *rj0, *rj1, *rj2, *rj3;   // [fc]
+    short *flist, *fpos, *xvar, *xcon, *widx;
+    signed char *st, *tabu;
+    double* red;
+    int* ired;
+#ifdef EEP_K3_TIMERS
+    long long* ph;              // [32] clock64() cycles by phase + [32] = last stamp (thread 0 only)
+#endif
+};
+
+#ifdef EEP_K3_TIMERS
+#define PH(i) do { if (threadIdx.x == 0) { long long t_ = clock64(); C.ph[i] += t_ - C.ph[32]; C.ph[32] = t_; } } while (0)
+#else
+#define PH(i) do { } while (0)
+#endif
+
+template <class CT> __device__ __forceinline__ int mi(const CT& c, int r, int col) { return r * c.fc - (r * (r - 1)) / 2 + (col - r); }
+#define QF(i, j) C.Q[(size_t)(j) * C.ldq + (i)]
+#define MM(r, c) C.M[mi(C, (r), (c))]
+
+template <class CT> __device__ __forceinline__ double lb_new(const CT& C, int c) { return C.lnw[c]; }
+template <class CT> __device__ __forceinline__ double ub_new(const CT& C, int c) { return C.unw[c]; }
+
+// ---- block reductions (results broadcast to every thread) ----
+#ifdef EEP_HOST_EMU
+template <class CT> __device__ __forceinline__ double block_sum(CT&, double v) { return v; }
+template <class CT> __device__ __forceinline__ double block_max(CT&, double v) { return v; }
+template <class CT> __device__ __forceinline__ void block_argmin(CT&, double&, int&) {}
+#else
+template <class CT> __device__ __forceinline__ double block_sum(CT& C, double v)
+{
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) C.red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0;
+    for (int w = 0; w < NT / 32; ++w) s += C.red[w];
+    return s;
+}
+template <class CT> __device__ __forceinline__ double block_max(CT& C, double v)
+{
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) C.red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = C.red[0];
+    for (int w = 1; w < NT / 32; ++w) s = fmax(s, C.red[w]);
+    return s;
+}
+// lexicographic (t, key) minimum
+template <class CT> __device__ __forceinline__ void block_argmin(CT& C, double& t, int& key)
+{
+    for (int o = 16; o > 0; o >>= 1) {
+        double t2 = __shfl_xor_sync(0xffffffffu, t, o);
+        int k2 = __shfl_xor_sync(0xffffffffu, key, o);
+        if (t2 < t || (t2 == t && k2 < key)) { t = t2; key = k2; }
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { C.red[threadIdx.x >> 5] = t; C.ired[threadIdx.x >> 5] = key; }
+    __syncthreads();
+    t = C.red[0]; key = C.ired[0];
+    for (int w = 1; w < NT / 32; ++w) {
+        double t2 = C.red[w]; int k2 = C.ired[w];
+        if (t2 < t || (t2 == t && k2 < key)) { t = t2; key = k2; }
+    }
+}
+#endif
+
+struct VestSrc { const double* v_est; };
+
+// ---- matrix-free operators: H = Psi' Hs Psi and A = Gs Psi are never formed ----
+template <class CT> __device__ void s_prep(CT& C, const double* v)
+{
+    const int NH = EEP_N;
+    for (int i = threadIdx.x; i < NH; i += NT) {
+        double d = v[i * CT::nu];
+        if (CT::nb == 2) d += v[i * CT::nu + 1];
+        C.drv[i] = d;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k <= NH; k += NT) {
+        double a = 0, b = 0;
+        for (int i = 0; i < k && i < NH; ++i) { a += C.PS[k * NH + i] * C.drv[i]; b += C.PV[k * NH + i] * C.drv[i]; }
+        C.sv[k] = a; C.vv[k] = b;
+    }
+    __syncthreads();
+}
+// ---- constraint rows: packed table, one 8-byte word per row c < m (built once per set-up, k3r_build_rowtab) ----
+//   b0  kst (int8): stage of the state entries, -1 none, -2 jerk row (-1 on the driven controls of stage aux)
+//   b1  aux: kst >= 0: bit 7 = coefficient 1 on s_k, bits 0-6 = id of the (a, b) pair, coefficient on v_k = a + b v_est(k);
+//            kst == -2: the stage before
+//   b2..b4  dense column of the <= 3 control entries (0xFF: none)        b5..b7  ids of their coefficients
+// Far-bound rows c >= m are the unit rows e_(c-m).  No switch, no divergence: a row is one LDS.64 + table reads.
+struct RowW { int kst, aux, j0, j1, j2, i0, i1, i2; };
+template <class CT> __device__ __forceinline__ RowW row_load(const CT& C, int c)
+{
+    RowW r;
+    if (c >= C.m) { r.kst = -1; r.aux = 0; r.j0 = c - C.m; r.j1 = r.j2 = 255; r.i0 = r.i1 = r.i2 = 0; return r; }
+    const unsigned long long w = C.rtab[c];
+    r.kst = (int)(signed char)(w & 0xff); r.aux = (int)((w >> 8) & 0xff);
+    r.j0 = (int)((w >> 16) & 0xff); r.j1 = (int)((w >> 24) & 0xff); r.j2 = (int)((w >> 32) & 0xff);
+    r.i0 = (int)((w >> 40) & 0xff); r.i1 = (int)((w >> 48) & 0xff); r.i2 = (int)((w >> 56) & 0xff);
+    return r;
+}
+template <class CT> __device__ __forceinline__ double row_cV(const CT& C, const RowW& r)
+{
+    const int id = r.aux & 127;
+    return C.cva[id] + C.cvb[id] * C.vest[r.kst];
+}
+// one entry A(c, j)
+template <class CT> __device__ __forceinline__ double s_entry(const CT& C, const RowW& r, int j)
+{
+    const int NH = EEP_N;
+    const int i = j / CT::nu, cj = j % CT::nu;
+    double val = 0.0;
+    if (r.kst >= 0 && cj < CT::nb && i < r.kst) {
+        val = row_cV(C, r) * C.PV[r.kst * NH + i];
+        if (r.aux & 128) val += C.PS[r.kst * NH + i];
+    }
+    if (r.j0 == j) val += C.cvals[r.i0];
+    if (r.j1 == j) val += C.cvals[r.i1];
+    if (r.j2 == j) val += C.cvals[r.i2];
+    if (r.kst == -2 && cj < CT::nb && i == r.aux) val -= 1.0;
+    return val;
+}
+// a_c' v for a vector whose state sensitivities are in sv/vv/drv (s_prep)
+template <class CT> __device__ __forceinline__ double s_rowdot(const CT& C, const RowW& r, const double* v)
+{
+    double val = 0.0;
+    if (r.kst >= 0) {
+        val = row_cV(C, r) * C.vv[r.kst];
+        if (r.aux & 128) val += C.sv[r.kst];
+    }
+    if (r.j0 != 255) val += C.cvals[r.i0] * v[r.j0];
+    if (r.j1 != 255) val += C.cvals[r.i1] * v[r.j1];
+    if (r.j2 != 255) val += C.cvals[r.i2] * v[r.j2];
+    if (r.kst == -2) val -= C.drv[r.aux];
+    return val;
+}
+// unit row?  -> variable index and coefficient
+template <class CT> __device__ __forceinline__ bool s_unit(const CT& C, const RowW& r, int& jv, double& cv)
+{
+    if (r.kst == -1 && r.j1 == 255 && r.j0 != 255) { jv = r.j0; cv = C.cvals[r.i0]; return true; }
+    return false;
+}
+
+// full row (all n entries)
+template <class CT> __device__ void get_row(CT& C, int c, double* a)
+{
+    const RowW rd = row_load(C, c);
+    for (int j = threadIdx.x; j < C.n; j += NT) a[j] = s_entry(C, rd, j);
+    __syncthreads();
+}
+template <class CT> __device__ void Hmul(CT& C, const double* v, double* out)
+{
+    const int n = C.n;
+    const int NH = EEP_N, nu = CT::nu, nb = CT::nb;
+    s_prep(C, v);
+    // y_k on the core [v, driven]: D_k w_k + C_k w_{k-1} + C_{k+1}' w_{k+1}
+    for (int k = threadIdx.x; k < NH; k += NT) {
+        double w0[3] = { C.vv[k], v[k * nu], nb == 2 ? v[k * nu + 1] : 0.0 };
+        double y[3] = { 0, 0, 0 };
+        const double* D = C.Dc + k * 9;
+        for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) y[a] += D[a * 3 + b] * w0[b];
+        if (k > 0) {
+            double w1[3] = { C.vv[k - 1], v[(k - 1) * nu], nb == 2 ? v[(k - 1) * nu + 1] : 0.0 };
+            const double* Cm = C.Cc + k * 9;
+            for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) y[a] += Cm[a * 3 + b] * w1[b];
+        }
+        if (k + 1 < NH) {
+            double w2[3] = { C.vv[k + 1], v[(k + 1) * nu], nb == 2 ? v[(k + 1) * nu + 1] : 0.0 };
+            const double* Cp = C.Cc + (k + 1) * 9;
+            for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) y[a] += Cp[b * 3 + a] * w2[b];
+        }
+        C.yc[k * 3] = y[0]; C.yc[k * 3 + 1] = y[1]; C.yc[k * 3 + 2] = y[2];
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < n; j += NT) {
+        const int i = j / nu, cj = j % nu;
+        double val;
+        if (cj < nb) {
+            val = C.yc[i * 3 + 1 + cj];
+            double acc = 0.0;
+            for (int k = i + 1; k < NH; ++k) acc += C.PV[k * NH + i] * C.yc[k * 3];
+            val += acc;
+        } else val = C.Dg[i * 4 + (cj - nb)] * v[j];
+        out[j] = val + C.reg * v[j];
+    }
+    __syncthreads();
+}
+template <class CT> __device__ void Amul(CT& C, const double* v, double* out)
+{
+    const int n = C.n, m = C.m;
+    s_prep(C, v);
+    for (int r = threadIdx.x; r < m; r += NT) {
+        out[r] = s_rowdot(C, row_load(C, r), v);
+    }
+    for (int j = threadIdx.x; j < n; j += NT) out[m + j] = v[j];
+    __syncthreads();
+}
+// w[j] = sum over the active general rows r in [nZ, nF) of A(widx[r], j) yv[r]
+//        (+ cv_k yXv[k] at j = xvar[k] when yXv != nullptr).  Deterministic gather, no atomics.
+template <class CT> __device__ void ATmul(CT& C, const double* yv, const double* yXv, double* w)
+{
+    const int n = C.n, NH = EEP_N, nu = CT::nu, nb = CT::nb, nZ = C.nZ, nF = C.nF;
+    __syncthreads();
+    for (int r = nZ + threadIdx.x; r < nF; r += NT) {
+        const RowW rd = row_load(C, C.widx[r]);
+        const double y = yv[r];
+        C.rk[r] = (short)rd.kst;
+        C.rS[r] = (rd.kst == -2 || (rd.aux & 128)) ? y : 0.0;     // jerk rows: -y on the driven controls of the stage before
+        C.rV[r] = (rd.kst >= 0) ? row_cV(C, rd) * y : 0.0;
+        C.rj0[r] = (short)(rd.kst == -2 ? 256 + rd.aux : rd.j0);  // jerk rows carry the stage before here (their own entries follow)
+        C.rj1[r] = (short)rd.j1; C.rj2[r] = (short)rd.j2;
+        C.rv0[r] = (rd.j0 != 255) ? C.cvals[rd.i0] * y : 0.0;
+        C.rv1[r] = (rd.j1 != 255) ? C.cvals[rd.i1] * y : 0.0;
+        C.rv2[r] = (rd.j2 != 255) ? C.cvals[rd.i2] * y : 0.0;
+        C.rj3[r] = (short)rd.j0;
+    }
+    __syncthreads();
+    // per-stage accumulators: thread k gathers its stage (oldest row first)
+    for (int k = threadIdx.x; k <= NH; k += NT) {
+        double s = 0, v = 0, d = 0;
+        for (int r = nF - 1; r >= nZ; --r) {
+            const int kr = C.rk[r];
+            if (kr == k) { s += C.rS[r]; v += C.rV[r]; }
+            else if (kr == -2 && C.rj0[r] - 256 == k) d += C.rS[r];
+        }
+        C.aS[k] = s; C.aV[k] = v;
+        if (k < NH) C.aD[k] = d;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < n; j += NT) {
+        const int i = j / nu, cj = j % nu;
+        double val = 0.0;
+        for (int r = nF - 1; r >= nZ; --r) {           // oldest first
+            if (C.rj3[r] == j) val += C.rv0[r];
+            if (C.rj1[r] == j) val += C.rv1[r];
+            if (C.rj2[r] == j) val += C.rv2[r];
+        }
+        if (cj < nb) {
+            double acc = 0.0;
+            for (int k = i + 1; k <= NH; ++k) acc += C.aS[k] * C.PS[k * NH + i] + C.aV[k] * C.PV[k * NH + i];
+            val += acc - C.aD[i];
+        }
+        w[j] = val;
+    }
+    __syncthreads();
+    if (yXv) {
+        for (int k = threadIdx.x; k < C.nX; k += NT) w[C.xvar[k]] += C.xcv[k] * yXv[k];
+        __syncthreads();
+    }
+}
+
+// ---- reduced dense primitives; every routine ends with data visible after a __syncthreads() ----
+template <class CT> __device__ void gatherF(CT& C, const double* a)
+{
+    for (int i = threadIdx.x; i < C.nF; i += NT) C.gF[i] = a[C.flist[i]];
+    __syncthreads();
+}
+// w[j] = qf_j' aF for j in [c0, c1), aF compact [nF]
+template <class CT> __device__ void Qtmul(CT& C, const double* aF, double* w, int c0, int c1)
+{
+    const int nF = C.nF;
+    for (int j = c0 + threadIdx.x; j < c1; j += NT) {
+        double s0 = 0, s1 = 0;
+        int i = 0;
+        for (; i + 1 < nF; i += 2) { s0 += QF(i, j) * aF[i]; s1 += QF(i + 1, j) * aF[i + 1]; }
+        if (i < nF) s0 += QF(i, j) * aF[i];
+        w[j] = s0 + s1;
+    }
+    __syncthreads();
+}
+// outF[i] = sum_{c in [c0,c1)} Qf(i,c) p[c], i < nF (compact)
+template <class CT> __device__ void Qmul(CT& C, const double* p, int c0, int c1, double* outF)
+{
+    const int nF = C.nF;
+    for (int i = threadIdx.x; i < nF; i += NT) {
+        double s0 = 0, s1 = 0;
+        int c = c0;
+        for (; c + 1 < c1; c += 2) { s0 += QF(i, c) * p[c]; s1 += QF(i, c + 1) * p[c + 1]; }
+        if (c < c1) s0 += QF(i, c) * p[c];
+        outF[i] = s0 + s1;
+    }
+    __syncthreads();
+}
+// solve M[lo:hi,lo:hi] x = b (back substitution); b is destroyed, x may not alias b
+template <class CT> __device__ void usolve(CT& C, int lo, int hi, double* b, double* x)
+{
+#ifdef EEP_HOST_EMU
+    for (int r = hi - 1; r >= lo; --r) {
+        double s = b[r];
+        for (int c = r + 1; c < hi; ++c) s -= MM(r, c) * x[c];
+        x[r] = s * (1.0 / MM(r, r));
+    }
+#else
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int b1 = hi; b1 > lo; b1 -= 32) {
+        const int b0 = (b1 - 32 > lo) ? b1 - 32 : lo, nbk = b1 - b0;
+        __syncthreads();
+        if (warp == 0) {
+            const int r = b0 + lane;
+            double acc = (lane < nbk) ? b[r] : 0.0;
+            const double inv = (lane < nbk) ? 1.0 / MM(r, r) : 0.0;
+            for (int t = nbk - 1; t >= 0; --t) {
+                const double xt = __shfl_sync(0xffffffffu, acc * inv, t);
+                if (lane < t) acc -= MM(r, b0 + t) * xt;
+                if (lane == t) x[r] = xt;
+            }
+        }
+        __syncthreads();
+        for (int i = lo + threadIdx.x; i < b0; i += NT) {
+            double s0 = 0, s1 = 0;
+            int c = b0;
+            for (; c + 1 < b1; c += 2) { s0 += MM(i, c) * x[c]; s1 += MM(i, c + 1) * x[c + 1]; }
+            if (c < b1) s0 += MM(i, c) * x[c];
+            b[i] -= s0 + s1;
+        }
+    }
+    __syncthreads();
+#endif
+}
+// solve M[lo:hi,lo:hi]' y = v (forward substitution); v destroyed
+template <class CT> __device__ void tsolve(CT& C, int lo, int hi, double* v, double* y)
+{
+#ifdef EEP_HOST_EMU
+    for (int r = lo; r < hi; ++r) {
+        double s = v[r];
+        for (int c = lo; c < r; ++c) s -= MM(c, r) * y[c];
+        y[r] = s * (1.0 / MM(r, r));
+    }
+#else
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int b0 = lo; b0 < hi; b0 += 32) {
+        const int b1 = (b0 + 32 < hi) ? b0 + 32 : hi, nbk = b1 - b0;
+        __syncthreads();
+        if (warp == 0) {
+            const int r = b0 + lane;
+            double acc = (lane < nbk) ? v[r] : 0.0;
+            const double inv = (lane < nbk) ? 1.0 / MM(r, r) : 0.0;
+            for (int t = 0; t < nbk; ++t) {
+                const double yt = __shfl_sync(0xffffffffu, acc * inv, t);
+                if (lane > t && lane < nbk) acc -= MM(b0 + t, r) * yt;
+                if (lane == t) y[r] = yt;
+            }
+        }
+        __syncthreads();
+        for (int i = b1 + threadIdx.x; i < hi; i += NT) {
+            double s0 = 0, s1 = 0;
+            int c = b0;
+            for (; c + 1 < b1; c += 2) { s0 += MM(c, i) * y[c]; s1 += MM(c + 1, i) * y[c + 1]; }
+            if (c < b1) s0 += MM(c, i) * y[c];
+            v[i] -= s0 + s1;
+        }
+    }
+    __syncthreads();
+#endif
+}
+
+// Givens sweep that adds the row whose free part is aF (compact).  nZt = null-space columns that take
+// part (0..nZt-1), nR = dimension of the valid R block to keep updated (0: none).  The new
+// range-space column / T row is nZt-1.  Returns 1 if the row is linearly dependent (no change).
+template <class CT> __device__ int givens_add(CT& C, int cidx, int side, const double* aF, double an2, int nZt, int nR, bool check_li)
+{
+    const int nF = C.nF;
+    Qtmul(C, aF, C.wv, 0, nF);
+    if (check_li) {
+        double zn = 0;
+        for (int j = threadIdx.x; j < nZt; j += NT) zn += C.wv[j] * C.wv[j];
+        zn = block_sum(C, zn);
+        const double san = sqrt(an2);
+        if (nZt == 0 || sqrt(zn) <= EPS_LI * (san > 1.0 ? san : 1.0)) return 1;
+    }
+    if (threadIdx.x == 0) {
+        double carry = C.wv[0];
+        for (int k = 0; k < nZt - 1; ++k) {
+            double p = carry, q = C.wv[k + 1];
+            double r = hypot(p, q);
+            double cs = 1.0, sn = 0.0;
+            if (r != 0.0) { cs = q / r; sn = p / r; carry = r; } else carry = q;
+            C.csA[k] = cs; C.snA[k] = sn;
+            C.wv[k] = 0.0;
+        }
+        if (nZt > 0) C.wv[nZt - 1] = carry;
+    }
+    __syncthreads();
+    // Qf: one row per thread, rotations applied left to right with the carry in a register
+    for (int i = threadIdx.x; i < nF; i += NT) {
+        double u = QF(i, 0);
+        for (int k = 0; k < nZt - 1; ++k) {
+            double v = QF(i, k + 1);
+            double cs = C.csA[k], sn = C.snA[k];
+            QF(i, k) = cs * u - sn * v;
+            u = sn * u + cs * v;
+        }
+        if (nZt > 0) QF(i, nZt - 1) = u;
+    }
+    if (nR > 1) {
+        // R phase A: column rotations k = 0..nR-2, one row of R per thread
+        for (int i = threadIdx.x; i < nR; i += NT) {
+            int k0 = i > 0 ? i - 1 : 0;
+            double u;
+            if (i > 0) {        // rotation k = i-1 mixes (i,i-1)=0 with (i,i)
+                double d = MM(i, i);
+                C.sub[i] = -C.snA[i - 1] * d;
+                u = C.csA[i - 1] * d;
+                k0 = i;
+            } else u = MM(0, 0);
+            for (int k = k0; k < nR - 1; ++k) {
+                double v = MM(i, k + 1);
+                double cs = C.csA[k], sn = C.snA[k];
+                MM(i, k) = cs * u - sn * v;
+                u = sn * u + cs * v;
+            }
+            MM(i, nR - 1) = u;
+        }
+        // R phase B: re-triangularise (row rotations), wavefront over k
+        for (int k = 0; k < nR - 1; ++k) {
+            __syncthreads();
+            double pa = MM(k, k), pb = C.sub[k + 1];
+            double rr = hypot(pa, pb);
+            __syncthreads();
+            if (rr != 0.0) {
+                double c2 = pa / rr, s2 = pb / rr;
+                for (int j = k + threadIdx.x; j < nR; j += NT) {
+                    double u = MM(k, j);
+                    double v = (j == k) ? pb : MM(k + 1, j);
+                    MM(k, j) = c2 * u + s2 * v;
+                    if (j > k) MM(k + 1, j) = -s2 * u + c2 * v;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // new T row = M row nZt-1 (columns >= nZt-1)
+    const int rn = nZt - 1;
+    for (int c = rn + threadIdx.x; c < nF; c += NT) MM(rn, c) = C.wv[c];
+    if (threadIdx.x == 0) { C.widx[rn] = (short)cidx; C.st[cidx] = (signed char)side; }
+    C.nZ = rn;
+    __syncthreads();
+    return 0;
+}
+
+// Remove the general row that owns Qf column rp.  Afterwards column nZ_old is the new null-space
+// direction; R is not touched.  yW / widx are shifted with the rows.
+template <class CT> __device__ void remove_general(CT& C, int rp)
+{
+    const int nF = C.nF, nZ = C.nZ;
+    if (threadIdx.x == 0) C.st[C.widx[rp]] = 0;
+    __syncthreads();
+    // shift rows nZ..rp-1 one row down the diagonal (row r-1 -> row r); one column per thread
+    for (int c = nZ + threadIdx.x; c < nF; c += NT) {
+        if (c < rp) C.sub[c + 1] = MM(c, c);
+        int rtop = c < rp ? c : rp;
+        for (int r = rtop; r > nZ; --r) MM(r, c) = MM(r - 1, c);
+    }
+    if (threadIdx.x == 0) {
+        for (int r = rp; r > nZ; --r) { C.widx[r] = C.widx[r - 1]; C.yW[r] = C.yW[r - 1]; }
+    }
+    // Givens wavefront: rotation at r (columns r-1, r) for r = rp .. nZ+1
+    for (int r = rp; r > nZ; --r) {
+        __syncthreads();
+        double a = C.sub[r], b = MM(r, r);
+        double rho = hypot(a, b);
+        double cs = 1.0, sn = 0.0;
+        if (rho != 0.0) { cs = b / rho; sn = a / rho; }
+        __syncthreads();
+        if (threadIdx.x == 0) { C.csA[r] = cs; C.snA[r] = sn; }
+        // rows r' in [nZ+1, r]: elements (r', r-1) and (r', r)
+        for (int rr = nZ + 1 + threadIdx.x; rr <= r; rr += NT) {
+            double u = (rr == r) ? a : MM(rr, r - 1);
+            double v = MM(rr, r);
+            if (rr < r) MM(rr, r - 1) = cs * u - sn * v;
+            MM(rr, r) = sn * u + cs * v;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nF; i += NT) {
+        if (rp > nZ) {
+            double v = QF(i, rp);
+            for (int r = rp; r > nZ; --r) {
+                double u = QF(i, r - 1);
+                double cs = C.csA[r], sn = C.snA[r];
+                QF(i, r) = sn * u + cs * v;
+                v = cs * u - sn * v;          // becomes column r-1, the right-hand column of the next rotation
+            }
+            QF(i, nZ) = v;
+        }
+    }
+    C.nZ = nZ + 1;
+    __syncthreads();
+}
+
+// Free the variable pinned by X entry k (remove its unit row from the working set): append the
+// coordinate to Qf and T (implicit last row of the full T made explicit), then remove that row.
+// Returns 1 if the capacity is exhausted (nothing changed).
+template <class CT> __device__ int free_var(CT& C, int k)
+{
+    const int nF = C.nF, nZ = C.nZ;
+    if (nF >= C.fc) return 1;
+    __syncthreads();
+    const int j = C.xvar[k], c = C.xcon[k];
+    const double cv = C.xcv[k], yk = C.yX[k];
+    __syncthreads();
+    for (int i = threadIdx.x; i <= nF; i += NT) { QF(i, nF) = (i == nF) ? 1.0 : 0.0; QF(nF, i) = (i == nF) ? 1.0 : 0.0; }
+    for (int r = nZ + threadIdx.x; r < nF; r += NT) {
+        const RowW rd = row_load(C, C.widx[r]);
+        MM(r, nF) = s_entry(C, rd, j);
+    }
+    if (threadIdx.x == 0) {
+        MM(nF, nF) = cv;
+        C.widx[nF] = (short)c; C.yW[nF] = yk;
+        C.flist[nF] = (short)j; C.fpos[j] = (short)nF;
+        for (int q = k; q + 1 < C.nX; ++q) {
+            C.xvar[q] = C.xvar[q + 1]; C.xcon[q] = C.xcon[q + 1]; C.xcv[q] = C.xcv[q + 1]; C.yX[q] = C.yX[q + 1];
+            C.fpos[C.xvar[q]] = (short)(-1 - q);
+        }
+    }
+    C.nF = nF + 1; C.nX -= 1;
+    __syncthreads();
+    remove_general(C, nF);
+    return 0;
+}
+
+// R = chol(Z' H Z) from scratch on the first nZ columns; returns 1 if not positive definite
+template <class CT> __device__ int refactor_R(CT& C)
+{
+    const int n = C.n, nF = C.nF, nZ = C.nZ;
+    for (int i = threadIdx.x; i < n; i += NT) C.t3[i] = 0.0;
+    __syncthreads();
+    for (int j = 0; j < nZ; ++j) {
+        for (int i = threadIdx.x; i < nF; i += NT) C.t3[C.flist[i]] = QF(i, j);
+        __syncthreads();
+        Hmul(C, C.t3, C.t1);
+        gatherF(C, C.t1);
+        Qtmul(C, C.gF, C.tF, 0, j + 1);
+        for (int i = threadIdx.x; i <= j; i += NT) MM(i, j) = C.tF[i];
+    }
+    const double thr = EPS_PD * C.hscale;
+    for (int k = 0; k < nZ; ++k) {
+        __syncthreads();
+        double d = MM(k, k);
+        if (!(d > thr)) return 1;
+        double rk = sqrt(d), inv = 1.0 / rk;
+        const int w = nZ - 1 - k;                 // trailing dimension
+        for (int e = threadIdx.x; e < w * w; e += NT) {
+            int i = k + 1 + e / w, j = k + 1 + e % w;
+            if (j >= i) MM(i, j) -= (MM(k, i) * inv) * (MM(k, j) * inv);
+        }
+        __syncthreads();
+        for (int j = k + threadIdx.x; j < nZ; j += NT) MM(k, j) = (j == k) ? rk : MM(k, j) * inv;
+    }
+    __syncthreads();
+    return 0;
+}
+
+// KKT step: H dx + dg = A_W' dy,  A_W dx = db.  db / dy: dbw,dyW by Qf column (general rows) and
+// dbX,dyX by X position (unit rows of the fixed variables).
+template <class CT> __device__ void kkt_step(CT& C, const double* dg, const double* dbw, const double* dbX, double* dx, double* dyW, double* dyX)
+{
+    const int n = C.n, nF = C.nF, nZ = C.nZ, nX = C.nX, nAC = nF - nZ;
+    double* u = C.t2;
+    for (int i = threadIdx.x; i < n; i += NT) dx[i] = 0.0;
+    __syncthreads();
+    for (int k = threadIdx.x; k < nX; k += NT) dx[C.xvar[k]] = dbX[k] / C.xcv[k];
+    __syncthreads();
+    if (nAC > 0) {
+        s_prep(C, dx);
+        for (int r = nZ + threadIdx.x; r < nF; r += NT) {
+            const RowW rd = row_load(C, C.widx[r]);
+            C.tF[r] = dbw[r] - s_rowdot(C, rd, dx);
+        }
+        __syncthreads();
+        usolve(C, nZ, nF, C.tF, C.pF);
+        Qmul(C, C.pF, nZ, nF, C.uF);
+        for (int i = threadIdx.x; i < nF; i += NT) dx[C.flist[i]] = C.uF[i];
+        __syncthreads();
+    }
+    PH(7);
+    Hmul(C, dx, u);
+    for (int i = threadIdx.x; i < n; i += NT) u[i] += dg[i];
+    __syncthreads();
+    PH(8);
+    if (nZ > 0) {
+        gatherF(C, u);
+        Qtmul(C, C.gF, C.tF, 0, nZ);
+        for (int j = threadIdx.x; j < nZ; j += NT) C.tF[j] = -C.tF[j];
+        __syncthreads();
+        tsolve(C, 0, nZ, C.tF, C.pF);
+        usolve(C, 0, nZ, C.pF, C.tF);
+        Qmul(C, C.tF, 0, nZ, C.uF);              // p = Z q (compact)
+        for (int i = threadIdx.x; i < n; i += NT) C.t1[i] = 0.0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < nF; i += NT) { const int j = C.flist[i]; C.t1[j] = C.uF[i]; dx[j] += C.uF[i]; }
+        __syncthreads();
+        PH(9);
+        Hmul(C, C.t1, C.t3);
+        for (int i = threadIdx.x; i < n; i += NT) u[i] += C.t3[i];
+        __syncthreads();
+        PH(10);
+    }
+    if (nAC > 0) {
+        gatherF(C, u);
+        Qtmul(C, C.gF, C.tF, nZ, nF);
+        tsolve(C, nZ, nF, C.tF, dyW);
+    }
+    PH(11);
+    if (nX > 0) {
+        ATmul(C, dyW, nullptr, C.t3);
+        for (int k = threadIdx.x; k < nX; k += NT) { const int j = C.xvar[k]; dyX[k] = (u[j] - C.t3[j]) / C.xcv[k]; }
+        __syncthreads();
+    }
+    PH(12);
+}
+
+// g_cur = A_W' y - H x  (optionally recomputing y by least squares first), duals sign-clamped
+template <class CT> __device__ void reanchor(CT& C, bool recompute_y)
+{
+    const int n = C.n, nF = C.nF, nZ = C.nZ, nX = C.nX;
+    Hmul(C, C.x, C.t1);
+    if (recompute_y && (nX + nF - nZ) > 0) {
+        for (int i = threadIdx.x; i < n; i += NT) C.t2[i] = C.t1[i] + C.gcur[i];
+        __syncthreads();
+        if (nF > nZ) {
+            gatherF(C, C.t2);
+            Qtmul(C, C.gF, C.tF, nZ, nF);
+            tsolve(C, nZ, nF, C.tF, C.yW);
+        }
+        if (nX > 0) {
+            ATmul(C, C.yW, nullptr, C.t3);
+            for (int k = threadIdx.x; k < nX; k += NT) { const int j = C.xvar[k]; C.yX[k] = (C.t2[j] - C.t3[j]) / C.xcv[k]; }
+            __syncthreads();
+        }
+    }
+    for (int r = nZ + threadIdx.x; r < nF; r += NT) {
+        int c = C.widx[r];
+        if (lb_new(C, c) != ub_new(C, c)) {
+            if (C.st[c] < 0 && C.yW[r] < 0) C.yW[r] = 0;
+            if (C.st[c] > 0 && C.yW[r] > 0) C.yW[r] = 0;
+        }
+    }
+    for (int k = threadIdx.x; k < nX; k += NT) {
+        int c = C.xcon[k];
+        if (lb_new(C, c) != ub_new(C, c)) {
+            if (C.st[c] < 0 && C.yX[k] < 0) C.yX[k] = 0;
+            if (C.st[c] > 0 && C.yX[k] > 0) C.yX[k] = 0;
+        }
+    }
+    __syncthreads();
+    ATmul(C, C.yW, C.yX, C.t3);
+    for (int j = threadIdx.x; j < n; j += NT) C.gcur[j] = C.t3[j] - C.t1[j];
+    __syncthreads();
+}
+
+// compact free part of row c into aF (and its full squared norm)
+template <class CT> __device__ double get_rowF(CT& C, int c, double* aF)
+{
+    const RowW rd = row_load(C, c);
+    double s2 = 0;
+    for (int j = threadIdx.x; j < C.n; j += NT) {
+        const double v = s_entry(C, rd, j);
+        s2 += v * v;
+        const int f = C.fpos[j];
+        if (f >= 0) aF[f] = v;
+    }
+    s2 = block_sum(C, s2);
+    __syncthreads();
+    return s2;
+}
+
+// see oracle/qp_oracle.c:resolve_pending
+template <class CT> __device__ int resolve_pending(CT& C, int c_out, int side_out, unsigned long long& n_exch, bool zero_step)
+{
+    const int n = C.n, mt = C.mt;
+    bool first = true, moved = false;
+    for (;;) {
+        const int kpd = C.nZ - 1;
+        if (kpd < 0) break;
+        const int nF = C.nF;
+        double *zf = C.t4, *hz = C.t1, *d = C.dx;
+        for (int i = threadIdx.x; i < n; i += NT) zf[i] = 0.0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < nF; i += NT) zf[C.flist[i]] = QF(i, kpd);
+        __syncthreads();
+        Hmul(C, zf, hz);
+        double zhz = 0;
+        for (int i = threadIdx.x; i < n; i += NT) zhz += zf[i] * hz[i];
+        zhz = block_sum(C, zhz);
+        gatherF(C, hz);
+        Qtmul(C, C.gF, C.tF, 0, kpd);
+        tsolve(C, 0, kpd, C.tF, C.pF);           // r = R'^-1 Z'Hz
+        double rr = 0;
+        for (int j = threadIdx.x; j < kpd; j += NT) rr += C.pF[j] * C.pF[j];
+        rr = block_sum(C, rr);
+        double rho2 = zhz - rr;
+        if (rho2 > EPS_PD * C.hscale) {
+            for (int j = threadIdx.x; j < kpd; j += NT) MM(j, kpd) = C.pF[j];
+            if (threadIdx.x == 0) MM(kpd, kpd) = sqrt(rho2);
+            __syncthreads();
+            break;
+        }
+        for (int j = threadIdx.x; j < kpd; j += NT) C.tF[j] = C.pF[j];
+        __syncthreads();
+        usolve(C, 0, kpd, C.tF, C.uF);           // q
+        Qmul(C, C.uF, 0, kpd, C.pF);             // Z q (compact)
+        for (int i = threadIdx.x; i < n; i += NT) d[i] = 0.0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < nF; i += NT) { const int j = C.flist[i]; d[j] = zf[j] - C.pF[i]; }
+        __syncthreads();
+        double sgn = 0;
+        if (first) {
+            get_row(C, c_out, C.t2);
+            for (int i = threadIdx.x; i < n; i += NT) sgn += C.t2[i] * d[i];
+            sgn = block_sum(C, sgn);
+            if (side_out > 0) sgn = -sgn;
+        } else {
+            Hmul(C, C.x, hz);
+            for (int i = threadIdx.x; i < n; i += NT) sgn -= (hz[i] + C.gcur[i]) * d[i];
+            sgn = block_sum(C, sgn);
+        }
+        if (sgn < 0) { __syncthreads(); for (int i = threadIdx.x; i < n; i += NT) d[i] = -d[i]; __syncthreads(); }
+        Amul(C, d, C.Adx);
+        double dn = 0;
+        for (int i = threadIdx.x; i < n; i += NT) dn += d[i] * d[i];
+        dn = sqrt(block_sum(C, dn));
+        double tmin = INFINITY; int key = 0x7fffffff;
+        for (int cc = threadIdx.x; cc < mt; cc += NT) {
+            if (C.st[cc] != 0 || C.anorm[cc] == 0.0f) continue;
+            double adx = C.Adx[cc];
+            const double rz = EPS_ROW * C.anorm[cc] * dn;
+            if (adx < -rz && !isinf(C.lbc[cc])) {
+                double sl = C.Ax[cc] - C.lbc[cc]; if (sl < 0) sl = 0;
+                double t = sl / (-adx);
+                int k = 2 * cc;
+                if (t < tmin || (t == tmin && k < key)) { tmin = t; key = k; }
+            } else if (adx > rz && !isinf(C.ubc[cc])) {
+                double sl = C.ubc[cc] - C.Ax[cc]; if (sl < 0) sl = 0;
+                double t = sl / adx;
+                int k = 2 * cc + 1;
+                if (t < tmin || (t == tmin && k < key)) { tmin = t; key = k; }
+            }
+        }
+        block_argmin(C, tmin, key);
+        if (key == 0x7fffffff) return EEPACC_QP_UNBOUNDED;
+        const int j = key >> 1, jside = (key & 1) ? 1 : -1;
+        for (int i = threadIdx.x; i < n; i += NT) C.x[i] += tmin * d[i];
+        for (int cc = threadIdx.x; cc < mt; cc += NT) C.Ax[cc] += tmin * C.Adx[cc];
+        __syncthreads();
+        if (threadIdx.x == 0) { if (jside < 0) C.lbc[j] = C.Ax[j]; else C.ubc[j] = C.Ax[j]; }
+        const double an2 = get_rowF(C, j, C.gF);
+        givens_add(C, j, jside, C.gF, an2, kpd + 1, kpd, false);
+        if (threadIdx.x == 0) { C.yW[kpd] = 0.0; if (zero_step) C.tabu[j] = 1; }
+        __syncthreads();
+        n_exch++;
+        first = false; moved = true;
+    }
+    if (moved) reanchor(C, true);
+    return 0;
+}
+
+// Warm start: rebuild the factorisation for the kept working set under the NEW data.
+// Unit rows -> fixed variables (X list, stored order kept, a second unit row on the same variable
+// is dropped); general rows -> Householder QR of A_gF' (nF x nG):  A_gF' = Qh [Rh; 0],
+// Qf = Qh with reversed columns, T(r, c) = Rh(nF-1-c, nF-1-r).  Rows whose new bound is infinite
+// or that became linearly dependent are dropped.  Returns 1 if nF exceeds the capacity.
+template <class CT> __device__ int warm_setup(CT& C, int old_nA, const short* gidx, const signed char* gside, const double* gy)
+{
+    const int n = C.n, mt = C.mt, m = C.m;
+    for (int c = threadIdx.x; c < mt; c += NT) C.st[c] = 0;
+    short* cand = reinterpret_cast<short*>(C.t1);        // [n] constraint index of general candidates
+    short* tmpc = reinterpret_cast<short*>(C.t3);        // classification scratch: [3n] shorts
+    double* tmpv = C.t2;                                 // [n] unit coefficient
+    double* ycand = C.t4;                                // [n] dual of general candidates
+    double* v0a = C.csA;                                 // v0 of every reflector
+    double* beta = C.snA;                                // 2 / v'v
+    double* rdiag = C.sub;                               // Rh(k,k)
+    double* cn2 = C.dbw;                                 // squared norm of the original row
+    __syncthreads();
+    // 1. classify the stored working set in parallel (position k was stored at index n-1-k)
+    for (int k = threadIdx.x; k < old_nA; k += NT) {
+        const int r = n - 1 - k;
+        const int c = gidx[r], sd = gside[r];
+        const double bnd = sd < 0 ? lb_new(C, c) : ub_new(C, c);
+        int jv = -1; double cv = 0.0; const int ok = !isinf(bnd);
+        if (ok) {
+            const RowW rd = row_load(C, c);
+            if (!s_unit(C, rd, jv, cv)) jv = -1;
+        }
+        tmpc[3 * k] = (short)(ok ? c : -1); tmpc[3 * k + 1] = (short)jv; tmpc[3 * k + 2] = (short)sd;
+        tmpv[k] = cv;
+    }
+    for (int j = threadIdx.x; j < n; j += NT) C.fpos[j] = 0;
+    __syncthreads();
+    // thread 0: X list, general candidates, free list
+    if (threadIdx.x == 0) {
+        int nx = 0, ng = 0;
+        for (int k = 0; k < old_nA; ++k) {
+            const int c = tmpc[3 * k], jv = tmpc[3 * k + 1];
+            if (c < 0) continue;
+            if (jv >= 0) {
+                if (C.fpos[jv] < 0) continue;             // coordinate already pinned: dependent, drop
+                C.xvar[nx] = (short)jv; C.xcon[nx] = (short)c; C.xcv[nx] = tmpv[k]; C.yX[nx] = gy[n - 1 - k];
+                C.fpos[jv] = (short)(-1 - nx);
+                C.st[c] = (signed char)tmpc[3 * k + 2];
+                ++nx;
+            } else {
+                cand[ng] = (short)c; ycand[ng] = gy[n - 1 - k]; C.st[c] = (signed char)tmpc[3 * k + 2];
+                ++ng;
+            }
+        }
+        int nf = 0;
+        for (int j = 0; j < n; ++j)
+            if (C.fpos[j] >= 0) { if (nf < C.fc) C.flist[nf] = (short)j; C.fpos[j] = (short)nf; ++nf; }
+        C.ired[4] = ng; C.ired[5] = nx; C.ired[6] = nf;
+    }
+    __syncthreads();
+    int cnt = C.ired[4];
+    const int nX = C.ired[5], nF = C.ired[6];
+    PH(1);
+    C.nX = nX; C.nF = nF;
+    if (nF > C.fc) return 1;
+    if (cnt > nF) {                                       // more general rows than free variables: the tail is dependent
+        __syncthreads();
+        for (int k = nF + threadIdx.x; k < cnt; k += NT) C.st[cand[k]] = 0;
+        cnt = nF;
+        __syncthreads();
+    }
+    // 2. stage the general rows (free part) as columns of W (= Qf storage)
+    for (int k = threadIdx.x; k < cnt; k += NT) {
+        const RowW rd = row_load(C, cand[k]);
+        double s2 = 0;
+        for (int j = 0; j < n; ++j) {
+            const double v = s_entry(C, rd, j);
+            s2 += v * v;
+            const int f = C.fpos[j];
+            if (f >= 0) QF(f, k) = v;
+        }
+        cn2[k] = s2;
+    }
+    __syncthreads();
+    PH(2);
+    // 3. Householder QR; a dependent column is swapped with the last and dropped
+    int k = 0;
+    while (k < cnt) {
+        double s2 = 0;
+        for (int i = k + threadIdx.x; i < nF; i += NT) s2 += QF(i, k) * QF(i, k);
+        s2 = block_sum(C, s2);
+        const double ref = cn2[k] > 1.0 ? cn2[k] : 1.0;
+        if (!(s2 > EPS_LI * EPS_LI * ref)) {
+            const int last = cnt - 1;
+            __syncthreads();
+            if (threadIdx.x == 0) C.st[cand[k]] = 0;
+            __syncthreads();
+            if (k != last) {
+                for (int i = threadIdx.x; i < nF; i += NT) QF(i, k) = QF(i, last);
+                if (threadIdx.x == 0) { cand[k] = cand[last]; ycand[k] = ycand[last]; cn2[k] = cn2[last]; }
+            }
+            cnt = last;
+            __syncthreads();
+            continue;
+        }
+        const double sigma = sqrt(s2), x0 = QF(k, k);
+        const double alpha = (x0 >= 0.0) ? -sigma : sigma;
+        const double v0 = x0 - alpha;
+        const double bt = 1.0 / (s2 - x0 * alpha);
+        __syncthreads();
+        for (int j = k + 1 + threadIdx.x; j < cnt; j += NT) {
+            double d = v0 * QF(k, j), d1 = 0, d2 = 0, d3 = 0;
+            int i = k + 1;
+            for (; i + 3 < nF; i += 4) {
+                d += QF(i, k) * QF(i, j); d1 += QF(i + 1, k) * QF(i + 1, j);
+                d2 += QF(i + 2, k) * QF(i + 2, j); d3 += QF(i + 3, k) * QF(i + 3, j);
+            }
+            for (; i < nF; ++i) d += QF(i, k) * QF(i, j);
+            d = ((d + d1) + (d2 + d3)) * bt;
+            QF(k, j) -= d * v0;
+            for (int i2 = k + 1; i2 < nF; ++i2) QF(i2, j) -= d * QF(i2, k);
+        }
+        if (threadIdx.x == 0) { v0a[k] = v0; beta[k] = bt; rdiag[k] = alpha; }
+        __syncthreads();
+        ++k;
+    }
+    PH(3);
+    const int nAC = cnt, nZ = nF - nAC;
+    // 4. T block of M from Rh:  M(r, c) = Rh(nF-1-c, nF-1-r),  c >= r >= nZ
+    for (int r = nZ + threadIdx.x; r < nF; r += NT) {
+        const int b = nF - 1 - r;
+        for (int c = r; c < nF; ++c) {
+            const int a = nF - 1 - c;
+            MM(r, c) = (a == b) ? rdiag[a] : QF(a, b);
+        }
+    }
+    __syncthreads();
+    // 5. form Qh: backward accumulation of the reflectors
+    for (int j = nAC + threadIdx.x; j < nF; j += NT)
+        for (int i = 0; i < nF; ++i) QF(i, j) = (i == j) ? 1.0 : 0.0;
+    __syncthreads();
+    for (int kk = nAC - 1; kk >= 0; --kk) {
+        const double v0 = v0a[kk], bt = beta[kk];
+        for (int j = kk + 1 + threadIdx.x; j < nF; j += NT) {
+            double d = v0 * QF(kk, j), d1 = 0, d2 = 0, d3 = 0;
+            int i = kk + 1;
+            for (; i + 3 < nF; i += 4) {
+                d += QF(i, kk) * QF(i, j); d1 += QF(i + 1, kk) * QF(i + 1, j);
+                d2 += QF(i + 2, kk) * QF(i + 2, j); d3 += QF(i + 3, kk) * QF(i + 3, j);
+            }
+            for (; i < nF; ++i) d += QF(i, kk) * QF(i, j);
+            d = ((d + d1) + (d2 + d3)) * bt;
+            QF(kk, j) -= d * v0;
+            for (int i2 = kk + 1; i2 < nF; ++i2) QF(i2, j) -= d * QF(i2, kk);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < nF; i += NT) {
+            double vi = QF(i, kk);
+            QF(i, kk) = (i < kk) ? 0.0 : (i == kk) ? 1.0 - bt * v0 * v0 : -bt * v0 * vi;
+        }
+        __syncthreads();
+    }
+    // 6. reverse the columns, 7. working-set bookkeeping by Qf column
+    for (int i = threadIdx.x; i < nF; i += NT)
+        for (int c = 0; c < nF / 2; ++c) { double a = QF(i, c), b = QF(i, nF - 1 - c); QF(i, c) = b; QF(i, nF - 1 - c) = a; }
+    for (int kq = threadIdx.x; kq < nAC; kq += NT) { C.yW[nF - 1 - kq] = ycand[kq]; C.widx[nF - 1 - kq] = cand[kq]; }
+    C.nZ = nZ;
+    __syncthreads();
+    PH(4);
+    return 0;
+}
+
+// all variables fixed at their (relaxed) lower far bound; position k <-> variable n-1-k (k3_qp.cu order)
+template <class CT> __device__ void cold_ws(CT& C)
+{
+    const int n = C.n, m = C.m, mt = C.mt;
+    __syncthreads();
+    for (int c = threadIdx.x; c < mt; c += NT) C.st[c] = 0;
+    __syncthreads();
+    for (int k = threadIdx.x; k < n; k += NT) {
+        const int v = n - 1 - k;
+        C.xvar[k] = (short)v; C.xcon[k] = (short)(m + v); C.xcv[k] = 1.0;
+        C.fpos[v] = (short)(-1 - k);
+        C.st[m + v] = -1;
+        C.yX[k] = 0.5 + 0.5 * (double)(m + v) / (double)mt;   // distinct initial duals ("ramping")
+    }
+    C.nX = n; C.nF = 0; C.nZ = 0;
+    __syncthreads();
+}
+
+// auxiliary QP for which the current (x, y, working set) is optimal: relaxed bounds + anchored gradient
+template <class CT> __device__ void setup_aux(CT& C)
+{
+    const int mt = C.mt;
+    Amul(C, C.x, C.Ax);
+    for (int c = threadIdx.x; c < mt; c += NT) {
+        int s = C.st[c];
+        double ax = C.Ax[c], ln = lb_new(C, c), un = ub_new(C, c);
+        bool eq = ln == un;
+        if (s < 0) { C.lbc[c] = ax; C.ubc[c] = eq ? ax : (isinf(un) ? INFINITY : ax + RELAX); }
+        else if (s > 0) { C.ubc[c] = ax; C.lbc[c] = eq ? ax : (isinf(ln) ? -INFINITY : ax - RELAX); }
+        else { C.lbc[c] = isinf(ln) ? -INFINITY : ax - RELAX; C.ubc[c] = isinf(un) ? INFINITY : ax + RELAX; }
+    }
+    __syncthreads();
+    reanchor(C, false);
+}
+
+}  // namespace k3r
+
+extern "C" __host__ __device__ size_t eep_qpr_smem_bytes(int n, int m, int fc);
+#ifndef EEP_HOST_EMU
+extern __shared__ __align__(16) unsigned char k3r_smem[];
+#endif
+
+// ---- row table builder (once per set-up; also runs on the host in the emulation build) ----
+// consts[96] = cvals[32] (control coefficients, [0] = 1), cva[32], cvb[32] (coefficient on v_k = a + b v_est(k)).
+// Returns 0, or a positive code if a row does not fit the encoding (set-up then fails loudly).
+__device__ int k3r_build_rowtab(int ctrl, const eepacc_params& p, int m, unsigned long long* tab, double* consts)
+{
+    const int NH = EEP_N, nu = (ctrl == EEPACC_FB) ? 6 : (ctrl == EEPACC_AB) ? 5 : 2;
+    double* cvals = consts; double* cva = consts + 32; double* cvb = consts + 64;
+    for (int i = 0; i < 96; ++i) consts[i] = 0.0;
+    int ncv = 1, npair = 1;
+    cvals[0] = 1.0;
+    double ve0[NH + 1], ve1[NH + 1], ve2[NH + 1];
+    const double big = 1048576.0;
+    for (int i = 0; i <= NH; ++i) { ve0[i] = 0.0; ve1[i] = big; ve2[i] = 3.0; }
+    k3r::VestSrc s0{ ve0 }, s1{ ve1 }, s2{ ve2 };
+    for (int c = 0; c < m; ++c) {
+        RowDesc r0, r1, r2;
+        eep_row<false>(ctrl, p, 1.0, s0, c, r0);
+        eep_row<false>(ctrl, p, 1.0, s1, c, r1);
+        eep_row<false>(ctrl, p, 1.0, s2, c, r2);
+        if (r0.kst != r1.kst || r0.nctl != r1.nctl || r0.cS != r1.cS) return 1;
+        if (r0.cv0 != r1.cv0 || r0.cv1 != r1.cv1 || r0.cv2 != r1.cv2) return 2;          // control coefficients must not depend on v_est
+        if (!(r0.cS == 0.0 || r0.cS == 1.0)) return 3;
+        if (r0.kst < -2 || r0.kst > NH) return 4;
+        int aux = 0;
+        if (r0.kst >= 0) {
+            const double a = r0.cV, b = (r1.cV - r0.cV) / big;
+            if (fabs(r2.cV - (a + b * 3.0)) > 1e-12 * (1.0 + fabs(r2.cV))) return 5;      // must be affine in v_est(k)
+            int id = -1;
+            for (int q = 0; q < npair; ++q) if (cva[q] == a && cvb[q] == b) { id = q; break; }
+            if (id < 0) { if (npair >= 32) return 6; id = npair++; cva[id] = a; cvb[id] = b; }
+            aux = id | (r0.cS != 0.0 ? 128 : 0);
+        } else if (r0.kst == -2) {
+            aux = r0.cj0 / nu - 1;
+            if (aux < 0 || aux >= NH || r0.cV != 0.0 || r0.cS != 0.0) return 7;
+        } else if (r0.cV != 0.0 || r0.cS != 0.0) return 8;
+        const int cj[3] = { r0.cj0, r0.cj1, r0.cj2 };
+        const double cv[3] = { r0.cv0, r0.cv1, r0.cv2 };
+        unsigned long long w = (unsigned long long)(unsigned char)(signed char)r0.kst | ((unsigned long long)aux << 8);
+        for (int e = 0; e < 3; ++e) {
+            int jj = 255, id = 0;
+            if (e < r0.nctl) {
+                jj = cj[e];
+                if (jj < 0 || jj >= 255) return 9;
+                id = -1;
+                for (int q = 0; q < ncv; ++q) if (cvals[q] == cv[e]) { id = q; break; }
+                if (id < 0) { if (ncv >= 32) return 10; id = ncv++; cvals[id] = cv[e]; }
+            }
+            w |= (unsigned long long)jj << (16 + 8 * e);
+            w |= (unsigned long long)id << (40 + 8 * e);
+        }
+        tab[c] = w;
+    }
+    return 0;
+}
+
+template <int NU, int NB>
+__device__ __forceinline__ void k3r_body(const eep_qp_io& io, unsigned char* k3r_smem)
+{
+    using namespace k3r;
+    typedef CtxT<NU, NB> CT;
+    CT C;
+    const int n = io.n, m = io.m, mt = n + m, fc = io.fc;
+    C.n = n; C.m = m; C.mt = mt; C.fc = fc; C.ldq = (fc + 1) | 1;
+    double *gS, *lnS, *unS;
+    {
+        double* p = reinterpret_cast<double*>(k3r_smem);
+        C.Q = p; p += (size_t)(fc + 1) * C.ldq;
+        C.M = p; p += (size_t)fc * (fc + 1) / 2 + fc + 2;
+        C.sub = p; p += fc + 2;
+        C.x = p; p += n; C.gcur = p; p += n; C.dx = p; p += n; C.dg = p; p += n;
+        C.t1 = p; p += n; C.t2 = p; p += n; C.t3 = p; p += n; C.t4 = p; p += n;
+        C.yX = p; p += n; C.dyX = p; p += n; C.xcv = p; p += n; C.dbX = p; p += n;
+        gS = p; p += n;
+        C.yW = p; p += fc + 1; C.dyW = p; p += fc + 1; C.dbw = p; p += fc + 1; C.wv = p; p += fc + 1;
+        C.csA = p; p += fc + 1; C.snA = p; p += fc + 1; C.pF = p; p += fc + 1; C.uF = p; p += fc + 1;
+        C.tF = p; p += fc + 1; C.gF = p; p += fc + 1;
+        C.Ax = p; p += mt; C.lbc = p; p += mt; C.ubc = p; p += mt; C.Adx = p; p += mt;
+        lnS = p; p += mt; unS = p; p += mt;
+        C.anorm = reinterpret_cast<float*>(p); p += (mt + 1) / 2;
+        const int NH = EEP_N;
+        C.PS = p; p += (NH + 1) * NH; C.PV = p; p += (NH + 1) * NH; C.vest = p; p += NH + 1;
+        C.Dc = p; p += NH * 9; C.Cc = p; p += NH * 9; C.Dg = p; p += NH * 4;
+        C.sv = p; p += NH + 1; C.vv = p; p += NH + 1; C.drv = p; p += NH; C.yc = p; p += NH * 3;
+        C.aS = p; p += NH + 1; C.aV = p; p += NH + 1; C.aD = p; p += NH;
+        C.rS = p; p += fc + 1; C.rV = p; p += fc + 1; C.rv0 = p; p += fc + 1; C.rv1 = p; p += fc + 1; C.rv2 = p; p += fc + 1;
+        C.red = p; p += 8;
+        C.ired = reinterpret_cast<int*>(p); p += 4;      // 8 ints
+        double* cst = p; p += 96;
+        unsigned long long* rt = reinterpret_cast<unsigned long long*>(p); p += m;
+        C.g = gS; C.lnw = lnS; C.unw = unS; C.rtab = rt; C.cvals = cst; C.cva = cst + 32; C.cvb = cst + 64;
+        short* sp = reinterpret_cast<short*>(p);
+        C.rk = sp; sp += fc + 1; C.rj0 = sp; sp += fc + 1; C.rj1 = sp; sp += fc + 1; C.rj2 = sp; sp += fc + 1; C.rj3 = sp; sp += fc + 1;
+        C.flist = sp; sp += fc + 1; C.widx = sp; sp += fc + 1;
+        C.fpos = sp; sp += n; C.xvar = sp; sp += n; C.xcon = sp; sp += n;
+        C.st = reinterpret_cast<signed char*>(sp);
+        C.tabu = C.st + mt;
+#ifdef EEP_K3_TIMERS
+        C.ph = reinterpret_cast<long long*>(k3r_smem + ((eep_qpr_smem_bytes(n, m, fc) - 34 * 8) & ~(size_t)7));
+#endif
+        // per-controller tables and the far bounds: the same for every vehicle this CTA solves
+        for (int e = threadIdx.x; e < m; e += NT) rt[e] = io.rowtab[e];
+        for (int e = threadIdx.x; e < 96; e += NT) cst[e] = io.rowc[e];
+        for (int c = m + threadIdx.x; c < mt; c += NT) { lnS[c] = -FARB; unS[c] = FARB; }
+        if (threadIdx.x == 0) C.vest[NH] = 0.0;
+    }
+    for (long long veh = blockIdx.x; veh < io.B; veh += gridDim.x) {
+        __syncthreads();
+        int status = EEPACC_QP_OK, iter = 0;
+        const int max_iter = 5 * (n + m);
+        const int restart_after = (4 * n > 400 ? 4 * n : 400);
+        unsigned long long n_exch = 0, n_refac = 0;
+#ifdef EEP_K3_TIMERS
+        if (threadIdx.x == 0) { for (int q = 0; q < 32; ++q) C.ph[q] = 0; C.ph[32] = clock64(); }
+#endif
+
+        // gradient, bounds, structured block, Hessian scale, LP regularisation, row norms
+        {
+            const double* gg = io.g + veh * (size_t)n;
+            const double* la = io.lba + veh * (size_t)m;
+            const double* ua = io.uba + veh * (size_t)m;
+            for (int i = threadIdx.x; i < n; i += NT) gS[i] = gg[i];
+            for (int c = threadIdx.x; c < m; c += NT) {
+                const double l = la[c], u = ua[c];
+                lnS[c] = (l <= -BIGB) ? -INFINITY : l;
+                unS[c] = (u >= BIGB) ? INFINITY : u;
+            }
+            const double* sb = io.sblk + veh * (size_t)EEP_SBLK;
+            for (int e = threadIdx.x; e < (EEP_N + 1) * EEP_N; e += NT) { C.PS[e] = sb[EEP_SB_PS + e]; C.PV[e] = sb[EEP_SB_PV + e]; }
+            for (int e = threadIdx.x; e < EEP_N * 9; e += NT) { C.Dc[e] = sb[EEP_SB_DC + e]; C.Cc[e] = sb[EEP_SB_CC + e]; }
+            for (int e = threadIdx.x; e < EEP_N * 4; e += NT) C.Dg[e] = sb[EEP_SB_DG + e];
+            for (int e = threadIdx.x; e < EEP_N; e += NT) C.vest[e] = sb[EEP_SB_VEST + e];
+            C.reg = (sb[EEP_SB_HMAX] == 0.0) ? LP_REG : 0.0;
+            C.hscale = fmax(sb[EEP_SB_HSCALE], LP_REG);
+            __syncthreads();
+            for (int r = threadIdx.x; r < m; r += NT) {
+                const RowW rd = row_load(C, r);
+                double sa = 0;
+                if (rd.kst >= 0) {
+                    const double cV = row_cV(C, rd), cS = (rd.aux & 128) ? 1.0 : 0.0;
+                    for (int i = 0; i < rd.kst && i < EEP_N; ++i)
+                        sa += CT::nb * fabs(cS * C.PS[rd.kst * EEP_N + i] + cV * C.PV[rd.kst * EEP_N + i]);
+                }
+                if (rd.j0 != 255) sa += fabs(C.cvals[rd.i0]);
+                if (rd.j1 != 255) sa += fabs(C.cvals[rd.i1]);
+                if (rd.j2 != 255) sa += fabs(C.cvals[rd.i2]);
+                if (rd.kst == -2) sa += CT::nb;
+                C.anorm[r] = (float)sa;
+            }
+        }
+        for (int j = threadIdx.x; j < n; j += NT) C.anorm[m + j] = 1.0f;
+        for (int c = threadIdx.x; c < mt; c += NT) C.tabu[c] = 0;
+        __syncthreads();
+        PH(0);
+
+        // ---------------- set-up ----------------
+        const int was_warm = io.warm[veh];
+        bool need_cold = !was_warm;
+        for (int i = threadIdx.x; i < n; i += NT) C.x[i] = was_warm ? io.wx[veh * (size_t)n + i] : 0.0;
+        if (!need_cold) {
+            if (warm_setup(C, io.wnA[veh], io.widx + veh * (size_t)n, io.wside + veh * (size_t)n, io.wy + veh * (size_t)n))
+                status = K3R_DEFER;
+            else {
+                n_refac++;
+                if (refactor_R(C)) need_cold = true;
+                PH(5);
+            }
+        }
+        if (status == EEPACC_QP_OK) {
+            if (need_cold) cold_ws(C);
+            setup_aux(C);
+        }
+        PH(6);
+
+        // ---------------- homotopy ----------------
+        while (status == EEPACC_QP_OK) {
+            const int nZ = C.nZ, nF = C.nF, nX = C.nX;
+            for (int i = threadIdx.x; i < n; i += NT) C.dg[i] = C.g[i] - C.gcur[i];
+            for (int r = nZ + threadIdx.x; r < nF; r += NT) {
+                int c = C.widx[r];
+                double nb = C.st[c] < 0 ? lb_new(C, c) : ub_new(C, c);
+                double cb = C.st[c] < 0 ? C.lbc[c] : C.ubc[c];
+                C.dbw[r] = isinf(nb) ? 0.0 : nb - cb;
+            }
+            for (int k = threadIdx.x; k < nX; k += NT) {
+                int c = C.xcon[k];
+                double nb = C.st[c] < 0 ? lb_new(C, c) : ub_new(C, c);
+                double cb = C.st[c] < 0 ? C.lbc[c] : C.ubc[c];
+                C.dbX[k] = isinf(nb) ? 0.0 : nb - cb;
+            }
+            __syncthreads();
+            PH(14);
+            kkt_step(C, C.dg, C.dbw, C.dbX, C.dx, C.dyW, C.dyX);
+            Amul(C, C.dx, C.Adx);
+            PH(13);
+
+            double dxmax = 0;
+            for (int i = threadIdx.x; i < n; i += NT) dxmax = fmax(dxmax, fabs(C.dx[i]));
+            dxmax = block_max(C, dxmax);
+            double tau = 1.0; int key = 0x7fffffff;
+            for (int c = threadIdx.x; c < mt; c += NT) {
+                if (C.st[c] != 0 || C.anorm[c] == 0.0f) continue;      // all-zero rows can never be added
+                if (C.tabu[c] == 2) continue;                          // left during this run of zero steps: no re-entry
+                double adx = C.Adx[c];
+                const double rz = EPS_ROW * C.anorm[c] * dxmax;
+                if (!isinf(C.lbc[c])) {
+                    double ln = lb_new(C, c);
+                    double dlb = isinf(ln) ? 0.0 : ln - C.lbc[c];
+                    double rate = adx - dlb;
+                    double sl = C.Ax[c] - C.lbc[c]; if (sl < 0) sl = 0;
+                    if (rate < -(EPS_RATE * (1.0 + fabs(adx) + fabs(dlb)) + rz) &&
+                        -rate - sl > FEAS_TOL * (1.0 + fabs(ln))) {
+                        double t = sl / (-rate);
+                        int k = 2 * c;
+                        if (t < tau || (t == tau && k < key && t < 1.0)) { tau = t; key = k; }
+                    }
+                }
+                if (!isinf(C.ubc[c])) {
+                    double un = ub_new(C, c);
+                    double dub = isinf(un) ? 0.0 : un - C.ubc[c];
+                    double rate = dub - adx;
+                    double sl = C.ubc[c] - C.Ax[c]; if (sl < 0) sl = 0;
+                    if (rate < -(EPS_RATE * (1.0 + fabs(adx) + fabs(dub)) + rz) &&
+                        -rate - sl > FEAS_TOL * (1.0 + fabs(un))) {
+                        double t = sl / (-rate);
+                        int k = 2 * c + 1;
+                        if (t < tau || (t == tau && k < key && t < 1.0)) { tau = t; key = k; }
+                    }
+                }
+            }
+            double dys = 0;
+            for (int r = nZ + threadIdx.x; r < nF; r += NT) dys = fmax(dys, fabs(C.dyW[r]));
+            for (int k = threadIdx.x; k < nX; k += NT) dys = fmax(dys, fabs(C.dyX[k]));
+            dys = block_max(C, dys);
+            const double thr = EPS_RATE * (1.0 + dys);
+            // dual ratio test; key = 2*mt + position (X entries are positions 0..nX-1, the general
+            // row of Qf column r is position nX + nF-1-r)
+            for (int q = threadIdx.x; q < nX + (nF - nZ); q += NT) {
+                int c; double yc, dy;
+                if (q < nX) { c = C.xcon[q]; yc = C.yX[q]; dy = C.dyX[q]; }
+                else { const int r = nF - 1 - (q - nX); c = C.widx[r]; yc = C.yW[r]; dy = C.dyW[r]; }
+                if (lb_new(C, c) == ub_new(C, c)) continue;
+                if (C.tabu[c] == 1) continue;            // entered during this run of zero steps: stays
+                int k = 2 * mt + q;
+                if (C.st[c] < 0 && dy < -thr) {
+                    double t = (yc > 0 ? yc : 0) / (-dy);
+                    if (t < tau || (t == tau && k < key && t < 1.0)) { tau = t; key = k; }
+                } else if (C.st[c] > 0 && dy > thr) {
+                    double t = (yc < 0 ? -yc : 0) / dy;
+                    if (t < tau || (t == tau && k < key && t < 1.0)) { tau = t; key = k; }
+                }
+            }
+            block_argmin(C, tau, key);
+            const bool full = !(tau < 1.0) || key == 0x7fffffff;
+            if (full) tau = 1.0;
+            // anti-cycling (see oracle/qp_oracle.c): constraints that enter while the homotopy makes no
+            // progress may not leave through the dual test until it does
+            const bool zero_step = !(tau > 1e-14);
+            if (!zero_step) for (int c = threadIdx.x; c < mt; c += NT) C.tabu[c] = 0;
+
+            // take the step
+            for (int i = threadIdx.x; i < n; i += NT) {
+                C.x[i] += tau * C.dx[i];
+                C.gcur[i] = full ? C.g[i] : C.gcur[i] + tau * C.dg[i];
+            }
+            for (int r = nZ + threadIdx.x; r < nF; r += NT) C.yW[r] += tau * C.dyW[r];
+            for (int k = threadIdx.x; k < nX; k += NT) C.yX[k] += tau * C.dyX[k];
+            for (int c = threadIdx.x; c < mt; c += NT) {
+                C.Ax[c] += tau * C.Adx[c];
+                double ln = lb_new(C, c), un = ub_new(C, c);
+                if (!isinf(ln)) C.lbc[c] = full ? ln : C.lbc[c] + tau * (ln - C.lbc[c]);
+                if (!isinf(un)) C.ubc[c] = full ? un : C.ubc[c] + tau * (un - C.ubc[c]);
+            }
+            __syncthreads();
+            PH(14);
+            if (full) break;
+            if (++iter > max_iter) { status = EEPACC_QP_MAXITER; break; }
+            if (iter == restart_after) {
+                // the warm-started path wanders (degenerate / non-convex stretches): start over from an
+                // all-fixed working set at the current point -- the cold-start path
+                cold_ws(C);
+                setup_aux(C);
+                for (int c = threadIdx.x; c < mt; c += NT) C.tabu[c] = 0;
+                __syncthreads();
+                continue;
+            }
+            if (io.dbg && veh == 0 && threadIdx.x == 0 && iter <= io.dbg_cap) {
+                double* o = io.dbg + (size_t)(iter - 1) * 4;
+                o[0] = tau; o[1] = (double)key; o[2] = (double)(C.nX + C.nF - C.nZ); o[3] = (double)n_exch;
+            }
+
+            if (key < 2 * mt) {
+                // ---------- primal blocking: add constraint ----------
+                const int blk = key >> 1, side = (key & 1) ? 1 : -1;
+                if (threadIdx.x == 0) {
+                    if (side < 0) C.lbc[blk] = C.Ax[blk]; else C.ubc[blk] = C.Ax[blk];
+                    if (zero_step) C.tabu[blk] = 1;
+                }
+                get_row(C, blk, C.t4);                      // full row (the exchange needs its fixed part)
+                double an2 = 0;
+                for (int j = threadIdx.x; j < n; j += NT) an2 += C.t4[j] * C.t4[j];
+                an2 = block_sum(C, an2);
+                gatherF(C, C.t4);
+                const int nZc = C.nZ;
+                if (givens_add(C, blk, side, C.gF, an2, nZc, nZc, true) == 0) {
+                    if (threadIdx.x == 0) C.yW[nZc - 1] = 0.0;
+                    __syncthreads();
+                } else {
+                    // linearly dependent: a = A_W' lam (general rows and fixed variables), exchange by a dual ratio test
+                    const int nFc = C.nF, nXc = C.nX;
+                    double* lamG = C.dyW;                   // by Qf column (dyW / dyX are recomputed by the next KKT step)
+                    double* lamX = C.dyX;
+                    for (int r = nZc + threadIdx.x; r < nFc; r += NT) C.tF[r] = C.wv[r];
+                    __syncthreads();
+                    tsolve(C, nZc, nFc, C.tF, lamG);
+                    ATmul(C, lamG, nullptr, C.t3);
+                    for (int k = threadIdx.x; k < nXc; k += NT) { const int j = C.xvar[k]; lamX[k] = (C.t4[j] - C.t3[j]) / C.xcv[k]; }
+                    __syncthreads();
+                    double lmax = 0;
+                    for (int r = nZc + threadIdx.x; r < nFc; r += NT) lmax = fmax(lmax, fabs(lamG[r]));
+                    for (int k = threadIdx.x; k < nXc; k += NT) lmax = fmax(lmax, fabs(lamX[k]));
+                    lmax = block_max(C, lmax);
+                    double theta = INFINITY; int kk = 0x7fffffff;
+                    for (int q = threadIdx.x; q < nXc + (nFc - nZc); q += NT) {
+                        int c; double yc, lr;
+                        if (q < nXc) { c = C.xcon[q]; yc = C.yX[q]; lr = lamX[q]; }
+                        else { const int r = nFc - 1 - (q - nXc); c = C.widx[r]; yc = C.yW[r]; lr = lamG[r]; }
+                        if (lb_new(C, c) == ub_new(C, c)) continue;
+                        double l = (side < 0) ? lr : -lr;
+                        if (fabs(l) <= 1e-11 * (1.0 + lmax)) continue;
+                        if (C.st[c] < 0 && l > 0) {
+                            double th = (yc > 0 ? yc : 0) / l;
+                            if (th < theta || (th == theta && q < kk)) { theta = th; kk = q; }
+                        } else if (C.st[c] > 0 && l < 0) {
+                            double th = (yc < 0 ? yc : 0) / l;
+                            if (th < theta || (th == theta && q < kk)) { theta = th; kk = q; }
+                        }
+                    }
+                    block_argmin(C, theta, kk);
+                    if (kk == 0x7fffffff) { status = EEPACC_QP_INFEASIBLE; break; }
+                    for (int r = nZc + threadIdx.x; r < nFc; r += NT) C.yW[r] -= theta * ((side < 0) ? lamG[r] : -lamG[r]);
+                    for (int k = threadIdx.x; k < nXc; k += NT) C.yX[k] -= theta * ((side < 0) ? lamX[k] : -lamX[k]);
+                    __syncthreads();
+                    if (kk < nXc) {
+                        if (threadIdx.x == 0 && zero_step) C.tabu[C.xcon[kk]] = 2;
+                        __syncthreads();
+                        if (free_var(C, kk)) { status = K3R_DEFER; break; }
+                    } else {
+                        const int rp = nFc - 1 - (kk - nXc);
+                        if (threadIdx.x == 0 && zero_step) C.tabu[C.widx[rp]] = 2;
+                        __syncthreads();
+                        remove_general(C, rp);
+                    }
+                    // new T row over the range space of the freed column; R untouched
+                    const int rn = C.nZ - 1;                 // freed column
+                    gatherF(C, C.t4);
+                    Qtmul(C, C.gF, C.tF, rn, C.nF);
+                    for (int c = rn + threadIdx.x; c < C.nF; c += NT) MM(rn, c) = C.tF[c];
+                    if (threadIdx.x == 0) {
+                        C.widx[rn] = (short)blk; C.st[blk] = (signed char)side;
+                        C.yW[rn] = (side < 0) ? theta : -theta;
+                    }
+                    C.nZ = rn;
+                    __syncthreads();
+                    n_exch++;
+                }
+                PH(15);
+            } else {
+                // ---------- dual blocking: remove constraint ----------
+                const int q = key - 2 * mt;
+                int c, side;
+                __syncthreads();
+                if (q < nX) {
+                    c = C.xcon[q]; side = C.st[c];
+                    __syncthreads();
+                    if (threadIdx.x == 0 && zero_step) C.tabu[c] = 2;
+                    if (free_var(C, q)) { status = K3R_DEFER; break; }
+                } else {
+                    const int rp = nF - 1 - (q - nX);
+                    c = C.widx[rp]; side = C.st[c];
+                    __syncthreads();
+                    if (threadIdx.x == 0 && zero_step) C.tabu[c] = 2;
+                    remove_general(C, rp);
+                }
+                int rc = resolve_pending(C, c, side, n_exch, zero_step);
+                PH(16);
+                if (rc) { status = rc; break; }
+            }
+        }
+
+        if (status == K3R_DEFER) {
+            // untouched warm state: the full-space kernel solves this vehicle from scratch
+            if (threadIdx.x == 0) {
+#ifdef EEP_HOST_EMU
+                io.defer_list[(*io.defer_cnt)++] = (int)veh;
+#else
+                io.defer_list[atomicAdd(io.defer_cnt, 1)] = (int)veh;
+#endif
+            }
+            continue;
+        }
+
+        // ---------------- iterative refinement on the final working set ----------------
+        if (status == EEPACC_QP_OK) {
+            const int nZ = C.nZ, nF = C.nF, nX = C.nX;
+            Amul(C, C.x, C.Adx);
+            Hmul(C, C.x, C.t4);
+            ATmul(C, C.yW, C.yX, C.t3);
+            // rg = Hx + g - A_W' y ; rb = bound - a'x
+            for (int j = threadIdx.x; j < n; j += NT) C.dg[j] = C.t4[j] + C.g[j] - C.t3[j];
+            for (int r = nZ + threadIdx.x; r < nF; r += NT) {
+                const int c = C.widx[r];
+                C.dbw[r] = (C.st[c] < 0 ? C.lbc[c] : C.ubc[c]) - C.Adx[c];
+            }
+            for (int k = threadIdx.x; k < nX; k += NT) {
+                const int c = C.xcon[k];
+                C.dbX[k] = (C.st[c] < 0 ? C.lbc[c] : C.ubc[c]) - C.Adx[c];
+            }
+            __syncthreads();
+            PH(17);
+            kkt_step(C, C.dg, C.dbw, C.dbX, C.dx, C.dyW, C.dyX);
+            for (int i = threadIdx.x; i < n; i += NT) C.x[i] += C.dx[i];
+            for (int r = nZ + threadIdx.x; r < nF; r += NT) C.yW[r] += C.dyW[r];
+            for (int k = threadIdx.x; k < nX; k += NT) C.yX[k] += C.dyX[k];
+            __syncthreads();
+        }
+        PH(17);
+
+        // ---------------- outputs + warm-start state ----------------
+        {
+            Hmul(C, C.x, C.t1);
+            double s = 0;
+            for (int i = threadIdx.x; i < n; i += NT) s += C.x[i] * (0.5 * (C.t1[i] - C.reg * C.x[i]) + C.g[i]);
+            s = block_sum(C, s);
+            const int nZ = C.nZ, nF = C.nF, nX = C.nX, nA = nX + nF - nZ;
+            if (status == EEPACC_QP_OK) {
+                int far = 0;
+                for (int r = nZ + threadIdx.x; r < nF; r += NT) { int c = C.widx[r]; if (c >= m && fabs(C.x[c - m]) >= FARB) far = 1; }
+                for (int k = threadIdx.x; k < nX; k += NT) { int c = C.xcon[k]; if (c >= m && fabs(C.x[c - m]) >= FARB) far = 1; }
+                if (block_max(C, (double)far) > 0) status = EEPACC_QP_UNBOUNDED;
+                int zr = 0;         // an all-zero row with inconsistent bounds: infeasible QP
+                for (int c = threadIdx.x; c < m; c += NT)
+                    if (C.anorm[c] == 0.0 && (lb_new(C, c) > 1e-8 || ub_new(C, c) < -1e-8)) zr = 1;
+                if (block_max(C, (double)zr) > 0) status = EEPACC_QP_INFEASIBLE;
+            }
+            // warm-start state in the layout of k3_qp.cu: position q lives at index n-1-q
+            for (int i = threadIdx.x; i < n; i += NT) {
+                io.x[veh * (size_t)n + i] = C.x[i];
+                io.wx[veh * (size_t)n + i] = C.x[i];
+                const int q = n - 1 - i;
+                double yv = 0.0; short ci = -1; signed char sd = 0;
+                if (q < nX) { yv = C.yX[q]; ci = C.xcon[q]; sd = C.st[ci]; }
+                else if (q < nA) { const int r = nF - 1 - (q - nX); yv = C.yW[r]; ci = C.widx[r]; sd = C.st[ci]; }
+                io.wy[veh * (size_t)n + i] = yv;
+                io.widx[veh * (size_t)n + i] = ci;
+                io.wside[veh * (size_t)n + i] = sd;
+            }
+            if (threadIdx.x == 0) {
+                io.cost[veh] = s;
+                io.status[veh] = (double)status;
+                io.iter[veh] = (double)iter;
+                io.wnA[veh] = nA;
+                io.warm[veh] = (status == EEPACC_QP_OK) ? 1 : 0;
+#ifdef EEP_K3_TIMERS
+                PH(18);
+                if (io.dbg && veh == 0) for (int q = 0; q < 28; ++q) io.dbg[(size_t)io.dbg_cap * 4 + q] = (double)C.ph[q];
+#endif
+                if (io.counters) {
+                    io.counters[veh * 4 + 0] += (unsigned long long)iter;
+                    io.counters[veh * 4 + 1] += (status != EEPACC_QP_OK);
+                    io.counters[veh * 4 + 2] += n_exch;
+                    io.counters[veh * 4 + 3] += n_refac;
+                }
+            }
+        }
+    }
+}
+
+template <int NU, int NB>
+__global__ void __launch_bounds__(NT, 2) k3r_qp_kernel(eep_qp_io io EMU_ONLY(, unsigned char* k3r_smem))
+{
+    k3r_body<NU, NB>(io, k3r_smem);
+}
+
+__global__ void k3r_rowtab_kernel(int ctrl, eepacc_params p, int m, unsigned long long* tab, double* consts, int* rc)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) *rc = k3r_build_rowtab(ctrl, p, m, tab, consts);
+}
+
+extern "C" __host__ __device__ size_t eep_qpr_smem_bytes(int n, int m, int fc)
+{
+    const int mt = n + m, ldq = (fc + 1) | 1, NH = EEP_N;
+    size_t d = (size_t)(fc + 1) * ldq + (size_t)fc * (fc + 1) / 2 + fc + 2 + (fc + 2) + 13 * (size_t)n + 10 * (size_t)(fc + 1)
+             + 6 * (size_t)mt + (mt + 1) / 2
+             + 2 * (size_t)(NH + 1) * NH + NH + 1 + 2 * NH * 9 + NH * 4 + 2 * (NH + 1) + NH + NH * 3
+             + 2 * (NH + 1) + NH + 5 * (size_t)(fc + 1) + 8 + 4 + 96 + (size_t)m;
+    size_t shorts = 7 * (size_t)(fc + 1) + 3 * (size_t)n;
+    size_t b = d * 8 + shorts * 2 + 2 * (size_t)mt + 16;
+#ifdef EEP_K3_TIMERS
+    b = ((b + 7) & ~(size_t)7) + 34 * 8;
+#endif
+    return b;
+}
+
+#ifndef EEP_HOST_EMU
+// one-off: packed row table of a controller into device memory; returns 0 or a CUDA / encoding error
+extern "C" int eep_qpr_build_rowtab(int ctrl, const eepacc_params* p, int m, unsigned long long* tab_dev, double* consts_dev, cudaStream_t st)
+{
+    int* rc_dev = nullptr;
+    cudaError_t e = cudaMalloc(&rc_dev, sizeof(int));
+    if (e != cudaSuccess) return (int)e;
+    k3r_rowtab_kernel<<<1, 32, 0, st>>>(ctrl, *p, m, tab_dev, consts_dev, rc_dev);
+    int rc = -1;
+    e = cudaMemcpyAsync(&rc, rc_dev, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(rc_dev);
+    if (e != cudaSuccess) return (int)e;
+    return rc ? 100000 + rc : 0;
+}
+
+template <int NU, int NB>
+static int launch_qpr(const eep_qp_io* io, cudaStream_t st)
+{
+    const size_t sm = eep_qpr_smem_bytes(io->n, io->m, io->fc);
+    static size_t attr_for = 0;
+    if (sm > attr_for) {
+        cudaError_t e = cudaFuncSetAttribute(k3r_qp_kernel<NU, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e != cudaSuccess) return (int)e;
+        attr_for = sm;
+    }
+    long long g = io->B;               // one CTA per vehicle: the hardware scheduler balances uneven solves
+    if (g < 1) g = 1;
+    if (g > 2147483647LL) g = 2147483647LL;
+    k3r_qp_kernel<NU, NB><<<(int)g, NT, sm, st>>>(*io);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int eep_launch_qpr(const eepacc_params*, const eep_qp_io* io, cudaStream_t st)
+{
+    if (!io->rowtab || !io->rowc || !io->sblk) return (int)cudaErrorInvalidValue;
+    switch (io->ctrl) {
+    case EEPACC_FB: return launch_qpr<6, 2>(io, st);
+    case EEPACC_AB: return launch_qpr<5, 1>(io, st);
+    default: return launch_qpr<2, 1>(io, st);
+    }
+}
+#endif

@@ -150,6 +150,13 @@ int eepacc_mem_get_timing(int mem, double* tot, double* step_ms, long long cap);
 int eepacc_mem_debug_trace(int mem, double* out, int cap);
 /* clock64() cycles of vehicle 0's last solve by solver phase, out[8] (tracing must be enabled). */
 int eepacc_mem_debug_phases(int mem, double* out);
+/* Closed-loop QP kernel selection.  mode 0 (default): reduced-space active-set kernel (factorisation over the
+ * free variables only, capacity fc of them, default 48) with the full-space kernel as fallback for vehicles
+ * that do not fit; mode 1: full-space kernel only. */
+int eepacc_mem_set_qp_mode(int mem, int mode, int fc);
+/* Developer aid: copy a per-step device buffer of the closed loop to the host (0 sblk, 1 g, 2 lba, 3 uba,
+ * 4 x, 5 status, 6 iter, 7 cost); returns the number of doubles written or < 0. */
+long long eepacc_mem_debug_fetch(int mem, int what, double* out, long long cap);
 /* FP64-FMA peak microbenchmark (register-resident DFMA chains); returns GFLOP/s or <0. */
 double eepacc_measure_dfma_peak(int device);
 

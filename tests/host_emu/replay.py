@@ -1,0 +1,124 @@
+"""TEST INFRASTRUCTURE: replay recorded closed-loop QP operands through the host emulation of k3r_qp.cu."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from eepacc_mpc_casadi_matlab_b200 import settings as S  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+class QpIO(C.Structure):
+    _fields_ = [("B", C.c_longlong), ("n", C.c_int), ("m", C.c_int), ("ctrl", C.c_int),
+                ("H", _dp), ("g", _dp), ("A", _dp), ("lba", _dp), ("uba", _dp), ("lbx", _dp), ("ubx", _dp),
+                ("sblk", _dp), ("wx", _dp), ("wy", _dp), ("widx", C.POINTER(C.c_short)),
+                ("wside", C.POINTER(C.c_byte)), ("wnA", _ip), ("warm", _ip),
+                ("x", _dp), ("cost", _dp), ("lam_a", _dp), ("lam_x", _dp), ("status", _dp), ("iter", _dp),
+                ("counters", C.POINTER(C.c_ulonglong)), ("dbg", _dp), ("dbg_cap", C.c_int), ("fc", C.c_int),
+                ("defer_list", _ip), ("defer_cnt", _ip), ("todo_list", _ip), ("todo_cnt", _ip),
+                ("rowtab", C.c_void_p), ("rowc", _dp)]
+
+
+def cuda_include():
+    for d in (os.environ.get("CUDA_HOME"), "/usr/local/cuda"):
+        if d and os.path.exists(os.path.join(d, "include", "cuda_runtime.h")):
+            return os.path.join(d, "include")
+    return None
+
+
+def build(opt="-O2"):
+    inc = cuda_include()
+    if inc is None:
+        return None
+    out = os.path.join(HERE, "_build")
+    os.makedirs(out, exist_ok=True)
+    lib = os.path.join(out, "libk3r_emu.so")
+    src = os.path.join(HERE, "k3r_emu.cpp")
+    deps = [src] + [os.path.join(ROOT, "eepacc_mpc_casadi_matlab_b200", "csrc", f)
+                    for f in ("k3r_qp.cu", "eepacc_rows.cuh", "eepacc_dev.cuh", "eepacc_kernels.h")]
+    if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
+        subprocess.check_call(["g++", opt, "-g", "-std=c++17", "-x", "c++", "-shared", "-fPIC", "-I", inc, src, "-o", lib])
+    L = C.CDLL(lib)
+    L.k3r_emu_sizeof_io.restype = C.c_longlong
+    assert L.k3r_emu_sizeof_io() == C.sizeof(QpIO), (L.k3r_emu_sizeof_io(), C.sizeof(QpIO))
+    return L
+
+
+class Replayer:
+    """Warm-started solver state for B vehicles, fed one recorded step at a time."""
+
+    def __init__(self, L, ctrl, n, m, B, fc, params=None):
+        self.L, self.ctrl, self.n, self.m, self.B, self.fc = L, ctrl, n, m, B, fc
+        self.p = params if params is not None else S.default_params("mc")
+        self.wx = np.zeros((B, n)); self.wy = np.zeros((B, n))
+        self.widx = np.zeros((B, n), np.int16); self.wside = np.zeros((B, n), np.int8)
+        self.wnA = np.zeros(B, np.int32); self.warm = np.zeros(B, np.int32)
+        self.x = np.zeros((B, n)); self.cost = np.zeros(B); self.status = np.zeros(B); self.iter = np.zeros(B)
+        self.counters = np.zeros((B, 4), np.uint64)
+        self.defer_list = np.zeros(B, np.int32); self.defer_cnt = np.zeros(1, np.int32)
+        self.dbg = np.zeros(4096 * 4 + 32)
+
+    def solve(self, sblk, g, lba, uba):
+        io = QpIO()
+        io.B, io.n, io.m, io.ctrl, io.fc = self.B, self.n, self.m, self.ctrl, self.fc
+        keep = [np.ascontiguousarray(a, dtype=np.float64) for a in (sblk, g, lba, uba)]
+        io.sblk, io.g, io.lba, io.uba = [a.ctypes.data_as(_dp) for a in keep]
+        io.wx = self.wx.ctypes.data_as(_dp); io.wy = self.wy.ctypes.data_as(_dp)
+        io.widx = self.widx.ctypes.data_as(C.POINTER(C.c_short))
+        io.wside = self.wside.ctypes.data_as(C.POINTER(C.c_byte))
+        io.wnA = self.wnA.ctypes.data_as(_ip); io.warm = self.warm.ctypes.data_as(_ip)
+        io.x = self.x.ctypes.data_as(_dp); io.cost = self.cost.ctypes.data_as(_dp)
+        io.status = self.status.ctypes.data_as(_dp); io.iter = self.iter.ctypes.data_as(_dp)
+        io.counters = self.counters.ctypes.data_as(C.POINTER(C.c_ulonglong))
+        io.dbg = self.dbg.ctypes.data_as(_dp); io.dbg_cap = 4096
+        self.defer_cnt[0] = 0
+        io.defer_list = self.defer_list.ctypes.data_as(_ip); io.defer_cnt = self.defer_cnt.ctypes.data_as(_ip)
+        rc = self.L.k3r_emu_solve(C.byref(self.p), C.byref(io))
+        assert rc == 0
+        dl = self.defer_list[:self.defer_cnt[0]].copy()
+        # deferred vehicles: what the full-space kernel does on the GPU is emulated here by the same code
+        # with the capacity set to n (it then never defers)
+        for b in dl:
+            sub = Replayer(self.L, self.ctrl, self.n, self.m, 1, self.n, self.p)
+            names = ("wx", "wy", "widx", "wside", "wnA", "warm", "counters")
+            for nm in names:
+                getattr(sub, nm)[0] = getattr(self, nm)[b]
+            assert len(sub.solve(keep[0][b:b + 1], keep[1][b:b + 1], keep[2][b:b + 1], keep[3][b:b + 1])) == 0
+            for nm in names + ("x", "cost", "status", "iter"):
+                getattr(self, nm)[b] = getattr(sub, nm)[0]
+        return dl
+
+
+def replay(path, fc=None, steps=None, verbose=True):
+    d = np.load(path)
+    n, m = int(d["n"]), int(d["m"])
+    ctrl = {"ab": S.AB, "fb": S.FB, "bl": S.BL, "tv": S.TV}[os.path.basename(path).split("_")[1].split(".")[0]]
+    ns, B = d["x"].shape[:2]
+    if steps:
+        ns = min(ns, steps)
+    L = build()
+    R = Replayer(L, ctrl, n, m, B, fc or n)
+    worst = 0.0
+    for k in range(ns):
+        dl = R.solve(d["sblk"][k], d["g"][k], d["lba"][k], d["uba"][k])
+        ex = np.abs(R.x - d["x"][k]).max(axis=1)
+        ec = np.abs(R.cost - d["cost"][k, :, 0]) / (1 + np.abs(d["cost"][k, :, 0]))
+        bad = (R.status != d["status"][k, :, 0])
+        worst = max(worst, ex.max())
+        if verbose and (ex.max() > 1e-6 or bad.any() or len(dl) or k % 50 == 0):
+            print(f"step {k}: max|dx| {ex.max():.3e} cost rel {ec.max():.2e} status {R.status.astype(int)} ref {d['status'][k,:,0].astype(int)}"
+                  f" iter {R.iter.astype(int)} ref {d['iter'][k,:,0].astype(int)} defer {dl}")
+    return worst
+
+
+if __name__ == "__main__":
+    w = replay(sys.argv[1], fc=int(sys.argv[2]) if len(sys.argv) > 2 else None,
+               steps=int(sys.argv[3]) if len(sys.argv) > 3 else None)
+    print("worst |x - x_ref| =", w)
