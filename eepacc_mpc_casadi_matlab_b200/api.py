@@ -22,7 +22,7 @@ import numpy as np
 from . import settings as S
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libeepacc.so")
+LIB_PATH = os.environ.get("EEPACC_LIB") or os.path.join(_HERE, "libeepacc.so")   # EEPACC_LIB: developer variant (timers)
 _dp = C.POINTER(C.c_double)
 _dpp = C.POINTER(_dp)
 
@@ -312,11 +312,20 @@ class Engine:
     def enable_timing(self, on=True):
         self.L.eepacc_mem_enable_timing(self.mem, 1 if on else 0)
 
+    def set_groups(self, groups):
+        """Number of slices `run` pipelines the batch as (0 = automatic)."""
+        if self.L.eepacc_mem_set_groups(self.mem, int(groups)):
+            raise EepaccError(self._err())
+
+    def groups(self):
+        return int(self.L.eepacc_mem_get_groups(self.mem))
+
     def timing(self, n_steps):
-        """-> dict(build_ms, qp_ms, post_ms, steps, step_ms[n_steps]) since the last reset/run start."""
+        """-> dict(build_ms, qp_ms, post_ms, steps, step_ms[n_steps * groups]) since the last reset/run start;
+        the ms sums are kernel time per slice, which overlaps between slices when groups > 1."""
         tot = np.zeros(4)
-        st = np.zeros(n_steps)
-        rc = self.L.eepacc_mem_get_timing(self.mem, tot.ctypes.data_as(_dp), st.ctypes.data_as(_dp), n_steps)
+        st = np.zeros(n_steps * max(self.groups(), 1))
+        rc = self.L.eepacc_mem_get_timing(self.mem, tot.ctypes.data_as(_dp), st.ctypes.data_as(_dp), st.size)
         if rc:
             raise EepaccError(self._err())
         return dict(build_ms=tot[0], qp_ms=tot[1], post_ms=tot[2], steps=int(tot[3]), step_ms=st)

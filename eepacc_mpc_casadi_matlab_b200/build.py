@@ -19,28 +19,37 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force=False, verbose=False):
+def build_library(force=False, verbose=False, timers=None):
+    """Compile the sources concurrently (one nvcc per file) and link.  timers=True (or EEP_K3_TIMERS=1)
+    builds the developer variant libeepacc_timers.so with clock64() phase timers in the QP kernels;
+    api.load_library() picks it up through EEPACC_LIB."""
     nvcc = os.environ.get("NVCC", "nvcc")
+    if timers is None:
+        timers = bool(os.environ.get("EEP_K3_TIMERS"))
     hdrs = [os.path.join(CSRC, h) for h in HEADERS]
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build_timers" if timers else "build")
+    lib = LIB.replace("libeepacc.so", "libeepacc_timers.so") if timers else LIB
     os.makedirs(objdir, exist_ok=True)
-    objs = []
+    objs, jobs = [], []
     for s in SOURCES:
         src = os.path.join(CSRC, s)
         obj = os.path.join(objdir, s.replace(".cu", ".o"))
         if force or _stale(obj, [src] + hdrs):
-            cmd = [nvcc] + NVCC_FLAGS + (["-DEEP_K3_TIMERS"] if os.environ.get("EEP_K3_TIMERS") else []) + ["-c", src, "-o", obj]
+            cmd = [nvcc] + NVCC_FLAGS + (["-DEEP_K3_TIMERS"] if timers else []) + ["-c", src, "-o", obj]
             if verbose:
-                print(" ".join(cmd))
-            subprocess.check_call(cmd)
+                print(" ".join(cmd), flush=True)
+            jobs.append((cmd, subprocess.Popen(cmd)))
         objs.append(obj)
-    if force or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"]
+    for cmd, job in jobs:
+        if job.wait() != 0:
+            raise subprocess.CalledProcessError(job.returncode, cmd)
+    if force or _stale(lib, objs):
+        cmd = [nvcc, "-shared", "-o", lib] + objs + ["-lcudart"]
         if verbose:
-            print(" ".join(cmd))
+            print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose=True))
+    print(build_library(force="--force" in sys.argv, verbose=True, timers=("--timers" in sys.argv) or None))

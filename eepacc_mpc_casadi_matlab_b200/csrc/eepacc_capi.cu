@@ -30,6 +30,8 @@ int fail(int code, const char* what, cudaError_t e = cudaSuccess)
 }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(EEPACC_ERR_CUDA, #call, e_); } while (0)
 
+#define MAX_GROUPS 32
+
 struct DBuf {
     void* p = nullptr; size_t cap = 0;
     int ensure(size_t bytes)
@@ -68,7 +70,13 @@ struct Mem {
     DBuf in[12], out[8];        // staging for host-pointer calls
     bool timing = false;        // CUDA-event timing of every kernel launch (bench.py roofline leg)
     std::vector<cudaEvent_t> evs;
-    int ev_steps = 0;
+    int ev_steps = 0, ev_groups = 1;
+    // eepacc_run pipelines the batch as n_groups contiguous slices, each with its own stream and its own
+    // sequence of MPC steps: vehicles never interact, so a slice whose slowest vehicle needs many
+    // working-set changes no longer idles the SMs the other slices can use
+    int n_groups = 1;
+    cudaStream_t gstream[MAX_GROUPS] = {};
+    cudaEvent_t gfork = nullptr, gjoin[MAX_GROUPS] = {};
     void release_all()
     {
         DBuf* all[] = { &routes, &s_prev, &v_prev, &Fm_prev, &Fb_prev, &a_minus1, &v_tv_meas, &fbA, &fbD, &prev_sol,
@@ -79,6 +87,13 @@ struct Mem {
         for (auto& b : out) b.release();
         for (auto e : evs) cudaEventDestroy(e);
         evs.clear(); ev_steps = 0;
+        for (int g = 0; g < MAX_GROUPS; ++g) {
+            if (gstream[g]) cudaStreamDestroy(gstream[g]);
+            if (gjoin[g]) cudaEventDestroy(gjoin[g]);
+            gstream[g] = nullptr; gjoin[g] = nullptr;
+        }
+        if (gfork) cudaEventDestroy(gfork);
+        gfork = nullptr;
         ready = false;
     }
 };
@@ -207,40 +222,86 @@ eep_qp_io make_qp_io(Mem* M)
     return io;
 }
 
-// one closed-loop step on the device: K5/K4/K2 -> K3 -> post.  lead_dev: [B][2] device pointer.
-int device_step(Mem* M, const double* lead_dev, double* log_dev)
+// Restrict the kernel argument blocks to the vehicles [v0, v0 + nb): every per-vehicle array is
+// indexed from its base pointer, so a slice is the same block with shifted pointers.
+template <class T> static inline T* shift(T* p, size_t k) { return p ? p + k : p; }
+static void slice_io(eep_build_io& io, size_t v0, long long nb, int m, int n)
+{
+    io.B = nb;
+    io.routes = shift(io.routes, v0 * (size_t)io.route_stride);
+    io.s_prev = shift(io.s_prev, v0); io.v_prev = shift(io.v_prev, v0);
+    io.Fm_prev = shift(io.Fm_prev, v0); io.Fb_prev = shift(io.Fb_prev, v0);
+    io.a_minus1 = shift(io.a_minus1, v0); io.v_tv_meas = shift(io.v_tv_meas, v0);
+    io.fbA = shift(io.fbA, v0 * NH); io.fbD = shift(io.fbD, v0 * NH);
+    io.prev_sol = shift(io.prev_sol, v0 * 2 * (NH + 1));
+    io.lead = shift(io.lead, v0 * 2);
+    io.x0 = shift(io.x0, v0 * 2);
+    io.g = shift(io.g, v0 * n); io.lba = shift(io.lba, v0 * m); io.uba = shift(io.uba, v0 * m);
+    io.sblk = shift(io.sblk, v0 * EEP_SBLK);
+    io.dyn = shift(io.dyn, v0 * 2 * NH);
+}
+static void slice_io(eep_qp_io& io, size_t v0, long long nb)
+{
+    const size_t n = io.n, m = io.m;
+    io.B = nb;
+    io.g = shift(io.g, v0 * n); io.lba = shift(io.lba, v0 * m); io.uba = shift(io.uba, v0 * m);
+    io.sblk = shift(io.sblk, v0 * EEP_SBLK);
+    io.wx = shift(io.wx, v0 * n); io.wy = shift(io.wy, v0 * n);
+    io.widx = shift(io.widx, v0 * n); io.wside = shift(io.wside, v0 * n);
+    io.wnA = shift(io.wnA, v0); io.warm = shift(io.warm, v0);
+    io.x = shift(io.x, v0 * n); io.cost = shift(io.cost, v0);
+    io.status = shift(io.status, v0); io.iter = shift(io.iter, v0);
+    io.counters = shift(io.counters, v0 * 4);
+    if (v0) { io.dbg = nullptr; io.dbg_cap = 0; }       // the trace follows vehicle 0 of the batch
+}
+static void slice_io(eep_post_io& io, size_t v0, long long nb)
+{
+    const size_t n = io.n;
+    io.B = nb;
+    io.routes = shift(io.routes, v0 * (size_t)io.route_stride);
+    io.x = shift(io.x, v0 * n); io.x0 = shift(io.x0, v0 * 2); io.dyn = shift(io.dyn, v0 * 2 * NH);
+    io.status = shift(io.status, v0); io.iter = shift(io.iter, v0); io.cost = shift(io.cost, v0);
+    io.s_prev = shift(io.s_prev, v0); io.v_prev = shift(io.v_prev, v0);
+    io.Fm_prev = shift(io.Fm_prev, v0); io.Fb_prev = shift(io.Fb_prev, v0);
+    io.prev_sol = shift(io.prev_sol, v0 * 2 * (NH + 1));
+    io.log = shift(io.log, v0 * EEPACC_LOG_W);
+    io.kpi_acc = shift(io.kpi_acc, v0 * ACC_W);
+}
+
+// One closed-loop step, K5/K4/K2 -> K3 -> post, of the vehicles [v0, v0 + nb) on stream st (slice g of
+// the batch) at MPC step kk / time t0.  lead_dev: [B][2], log_dev: [B][EEPACC_LOG_W] of the whole batch.
+// ev: four events (build start, build end, QP end, post end) or null.
+int device_step_slice(Mem* M, int g, size_t v0, long long nb, cudaStream_t st, int kk, double t0,
+                      const double* lead_dev, double* log_dev, cudaEvent_t* ev)
 {
     eep_build_io bio = make_build_io(M, 0);
+    bio.kk = kk; bio.t0 = t0;
     bio.lead = lead_dev;
-    cudaEvent_t* ev = nullptr;
-    if (M->timing) {
-        const size_t need = (size_t)(M->kk + 1) * 4;
-        while (M->evs.size() < need) { cudaEvent_t e; CK(cudaEventCreate(&e)); M->evs.push_back(e); }
-        ev = &M->evs[(size_t)M->kk * 4];
-        M->ev_steps = M->kk + 1;
-        CK(cudaEventRecord(ev[0], M->stream));
-    }
-    int rc = eep_launch_build(&M->p, &bio, M->stream);
-    if (ev) CK(cudaEventRecord(ev[1], M->stream));
+    slice_io(bio, v0, nb, M->m, M->n);
+    if (ev) CK(cudaEventRecord(ev[0], st));
+    int rc = eep_launch_build(&M->p, &bio, st);
+    if (ev) CK(cudaEventRecord(ev[1], st));
     if (rc) return fail(EEPACC_ERR_CUDA, "k2_build launch", (cudaError_t)rc);
     eep_qp_io qio = make_qp_io(M);
+    slice_io(qio, v0, nb);
     if (M->qp_mode == 0) {
         // reduced-space kernel first; whatever it cannot hold goes to the full-space kernel
-        CK(cudaMemsetAsync(M->defer_cnt.p, 0, sizeof(int), M->stream));
+        int* cnt = M->defer_cnt.as<int>() + 4 * g;
+        CK(cudaMemsetAsync(cnt, 0, sizeof(int), st));
         qio.fc = M->qp_fc;
-        qio.defer_list = M->defer_list.as<int>(); qio.defer_cnt = M->defer_cnt.as<int>();
+        qio.defer_list = M->defer_list.as<int>() + v0; qio.defer_cnt = cnt;      // indices relative to v0
         qio.rowtab = M->rowtab.as<unsigned long long>(); qio.rowc = M->rowc.as<double>();
-        rc = eep_launch_qpr(&M->p, &qio, M->stream);
+        rc = eep_launch_qpr(&M->p, &qio, st);
         if (rc) return fail(EEPACC_ERR_CUDA, "k3r_qp launch", (cudaError_t)rc);
-        qio.todo_list = M->defer_list.as<int>(); qio.todo_cnt = M->defer_cnt.as<int>();
+        qio.todo_list = qio.defer_list; qio.todo_cnt = cnt;
         M->launches += 1;
     }
-    rc = eep_launch_qp(&M->p, &qio, M->stream);
+    rc = eep_launch_qp(&M->p, &qio, st);
     if (rc) return fail(EEPACC_ERR_CUDA, "k3_qp launch", (cudaError_t)rc);
-    if (ev) CK(cudaEventRecord(ev[2], M->stream));
+    if (ev) CK(cudaEventRecord(ev[2], st));
     eep_post_io pio;
     memset(&pio, 0, sizeof pio);
-    pio.B = M->B; pio.ctrl = M->ctrl; pio.n = M->n; pio.kk = M->kk;
+    pio.B = M->B; pio.ctrl = M->ctrl; pio.n = M->n; pio.kk = kk;
     pio.routes = M->routes.as<eepacc_route>(); pio.route_stride = 1;
     pio.x = M->xsol.as<double>(); pio.x0 = M->x0.as<double>(); pio.dyn = M->dyn.as<double>();
     pio.status = M->status.as<double>(); pio.iter = M->iter.as<double>(); pio.cost = M->cost.as<double>();
@@ -249,10 +310,31 @@ int device_step(Mem* M, const double* lead_dev, double* log_dev)
     pio.prev_sol = M->prev_sol.as<double>();
     pio.log = log_dev;
     pio.kpi_acc = M->kpi_acc.as<double>();
-    rc = eep_launch_post(&M->p, &pio, M->stream);
+    slice_io(pio, v0, nb);
+    rc = eep_launch_post(&M->p, &pio, st);
     if (rc) return fail(EEPACC_ERR_CUDA, "k4_post launch", (cudaError_t)rc);
-    if (ev) CK(cudaEventRecord(ev[3], M->stream));
+    if (ev) CK(cudaEventRecord(ev[3], st));
     M->launches += 3;
+    return EEPACC_OK;
+}
+
+static int timing_events(Mem* M, size_t need)
+{
+    while (M->evs.size() < need) { cudaEvent_t e; CK(cudaEventCreate(&e)); M->evs.push_back(e); }
+    return 0;
+}
+
+// the whole batch, one step, on the mem's stream (eepacc_step_* and the single-slice eepacc_run)
+int device_step(Mem* M, const double* lead_dev, double* log_dev)
+{
+    cudaEvent_t* ev = nullptr;
+    if (M->timing) {
+        if (timing_events(M, (size_t)(M->kk + 1) * 4)) return EEPACC_ERR_CUDA;
+        ev = &M->evs[(size_t)M->kk * 4];
+        M->ev_steps = M->kk + 1; M->ev_groups = 1;
+    }
+    int rc = device_step_slice(M, 0, 0, M->B, M->stream, M->kk, M->t0, lead_dev, log_dev, ev);
+    if (rc) return rc;
     M->kk += 1;
     M->t0 += M->p.Ts;
     return EEPACC_OK;
@@ -343,7 +425,7 @@ int eepacc_mem_setup(int mem, int ctrl, const eepacc_params* p, const eepacc_rou
         { &M->iter, (size_t)B * 8 }, { &M->counters, (size_t)B * 4 * 8 },
         { &M->kpi_acc, (size_t)B * ACC_W * 8 }, { &M->kpi, (size_t)B * EEPACC_N_KPI * 8 },
         { &M->lead_step, (size_t)B * 2 * 8 }, { &M->logrow, (size_t)B * EEPACC_LOG_W * 8 },
-        { &M->defer_list, (size_t)(B + 1) * 4 }, { &M->defer_cnt, 16 },
+        { &M->defer_list, (size_t)(B + 1) * 4 }, { &M->defer_cnt, 16 * MAX_GROUPS },
         { &M->rowtab, (size_t)(m + 1) * 8 }, { &M->rowc, 96 * 8 },
     };
     for (auto& e : plan) if (e.b->ensure(e.bytes)) return EEPACC_ERR_MEM;
@@ -372,6 +454,12 @@ int eepacc_mem_setup(int mem, int ctrl, const eepacc_params* p, const eepacc_rou
     if (const char* e = getenv("EEPACC_QP_FC")) { int v = atoi(e); if (v >= 8 && v <= EEPACC_MAX_NVAR) M->qp_fc = v; }
     if (M->qp_fc > M->n) M->qp_fc = M->n;
     M->ready = true;
+    {
+        int G = 0;
+        if (const char* e = getenv("EEPACC_GROUPS")) G = atoi(e);
+        if (G < 0 || G > MAX_GROUPS) G = 0;
+        if (eepacc_mem_set_groups(mem, G)) return EEPACC_ERR_ARG;
+    }
     return reset_state(M);
 }
 
@@ -483,7 +571,8 @@ int eepacc_mem_get_timing(int mem, double* tot, double* step_ms, long long cap)
     CK(cudaSetDevice(M->device));
     CK(cudaStreamSynchronize(M->stream));
     tot[0] = tot[1] = tot[2] = 0.0; tot[3] = (double)M->ev_steps;
-    for (int k = 0; k < M->ev_steps; ++k) {
+    const long long sets = (long long)M->ev_steps * M->ev_groups;     // one set of events per (step, slice)
+    for (long long k = 0; k < sets; ++k) {
         cudaEvent_t* ev = &M->evs[(size_t)k * 4];
         float a = 0, b = 0, c2 = 0;
         CK(cudaEventElapsedTime(&a, ev[0], ev[1]));
@@ -493,6 +582,25 @@ int eepacc_mem_get_timing(int mem, double* tot, double* step_ms, long long cap)
         if (step_ms && k < cap) step_ms[k] = (double)a + b + c2;
     }
     return EEPACC_OK;
+}
+
+/* eepacc_run pipelining: the batch is cut into `groups` contiguous slices (1..32), each advancing through
+ * its MPC steps on its own stream.  0 = automatic (8 slices of >= 256 vehicles).  Results do not depend
+ * on the slicing (vehicles never interact). */
+int eepacc_mem_set_groups(int mem, int groups)
+{
+    Mem* M = get_mem(mem);
+    if (!M || !M->ready) return fail(EEPACC_ERR_ARG, "mem not set up");
+    if (groups < 0 || groups > MAX_GROUPS) return fail(EEPACC_ERR_ARG, "groups must be 0 (auto) .. 32");
+    if (groups == 0) { groups = (int)(M->B / 256); if (groups > 8) groups = 8; if (groups < 1) groups = 1; }
+    if (groups > M->B) groups = (int)M->B;
+    M->n_groups = groups;
+    return EEPACC_OK;
+}
+int eepacc_mem_get_groups(int mem)
+{
+    Mem* M = get_mem(mem);
+    return (M && M->ready) ? M->n_groups : -1;
 }
 
 /* Developer aid: enable (cap > 0) / fetch the per-iteration trace of vehicle 0's last solve:
@@ -534,6 +642,7 @@ long long eepacc_mem_debug_fetch(int mem, int what, double* out, long long cap)
     case 5: src = M->status.p; cnt = B; break;
     case 6: src = M->iter.p; cnt = B; break;
     case 7: src = M->cost.p; cnt = B; break;
+    case 8: src = M->defer_cnt.p; cnt = 2; break;   // int[4]: vehicles deferred to the full-space kernel in the last step
     default: fail(EEPACC_ERR_ARG, "unknown buffer"); return -1;
     }
     if (cnt > cap) cnt = cap;
@@ -786,10 +895,42 @@ int eepacc_run(const double** arg, double** res, long long* iw, double*, int mem
         if (c.dev) log_dev = res[0];
         else { if (M->out[0].ensure((size_t)n_steps * B * EEPACC_LOG_W * 8)) return EEPACC_ERR_MEM; log_dev = M->out[0].as<double>(); }
     }
-    for (long long k = 0; k < n_steps; ++k) {
-        const double* lead = (M->ctrl == EEPACC_TV) ? nullptr : M->lead.as<double>() + (size_t)k * B * 2;
-        double* lg = log_dev ? log_dev + (size_t)k * B * EEPACC_LOG_W : nullptr;
-        if ((rc = device_step(M, lead, lg))) return rc;
+    const int G = M->n_groups;
+    if (G <= 1) {
+        for (long long k = 0; k < n_steps; ++k) {
+            const double* lead = (M->ctrl == EEPACC_TV) ? nullptr : M->lead.as<double>() + (size_t)k * B * 2;
+            double* lg = log_dev ? log_dev + (size_t)k * B * EEPACC_LOG_W : nullptr;
+            if ((rc = device_step(M, lead, lg))) return rc;
+        }
+    } else {
+        // slices on their own streams: fork from the mem's stream, join back before the KPI kernel
+        if (!M->gfork) CK(cudaEventCreateWithFlags(&M->gfork, cudaEventDisableTiming));
+        for (int g = 0; g < G; ++g) {
+            if (!M->gstream[g]) CK(cudaStreamCreateWithFlags(&M->gstream[g], cudaStreamNonBlocking));
+            if (!M->gjoin[g]) CK(cudaEventCreateWithFlags(&M->gjoin[g], cudaEventDisableTiming));
+        }
+        if (M->timing) {
+            if (timing_events(M, (size_t)n_steps * G * 4)) return EEPACC_ERR_CUDA;
+            M->ev_steps = (int)n_steps; M->ev_groups = G;
+        }
+        CK(cudaEventRecord(M->gfork, M->stream));
+        for (int g = 0; g < G; ++g) CK(cudaStreamWaitEvent(M->gstream[g], M->gfork, 0));
+        double t0 = M->t0;
+        for (long long k = 0; k < n_steps; ++k) {
+            const double* lead = (M->ctrl == EEPACC_TV) ? nullptr : M->lead.as<double>() + (size_t)k * B * 2;
+            double* lg = log_dev ? log_dev + (size_t)k * B * EEPACC_LOG_W : nullptr;
+            for (int g = 0; g < G; ++g) {
+                const size_t v0 = B * (size_t)g / G, v1 = B * (size_t)(g + 1) / G;
+                cudaEvent_t* ev = M->timing ? &M->evs[((size_t)k * G + g) * 4] : nullptr;
+                if ((rc = device_step_slice(M, g, v0, (long long)(v1 - v0), M->gstream[g], (int)k, t0, lead, lg, ev))) return rc;
+            }
+            t0 += M->p.Ts;
+        }
+        for (int g = 0; g < G; ++g) {
+            CK(cudaEventRecord(M->gjoin[g], M->gstream[g]));
+            CK(cudaStreamWaitEvent(M->stream, M->gjoin[g], 0));
+        }
+        M->kk = (int)n_steps; M->t0 = t0;
     }
     rc = eep_launch_kpi_final(&M->p, M->B, (int)n_steps, M->kpi_acc.as<double>(), M->kpi.as<double>(), M->stream);
     if (rc) return fail(EEPACC_ERR_CUDA, "kpi launch", (cudaError_t)rc);

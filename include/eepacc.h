@@ -154,8 +154,14 @@ int eepacc_mem_debug_phases(int mem, double* out);
  * free variables only, capacity fc of them, default 48) with the full-space kernel as fallback for vehicles
  * that do not fit; mode 1: full-space kernel only. */
 int eepacc_mem_set_qp_mode(int mem, int mode, int fc);
+/* eepacc_run pipelining: the batch advances as `groups` contiguous slices (1..32), each on its own CUDA stream
+ * with its own sequence of MPC steps (vehicles never interact; results do not depend on the slicing).
+ * 0 = automatic (up to 8 slices of >= 256 vehicles).  With G slices eepacc_mem_get_timing reports one latency
+ * per (step, slice), step-major. */
+int eepacc_mem_set_groups(int mem, int groups);
+int eepacc_mem_get_groups(int mem);
 /* Developer aid: copy a per-step device buffer of the closed loop to the host (0 sblk, 1 g, 2 lba, 3 uba,
- * 4 x, 5 status, 6 iter, 7 cost); returns the number of doubles written or < 0. */
+ * 4 x, 5 status, 6 iter, 7 cost, 8 deferred-vehicle count); returns the number of doubles written or < 0. */
 long long eepacc_mem_debug_fetch(int mem, int what, double* out, long long cap);
 /* FP64-FMA peak microbenchmark (register-resident DFMA chains); returns GFLOP/s or <0. */
 double eepacc_measure_dfma_peak(int device);
