@@ -51,5 +51,25 @@ def build_library(force=False, verbose=False, timers=None):
     return lib
 
 
+def build_variant(name, k3r_flags, verbose=True):
+    """Developer aid: libeepacc_<name>.so = the standard objects with k3r_qp.cu recompiled under extra
+    flags (e.g. -DK3R_NT=64 -DK3R_MINB=4).  Select it at run time with EEPACC_LIB=<path>."""
+    nvcc = os.environ.get("NVCC", "nvcc")
+    objdir = os.path.join(HERE, "build")            # the standard objects must exist (build_library)
+    vobj = os.path.join(objdir, f"k3r_qp_{name}.o")
+    cmd = [nvcc] + NVCC_FLAGS + list(k3r_flags) + ["-Xptxas", "-v", "-c", os.path.join(CSRC, "k3r_qp.cu"), "-o", vobj]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    subprocess.check_call(cmd)
+    objs = [os.path.join(objdir, s.replace(".cu", ".o")) for s in SOURCES if s != "k3r_qp.cu"] + [vobj]
+    lib = LIB.replace("libeepacc.so", f"libeepacc_{name}.so")
+    subprocess.check_call([nvcc, "-shared", "-o", lib] + objs + ["-lcudart"])
+    return lib
+
+
 if __name__ == "__main__":
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+        sys.exit(0)
     print(build_library(force="--force" in sys.argv, verbose=True, timers=("--timers" in sys.argv) or None))

@@ -64,6 +64,9 @@ struct Mem {
     DBuf kpi_acc, kpi, lead, lead_step, logrow, dbg;
     DBuf rowtab, rowc;          // packed constraint rows of the controller for the reduced-space QP kernel
     DBuf defer_list, defer_cnt; // vehicles the reduced-space QP kernel hands to the full-space kernel
+    DBuf hscr;                  // [B][4 (n + m)] homotopy state of the reduced-space QP kernel
+    DBuf defer_list2;           // second hand-over list: reduced-space kernel at full capacity -> full-space kernel
+    int qp_fc2 = 0;             // capacity of the second-level reduced-space launch (0: none)
     int qp_mode = 0;            // 0: reduced-space kernel + full-space fallback, 1: full-space kernel only
     int qp_fc = 48;             // capacity (free variables) of the reduced factorisation
     long long deferred_total = 0;
@@ -81,7 +84,7 @@ struct Mem {
     {
         DBuf* all[] = { &routes, &s_prev, &v_prev, &Fm_prev, &Fb_prev, &a_minus1, &v_tv_meas, &fbA, &fbD, &prev_sol,
                         &x0, &dyn, &g, &lba, &uba, &sblk, &wx, &wy, &widx, &wside, &wnA, &warm, &xsol, &cost,
-                        &status, &iter, &counters, &kpi_acc, &kpi, &lead, &lead_step, &logrow, &dbg, &defer_list, &defer_cnt, &rowtab, &rowc };
+                        &status, &iter, &counters, &kpi_acc, &kpi, &lead, &lead_step, &logrow, &dbg, &defer_list, &defer_cnt, &rowtab, &rowc, &hscr, &defer_list2 };
         for (DBuf* b : all) b->release();
         for (auto& b : in) b.release();
         for (auto& b : out) b.release();
@@ -287,14 +290,27 @@ int device_step_slice(Mem* M, int g, size_t v0, long long nb, cudaStream_t st, i
     if (M->qp_mode == 0) {
         // reduced-space kernel first; whatever it cannot hold goes to the full-space kernel
         int* cnt = M->defer_cnt.as<int>() + 4 * g;
-        CK(cudaMemsetAsync(cnt, 0, sizeof(int), st));
+        CK(cudaMemsetAsync(cnt, 0, 2 * sizeof(int), st));
         qio.fc = M->qp_fc;
         qio.defer_list = M->defer_list.as<int>() + v0; qio.defer_cnt = cnt;      // indices relative to v0
         qio.rowtab = M->rowtab.as<unsigned long long>(); qio.rowc = M->rowc.as<double>();
+        qio.hscr = M->hscr.as<double>() + v0 * 4 * (size_t)(M->n + M->m);
         rc = eep_launch_qpr(&M->p, &qio, st);
         if (rc) return fail(EEPACC_ERR_CUDA, "k3r_qp launch", (cudaError_t)rc);
         qio.todo_list = qio.defer_list; qio.todo_cnt = cnt;
         M->launches += 1;
+        if (M->qp_fc2 > M->qp_fc) {
+            // second level: the same kernel with (almost) every variable allowed to be free, one CTA per SM,
+            // over the hand-over list (the cold-start step and the rare wide working sets); what even that
+            // cannot hold goes on to the full-space kernel
+            eep_qp_io q2 = qio;
+            q2.fc = M->qp_fc2;
+            q2.defer_list = M->defer_list2.as<int>() + v0; q2.defer_cnt = cnt + 1;
+            rc = eep_launch_qpr(&M->p, &q2, st);
+            if (rc) return fail(EEPACC_ERR_CUDA, "k3r_qp second-level launch", (cudaError_t)rc);
+            qio.todo_list = q2.defer_list; qio.todo_cnt = cnt + 1;
+            M->launches += 1;
+        }
     }
     rc = eep_launch_qp(&M->p, &qio, st);
     if (rc) return fail(EEPACC_ERR_CUDA, "k3_qp launch", (cudaError_t)rc);
@@ -427,6 +443,7 @@ int eepacc_mem_setup(int mem, int ctrl, const eepacc_params* p, const eepacc_rou
         { &M->lead_step, (size_t)B * 2 * 8 }, { &M->logrow, (size_t)B * EEPACC_LOG_W * 8 },
         { &M->defer_list, (size_t)(B + 1) * 4 }, { &M->defer_cnt, 16 * MAX_GROUPS },
         { &M->rowtab, (size_t)(m + 1) * 8 }, { &M->rowc, 96 * 8 },
+        { &M->hscr, (size_t)B * 4 * (size_t)(n + m) * 8 }, { &M->defer_list2, (size_t)(B + 1) * 4 },
     };
     for (auto& e : plan) if (e.b->ensure(e.bytes)) return EEPACC_ERR_MEM;
     CK(cudaMemcpyAsync(M->routes.p, routes, (size_t)B * sizeof(eepacc_route), cudaMemcpyHostToDevice, M->stream));
@@ -453,6 +470,13 @@ int eepacc_mem_setup(int mem, int ctrl, const eepacc_params* p, const eepacc_rou
     if (const char* e = getenv("EEPACC_QP_MODE")) M->qp_mode = atoi(e) ? 1 : 0;
     if (const char* e = getenv("EEPACC_QP_FC")) { int v = atoi(e); if (v >= 8 && v <= EEPACC_MAX_NVAR) M->qp_fc = v; }
     if (M->qp_fc > M->n) M->qp_fc = M->n;
+    {
+        // largest capacity whose shared memory still fits one CTA per SM (227 KB opt-in limit)
+        int f2 = M->n;
+        while (f2 > M->qp_fc && eep_qpr_smem_bytes(M->n, M->m, f2) > 227 * 1024) --f2;
+        M->qp_fc2 = f2 > M->qp_fc ? f2 : 0;
+        if (const char* e = getenv("EEPACC_QP_FC2")) { int v = atoi(e); M->qp_fc2 = (v > M->qp_fc && v <= f2) ? v : 0; }
+    }
     M->ready = true;
     {
         int G = 0;
@@ -474,6 +498,7 @@ int eepacc_mem_set_qp_mode(int mem, int mode, int fc)
     if (fc < 8) fc = 8;
     if (fc > M->n) fc = M->n;
     M->qp_mode = mode; M->qp_fc = fc;
+    if (M->qp_fc2 <= fc) M->qp_fc2 = 0;
     return EEPACC_OK;
 }
 

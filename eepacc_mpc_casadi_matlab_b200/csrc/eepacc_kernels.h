@@ -67,6 +67,7 @@ struct eep_qp_io {
     const int *todo_list, *todo_cnt;
     const unsigned long long* rowtab;   // [m] packed constraint rows of the controller (eep_qpr_build_rowtab)
     const double* rowc;                 // [96] their coefficient tables
+    double* hscr;                       // [B][4 (n + m)] homotopy state of the reduced-space kernel (a x, current bounds, a dx)
 };
 
 // post kernel (k4_post.cu): z recovery, force allocation, logging, KPI accumulation

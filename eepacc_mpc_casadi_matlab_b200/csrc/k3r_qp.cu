@@ -28,8 +28,17 @@
 #include "eepacc_rows.cuh"
 
 #ifndef EEP_HOST_EMU
-#define NT 128
+#ifndef K3R_NT
+#define K3R_NT 64             // threads per vehicle (CTA): halving 128 costs 3-6 % latency, doubles the CTAs an SM holds
+#endif
+#ifndef K3R_MINB
+#define K3R_MINB 4            // CTAs per SM the register allocation is held to
+#endif
+#define NT K3R_NT
 #define EMU_ONLY(...)
+#define LDG(p) __ldg(p)
+#else
+#define LDG(p) (*(p))
 #endif
 
 #define FARB      1.0e6
@@ -51,8 +60,9 @@ struct CtxT {
     int n, m, mt, fc, ldq;
     int nF, nX, nZ;             // free variables, fixed variables (nF + nX = n), null-space columns
     double reg, hscale;
-    const double *g, *lnw, *unw;               // shared copies: gradient [n], new bounds of all m+n rows
-    const unsigned long long* rtab;            // [m] packed constraint rows (k3r_build_rowtab)
+    const double* g;                           // shared copy of the gradient [n]
+    const double *lba, *uba;                   // GLOBAL: this vehicle's new row bounds [m] (far bounds for rows >= m are constants)
+    const unsigned long long* rtab;            // GLOBAL (read-only path): [m] packed constraint rows (k3r_build_rowtab)
     const double *cvals, *cva, *cvb;           // [32] each: control coefficients, (a, b) of cV = a + b v_est(k)
     // factorisation
     double *Q, *M, *sub;
@@ -62,7 +72,9 @@ struct CtxT {
     double *yX, *dyX, *xcv, *dbX;
     // reduced vectors, by Qf column / row [fc + 1]
     double *yW, *dyW, *dbw, *wv, *csA, *snA, *pF, *uF, *tF, *gF;
-    // homotopy state over all rows [mt]
+    // homotopy state over all rows [mt]: GLOBAL scratch of this vehicle (io.hscr), touched a few times
+    // per working-set change with coalesced accesses; keeping it out of shared memory is what lets
+    // four vehicles share an SM
     double *Ax, *lbc, *ubc, *Adx;
     float* anorm;
     // structured block
@@ -90,8 +102,18 @@ template <class CT> __device__ __forceinline__ int mi(const CT& c, int r, int co
 #define QF(i, j) C.Q[(size_t)(j) * C.ldq + (i)]
 #define MM(r, c) C.M[mi(C, (r), (c))]
 
-template <class CT> __device__ __forceinline__ double lb_new(const CT& C, int c) { return C.lnw[c]; }
-template <class CT> __device__ __forceinline__ double ub_new(const CT& C, int c) { return C.unw[c]; }
+template <class CT> __device__ __forceinline__ double lb_new(const CT& C, int c)
+{
+    if (c >= C.m) return -FARB;
+    const double l = LDG(C.lba + c);
+    return (l <= -BIGB) ? -INFINITY : l;
+}
+template <class CT> __device__ __forceinline__ double ub_new(const CT& C, int c)
+{
+    if (c >= C.m) return FARB;
+    const double u = LDG(C.uba + c);
+    return (u >= BIGB) ? INFINITY : u;
+}
 
 // ---- block reductions (results broadcast to every thread) ----
 #ifdef EEP_HOST_EMU
@@ -138,6 +160,20 @@ template <class CT> __device__ __forceinline__ void block_argmin(CT& C, double& 
 }
 #endif
 
+// ---- lane groups: LPC consecutive lanes of a warp share one matrix column (QR / Q accumulation) ----
+#ifdef EEP_HOST_EMU
+#define LPC 1
+__device__ __forceinline__ double group_sum(double v) { return v; }
+#else
+#define LPC 4
+__device__ __forceinline__ double group_sum(double v)
+{
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    return v;
+}
+#endif
+
 struct VestSrc { const double* v_est; };
 
 // ---- matrix-free operators: H = Psi' Hs Psi and A = Gs Psi are never formed ----
@@ -168,7 +204,7 @@ template <class CT> __device__ __forceinline__ RowW row_load(const CT& C, int c)
 {
     RowW r;
     if (c >= C.m) { r.kst = -1; r.aux = 0; r.j0 = c - C.m; r.j1 = r.j2 = 255; r.i0 = r.i1 = r.i2 = 0; return r; }
-    const unsigned long long w = C.rtab[c];
+    const unsigned long long w = LDG(C.rtab + c);
     r.kst = (int)(signed char)(w & 0xff); r.aux = (int)((w >> 8) & 0xff);
     r.j0 = (int)((w >> 16) & 0xff); r.j1 = (int)((w >> 24) & 0xff); r.j2 = (int)((w >> 32) & 0xff);
     r.i0 = (int)((w >> 40) & 0xff); r.i1 = (int)((w >> 48) & 0xff); r.i2 = (int)((w >> 56) & 0xff);
@@ -594,19 +630,101 @@ template <class CT> __device__ int free_var(CT& C, int k)
     return 0;
 }
 
-// R = chol(Z' H Z) from scratch on the first nZ columns; returns 1 if not positive definite
+// OUT_g = H V_g for g < G vectors at once (same arithmetic as Hmul per vector; the stage phases of the G
+// vectors share the barriers).  V, OUT: [G][n] (OUT may alias V: the last phase reads V only at the entry
+// it writes); scr: [G][HG_SCR] doubles.
+#define HG_SCR (4 * EEP_N + 2 * (EEP_N + 1))
+template <class CT> __device__ void HmulG(CT& C, int G, const double* V, double* OUT, double* scr)
+{
+    const int n = C.n, NH = EEP_N, nu = CT::nu, nb = CT::nb;
+    for (int e = threadIdx.x; e < G * NH; e += NT) {
+        const int g = e / NH, i = e - g * NH;
+        const double* v = V + g * n;
+        double d = v[i * nu];
+        if (nb == 2) d += v[i * nu + 1];
+        scr[g * HG_SCR + i] = d;                                    // drv
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < G * (NH + 1); e += NT) {
+        const int g = e / (NH + 1), k = e - g * (NH + 1);
+        const double* drv = scr + g * HG_SCR;
+        double a = 0, b = 0;
+        for (int i = 0; i < k && i < NH; ++i) { a += C.PS[k * NH + i] * drv[i]; b += C.PV[k * NH + i] * drv[i]; }
+        scr[g * HG_SCR + NH + k] = b;                               // vv (sv does not enter H v)
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < G * NH; e += NT) {
+        const int g = e / NH, k = e - g * NH;
+        const double* v = V + g * n;
+        const double* vv = scr + g * HG_SCR + NH;
+        double* yc = scr + g * HG_SCR + 2 * NH + 1;
+        double w0[3] = { vv[k], v[k * nu], nb == 2 ? v[k * nu + 1] : 0.0 };
+        double y[3] = { 0, 0, 0 };
+        const double* D = C.Dc + k * 9;
+        for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) y[a] += D[a * 3 + b] * w0[b];
+        if (k > 0) {
+            double w1[3] = { vv[k - 1], v[(k - 1) * nu], nb == 2 ? v[(k - 1) * nu + 1] : 0.0 };
+            const double* Cm = C.Cc + k * 9;
+            for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) y[a] += Cm[a * 3 + b] * w1[b];
+        }
+        if (k + 1 < NH) {
+            double w2[3] = { vv[k + 1], v[(k + 1) * nu], nb == 2 ? v[(k + 1) * nu + 1] : 0.0 };
+            const double* Cp = C.Cc + (k + 1) * 9;
+            for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) y[a] += Cp[b * 3 + a] * w2[b];
+        }
+        yc[k * 3] = y[0]; yc[k * 3 + 1] = y[1]; yc[k * 3 + 2] = y[2];
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < G * n; e += NT) {
+        const int g = e / n, j = e - g * n;
+        const double* v = V + g * n;
+        const double* yc = scr + g * HG_SCR + 2 * NH + 1;
+        const int i = j / nu, cj = j % nu;
+        double val;
+        if (cj < nb) {
+            val = yc[i * 3 + 1 + cj];
+            double acc = 0.0;
+            for (int k = i + 1; k < NH; ++k) acc += C.PV[k * NH + i] * yc[k * 3];
+            val += acc;
+        } else val = C.Dg[i * 4 + (cj - nb)] * v[j];
+        OUT[g * n + j] = val + C.reg * v[j];
+    }
+    __syncthreads();
+}
+
+// R = chol(Z' H Z) from scratch on the first nZ columns; returns 1 if not positive definite.
+// H Z is formed up to four null-space columns at a time, in place, in the nine work vectors gcur .. dbX
+// (9 n contiguous doubles; none of them is live between warm_setup and setup_aux).
 template <class CT> __device__ int refactor_R(CT& C)
 {
     const int n = C.n, nF = C.nF, nZ = C.nZ;
-    for (int i = threadIdx.x; i < n; i += NT) C.t3[i] = 0.0;
-    __syncthreads();
-    for (int j = 0; j < nZ; ++j) {
-        for (int i = threadIdx.x; i < nF; i += NT) C.t3[C.flist[i]] = QF(i, j);
+    int GMAX = (9 * n) / (n + HG_SCR);
+    if (GMAX > 4) GMAX = 4;
+    double* V = C.gcur;
+    double* scr = V + GMAX * n;
+    for (int j0 = 0; j0 < nZ; j0 += GMAX) {
+        const int G = (nZ - j0 < GMAX) ? nZ - j0 : GMAX;
+        for (int e = threadIdx.x; e < G * n; e += NT) V[e] = 0.0;
         __syncthreads();
-        Hmul(C, C.t3, C.t1);
-        gatherF(C, C.t1);
-        Qtmul(C, C.gF, C.tF, 0, j + 1);
-        for (int i = threadIdx.x; i <= j; i += NT) MM(i, j) = C.tF[i];
+        for (int e = threadIdx.x; e < G * nF; e += NT) {
+            const int g = e / nF, i = e - g * nF;
+            V[g * n + C.flist[i]] = QF(i, j0 + g);
+        }
+        __syncthreads();
+        HmulG(C, G, V, V, scr);
+        // M(i, j0 + g) = z_i' (H z_(j0+g)),  i <= j0 + g
+        const int rows = j0 + G;
+        for (int e = threadIdx.x; e < G * rows; e += NT) {
+            const int g = e / rows, i = e - g * rows;
+            if (i > j0 + g) continue;
+            const double* hz = V + g * n;
+            double s0 = 0, s1 = 0;
+            int f = 0;
+            for (; f + 1 < nF; f += 2) { s0 += QF(f, i) * hz[C.flist[f]]; s1 += QF(f + 1, i) * hz[C.flist[f + 1]]; }
+            if (f < nF) s0 += QF(f, i) * hz[C.flist[f]];
+            MM(i, j0 + g) = s0 + s1;
+        }
+        __syncthreads();
     }
     const double thr = EPS_PD * C.hscale;
     for (int k = 0; k < nZ; ++k) {
@@ -842,6 +960,7 @@ template <class CT> __device__ int warm_setup(CT& C, int old_nA, const short* gi
     short* cand = reinterpret_cast<short*>(C.t1);        // [n] constraint index of general candidates
     short* tmpc = reinterpret_cast<short*>(C.t3);        // classification scratch: [3n] shorts
     double* tmpv = C.t2;                                 // [n] unit coefficient
+    double* tmpy = C.dx;                                 // [n] stored dual, by stored position
     double* ycand = C.t4;                                // [n] dual of general candidates
     double* v0a = C.csA;                                 // v0 of every reflector
     double* beta = C.snA;                                // 2 / v'v
@@ -860,6 +979,7 @@ template <class CT> __device__ int warm_setup(CT& C, int old_nA, const short* gi
         }
         tmpc[3 * k] = (short)(ok ? c : -1); tmpc[3 * k + 1] = (short)jv; tmpc[3 * k + 2] = (short)sd;
         tmpv[k] = cv;
+        tmpy[k] = gy[r];                                  // coalesced: thread 0 below never touches global memory
     }
     for (int j = threadIdx.x; j < n; j += NT) C.fpos[j] = 0;
     __syncthreads();
@@ -871,12 +991,12 @@ template <class CT> __device__ int warm_setup(CT& C, int old_nA, const short* gi
             if (c < 0) continue;
             if (jv >= 0) {
                 if (C.fpos[jv] < 0) continue;             // coordinate already pinned: dependent, drop
-                C.xvar[nx] = (short)jv; C.xcon[nx] = (short)c; C.xcv[nx] = tmpv[k]; C.yX[nx] = gy[n - 1 - k];
+                C.xvar[nx] = (short)jv; C.xcon[nx] = (short)c; C.xcv[nx] = tmpv[k]; C.yX[nx] = tmpy[k];
                 C.fpos[jv] = (short)(-1 - nx);
                 C.st[c] = (signed char)tmpc[3 * k + 2];
                 ++nx;
             } else {
-                cand[ng] = (short)c; ycand[ng] = gy[n - 1 - k]; C.st[c] = (signed char)tmpc[3 * k + 2];
+                cand[ng] = (short)c; ycand[ng] = tmpy[k]; C.st[c] = (signed char)tmpc[3 * k + 2];
                 ++ng;
             }
         }
@@ -897,26 +1017,37 @@ template <class CT> __device__ int warm_setup(CT& C, int old_nA, const short* gi
         cnt = nF;
         __syncthreads();
     }
-    // 2. stage the general rows (free part) as columns of W (= Qf storage)
-    for (int k = threadIdx.x; k < cnt; k += NT) {
-        const RowW rd = row_load(C, cand[k]);
+    // 2. stage the general rows (free part) as columns of W (= Qf storage): LPC lanes per row
+    for (int k0 = 0; k0 < cnt; k0 += NT / LPC) {          // warp-uniform trip count (full-mask shuffles inside)
+        const int k = k0 + threadIdx.x / LPC, lane = threadIdx.x % LPC;
         double s2 = 0;
-        for (int j = 0; j < n; ++j) {
-            const double v = s_entry(C, rd, j);
-            s2 += v * v;
-            const int f = C.fpos[j];
-            if (f >= 0) QF(f, k) = v;
+        if (k < cnt) {
+            const RowW rd = row_load(C, cand[k]);
+            for (int j = lane; j < n; j += LPC) {
+                const double v = s_entry(C, rd, j);
+                s2 += v * v;
+                const int f = C.fpos[j];
+                if (f >= 0) QF(f, k) = v;
+            }
         }
-        cn2[k] = s2;
+        s2 = group_sum(s2);
+        if (k < cnt && lane == 0) cn2[k] = s2;
     }
     __syncthreads();
     PH(2);
-    // 3. Householder QR; a dependent column is swapped with the last and dropped
-    int k = 0;
+    // 3. Householder QR; a dependent column is swapped with the last and dropped.  LPC lanes share a
+    //    column; the lane group of column k+1 also hands the next pivot norm over (C.red[6 + slot]), so a
+    //    regular column costs ONE barrier.
+    int k = 0, slot = 0;
+    bool have_s2 = false;
+    double s2 = 0;
     while (k < cnt) {
-        double s2 = 0;
-        for (int i = k + threadIdx.x; i < nF; i += NT) s2 += QF(i, k) * QF(i, k);
-        s2 = block_sum(C, s2);
+        if (!have_s2) {
+            double a2 = 0;
+            for (int i = k + threadIdx.x; i < nF; i += NT) a2 += QF(i, k) * QF(i, k);
+            s2 = block_sum(C, a2);
+        }
+        have_s2 = false;
         const double ref = cn2[k] > 1.0 ? cn2[k] : 1.0;
         if (!(s2 > EPS_LI * EPS_LI * ref)) {
             const int last = cnt - 1;
@@ -935,22 +1066,36 @@ template <class CT> __device__ int warm_setup(CT& C, int old_nA, const short* gi
         const double alpha = (x0 >= 0.0) ? -sigma : sigma;
         const double v0 = x0 - alpha;
         const double bt = 1.0 / (s2 - x0 * alpha);
-        __syncthreads();
-        for (int j = k + 1 + threadIdx.x; j < cnt; j += NT) {
-            double d = v0 * QF(k, j), d1 = 0, d2 = 0, d3 = 0;
-            int i = k + 1;
-            for (; i + 3 < nF; i += 4) {
-                d += QF(i, k) * QF(i, j); d1 += QF(i + 1, k) * QF(i + 1, j);
-                d2 += QF(i + 2, k) * QF(i + 2, j); d3 += QF(i + 3, k) * QF(i + 3, j);
+        for (int j0 = k + 1; j0 < cnt; j0 += NT / LPC) {
+            const int j = j0 + threadIdx.x / LPC, lane = threadIdx.x % LPC;
+            const bool act = j < cnt;
+            double d = 0, d1 = 0;
+            if (act) {
+                int i = k + 1 + lane;
+                for (; i + LPC < nF; i += 2 * LPC) { d += QF(i, k) * QF(i, j); d1 += QF(i + LPC, k) * QF(i + LPC, j); }
+                if (i < nF) d += QF(i, k) * QF(i, j);
             }
-            for (; i < nF; ++i) d += QF(i, k) * QF(i, j);
-            d = ((d + d1) + (d2 + d3)) * bt;
-            QF(k, j) -= d * v0;
-            for (int i2 = k + 1; i2 < nF; ++i2) QF(i2, j) -= d * QF(i2, k);
+            if (act && lane == 0) d += v0 * QF(k, j);     // consumed before the shuffle: lane 0 rewrites it below
+            d = group_sum(d + d1);
+            double nn = 0;
+            if (act) {
+                d *= bt;
+                for (int i = k + 1 + lane; i < nF; i += LPC) {
+                    const double v = QF(i, j) - d * QF(i, k);
+                    QF(i, j) = v;
+                    nn += v * v;
+                }
+            }
+            if (j0 == k + 1) {                            // warp-uniform: first pass only
+                nn = group_sum(nn);
+                if (act && j == k + 1 && lane == 0) C.red[6 + slot] = nn;
+            }
+            if (act && lane == 0) QF(k, j) -= d * v0;
         }
         if (threadIdx.x == 0) { v0a[k] = v0; beta[k] = bt; rdiag[k] = alpha; }
         __syncthreads();
         ++k;
+        if (k < cnt) { s2 = C.red[6 + slot]; have_s2 = true; slot ^= 1; }
     }
     PH(3);
     const int nAC = cnt, nZ = nF - nAC;
@@ -967,30 +1112,51 @@ template <class CT> __device__ int warm_setup(CT& C, int old_nA, const short* gi
     for (int j = nAC + threadIdx.x; j < nF; j += NT)
         for (int i = 0; i < nF; ++i) QF(i, j) = (i == j) ? 1.0 : 0.0;
     __syncthreads();
+    // Reflector kk is applied to the columns right of it by LPC lanes per column.  Column kk+1 still holds
+    // the raw reflector kk+1 at that point: its lane group turns it into H_(kk+1) e_(kk+1) on the fly
+    // (rows above the diagonal become zero), so one barrier per reflector is enough.
     for (int kk = nAC - 1; kk >= 0; --kk) {
         const double v0 = v0a[kk], bt = beta[kk];
-        for (int j = kk + 1 + threadIdx.x; j < nF; j += NT) {
-            double d = v0 * QF(kk, j), d1 = 0, d2 = 0, d3 = 0;
-            int i = kk + 1;
-            for (; i + 3 < nF; i += 4) {
-                d += QF(i, kk) * QF(i, j); d1 += QF(i + 1, kk) * QF(i + 1, j);
-                d2 += QF(i + 2, kk) * QF(i + 2, j); d3 += QF(i + 3, kk) * QF(i + 3, j);
+        for (int j0 = kk + 1; j0 < nF; j0 += NT / LPC) {
+            const int j = j0 + threadIdx.x / LPC, lane = threadIdx.x % LPC;
+            const bool act = j < nF;
+            const bool conv = act && j == kk + 1 && j < nAC;
+            const double cj = conv ? -beta[j] * v0a[j] : 1.0;      // scale of the raw entries below the diagonal
+            const double dj = conv ? 1.0 - beta[j] * v0a[j] * v0a[j] : 0.0;
+            double d = 0;
+            if (act) {
+                for (int i = kk + 1 + lane; i < nF; i += LPC) {
+                    const double c = (conv && i == j) ? dj : cj * QF(i, j);
+                    d += QF(i, kk) * c;
+                }
+                if (lane == 0 && !conv) d += v0 * QF(kk, j);
             }
-            for (; i < nF; ++i) d += QF(i, kk) * QF(i, j);
-            d = ((d + d1) + (d2 + d3)) * bt;
-            QF(kk, j) -= d * v0;
-            for (int i2 = kk + 1; i2 < nF; ++i2) QF(i2, j) -= d * QF(i2, kk);
+            d = group_sum(d) * bt;
+            if (act) {
+                for (int i = kk + 1 + lane; i < nF; i += LPC) {
+                    const double c = (conv && i == j) ? dj : cj * QF(i, j);
+                    QF(i, j) = c - d * QF(i, kk);
+                }
+                if (lane == 0) QF(kk, j) = (conv ? 0.0 : QF(kk, j)) - d * v0;
+                if (conv) for (int i = lane; i < kk; i += LPC) QF(i, j) = 0.0;
+            }
         }
         __syncthreads();
+    }
+    if (nAC > 0) {
+        const double v0 = v0a[0], bt = beta[0];
         for (int i = threadIdx.x; i < nF; i += NT) {
-            double vi = QF(i, kk);
-            QF(i, kk) = (i < kk) ? 0.0 : (i == kk) ? 1.0 - bt * v0 * v0 : -bt * v0 * vi;
+            const double vi = QF(i, 0);
+            QF(i, 0) = (i == 0) ? 1.0 - bt * v0 * v0 : -bt * v0 * vi;
         }
         __syncthreads();
     }
     // 6. reverse the columns, 7. working-set bookkeeping by Qf column
-    for (int i = threadIdx.x; i < nF; i += NT)
-        for (int c = 0; c < nF / 2; ++c) { double a = QF(i, c), b = QF(i, nF - 1 - c); QF(i, c) = b; QF(i, nF - 1 - c) = a; }
+    for (int e = threadIdx.x; e < nF * (nF / 2); e += NT) {
+        const int c = e / nF, i = e - c * nF;
+        const double a = QF(i, c), b2 = QF(i, nF - 1 - c);
+        QF(i, c) = b2; QF(i, nF - 1 - c) = a;
+    }
     for (int kq = threadIdx.x; kq < nAC; kq += NT) { C.yW[nF - 1 - kq] = ycand[kq]; C.widx[nF - 1 - kq] = cand[kq]; }
     C.nZ = nZ;
     __syncthreads();
@@ -1103,21 +1269,20 @@ __device__ __forceinline__ void k3r_body(const eep_qp_io& io, unsigned char* k3r
     CT C;
     const int n = io.n, m = io.m, mt = n + m, fc = io.fc;
     C.n = n; C.m = m; C.mt = mt; C.fc = fc; C.ldq = (fc + 1) | 1;
-    double *gS, *lnS, *unS;
+    double* gS;
     {
         double* p = reinterpret_cast<double*>(k3r_smem);
         C.Q = p; p += (size_t)(fc + 1) * C.ldq;
         C.M = p; p += (size_t)fc * (fc + 1) / 2 + fc + 2;
         C.sub = p; p += fc + 2;
-        C.x = p; p += n; C.gcur = p; p += n; C.dx = p; p += n; C.dg = p; p += n;
+        C.x = p; p += n; C.yX = p; p += n; C.xcv = p; p += n; gS = p; p += n;
+        // the next nine vectors are contiguous: refactor_R borrows them as scratch (nothing in them is live then)
+        C.gcur = p; p += n; C.dx = p; p += n; C.dg = p; p += n;
         C.t1 = p; p += n; C.t2 = p; p += n; C.t3 = p; p += n; C.t4 = p; p += n;
-        C.yX = p; p += n; C.dyX = p; p += n; C.xcv = p; p += n; C.dbX = p; p += n;
-        gS = p; p += n;
+        C.dyX = p; p += n; C.dbX = p; p += n;
         C.yW = p; p += fc + 1; C.dyW = p; p += fc + 1; C.dbw = p; p += fc + 1; C.wv = p; p += fc + 1;
         C.csA = p; p += fc + 1; C.snA = p; p += fc + 1; C.pF = p; p += fc + 1; C.uF = p; p += fc + 1;
         C.tF = p; p += fc + 1; C.gF = p; p += fc + 1;
-        C.Ax = p; p += mt; C.lbc = p; p += mt; C.ubc = p; p += mt; C.Adx = p; p += mt;
-        lnS = p; p += mt; unS = p; p += mt;
         C.anorm = reinterpret_cast<float*>(p); p += (mt + 1) / 2;
         const int NH = EEP_N;
         C.PS = p; p += (NH + 1) * NH; C.PV = p; p += (NH + 1) * NH; C.vest = p; p += NH + 1;
@@ -1128,8 +1293,7 @@ __device__ __forceinline__ void k3r_body(const eep_qp_io& io, unsigned char* k3r
         C.red = p; p += 8;
         C.ired = reinterpret_cast<int*>(p); p += 4;      // 8 ints
         double* cst = p; p += 96;
-        unsigned long long* rt = reinterpret_cast<unsigned long long*>(p); p += m;
-        C.g = gS; C.lnw = lnS; C.unw = unS; C.rtab = rt; C.cvals = cst; C.cva = cst + 32; C.cvb = cst + 64;
+        C.g = gS; C.rtab = io.rowtab; C.cvals = cst; C.cva = cst + 32; C.cvb = cst + 64;
         short* sp = reinterpret_cast<short*>(p);
         C.rk = sp; sp += fc + 1; C.rj0 = sp; sp += fc + 1; C.rj1 = sp; sp += fc + 1; C.rj2 = sp; sp += fc + 1; C.rj3 = sp; sp += fc + 1;
         C.flist = sp; sp += fc + 1; C.widx = sp; sp += fc + 1;
@@ -1140,12 +1304,13 @@ __device__ __forceinline__ void k3r_body(const eep_qp_io& io, unsigned char* k3r
         C.ph = reinterpret_cast<long long*>(k3r_smem + ((eep_qpr_smem_bytes(n, m, fc) - 34 * 8) & ~(size_t)7));
 #endif
         // per-controller tables and the far bounds: the same for every vehicle this CTA solves
-        for (int e = threadIdx.x; e < m; e += NT) rt[e] = io.rowtab[e];
         for (int e = threadIdx.x; e < 96; e += NT) cst[e] = io.rowc[e];
-        for (int c = m + threadIdx.x; c < mt; c += NT) { lnS[c] = -FARB; unS[c] = FARB; }
         if (threadIdx.x == 0) C.vest[NH] = 0.0;
     }
-    for (long long veh = blockIdx.x; veh < io.B; veh += gridDim.x) {
+    // second-level launch (large capacity): only the vehicles the first level handed over
+    const long long n_work = io.todo_list ? (long long)*io.todo_cnt : io.B;
+    for (long long wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
+        const long long veh = io.todo_list ? (long long)io.todo_list[wi] : wi;
         __syncthreads();
         int status = EEPACC_QP_OK, iter = 0;
         const int max_iter = 5 * (n + m);
@@ -1161,10 +1326,10 @@ __device__ __forceinline__ void k3r_body(const eep_qp_io& io, unsigned char* k3r
             const double* la = io.lba + veh * (size_t)m;
             const double* ua = io.uba + veh * (size_t)m;
             for (int i = threadIdx.x; i < n; i += NT) gS[i] = gg[i];
-            for (int c = threadIdx.x; c < m; c += NT) {
-                const double l = la[c], u = ua[c];
-                lnS[c] = (l <= -BIGB) ? -INFINITY : l;
-                unS[c] = (u >= BIGB) ? INFINITY : u;
+            C.lba = la; C.uba = ua;
+            {
+                double* hs = io.hscr + veh * (size_t)(4 * mt);
+                C.Ax = hs; C.lbc = hs + mt; C.ubc = hs + 2 * mt; C.Adx = hs + 3 * mt;
             }
             const double* sb = io.sblk + veh * (size_t)EEP_SBLK;
             for (int e = threadIdx.x; e < (EEP_N + 1) * EEP_N; e += NT) { C.PS[e] = sb[EEP_SB_PS + e]; C.PV[e] = sb[EEP_SB_PV + e]; }
@@ -1518,7 +1683,7 @@ __device__ __forceinline__ void k3r_body(const eep_qp_io& io, unsigned char* k3r
 }
 
 template <int NU, int NB>
-__global__ void __launch_bounds__(NT, 2) k3r_qp_kernel(eep_qp_io io EMU_ONLY(, unsigned char* k3r_smem))
+__global__ void __launch_bounds__(NT, K3R_MINB) k3r_qp_kernel(eep_qp_io io EMU_ONLY(, unsigned char* k3r_smem))
 {
     k3r_body<NU, NB>(io, k3r_smem);
 }
@@ -1532,9 +1697,9 @@ extern "C" __host__ __device__ size_t eep_qpr_smem_bytes(int n, int m, int fc)
 {
     const int mt = n + m, ldq = (fc + 1) | 1, NH = EEP_N;
     size_t d = (size_t)(fc + 1) * ldq + (size_t)fc * (fc + 1) / 2 + fc + 2 + (fc + 2) + 13 * (size_t)n + 10 * (size_t)(fc + 1)
-             + 6 * (size_t)mt + (mt + 1) / 2
+             + (mt + 1) / 2
              + 2 * (size_t)(NH + 1) * NH + NH + 1 + 2 * NH * 9 + NH * 4 + 2 * (NH + 1) + NH + NH * 3
-             + 2 * (NH + 1) + NH + 5 * (size_t)(fc + 1) + 8 + 4 + 96 + (size_t)m;
+             + 2 * (NH + 1) + NH + 5 * (size_t)(fc + 1) + 8 + 4 + 96;
     size_t shorts = 7 * (size_t)(fc + 1) + 3 * (size_t)n;
     size_t b = d * 8 + shorts * 2 + 2 * (size_t)mt + 16;
 #ifdef EEP_K3_TIMERS
@@ -1570,6 +1735,7 @@ static int launch_qpr(const eep_qp_io* io, cudaStream_t st)
         attr_for = sm;
     }
     long long g = io->B;               // one CTA per vehicle: the hardware scheduler balances uneven solves
+    if (io->todo_list && g > 148) g = 148;      // hand-over list: a few persistent CTAs walk it
     if (g < 1) g = 1;
     if (g > 2147483647LL) g = 2147483647LL;
     k3r_qp_kernel<NU, NB><<<(int)g, NT, sm, st>>>(*io);

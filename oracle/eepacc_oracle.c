@@ -885,6 +885,12 @@ orc_vehicle* orc_vehicle_new(int ctrl, const eepacc_params* p, const eepacc_rout
 void orc_vehicle_free(orc_vehicle* v) { if (v) { orc_qpws_free(v->ws); free(v); } }
 const orc_qp* orc_vehicle_qp(const orc_vehicle* v) { return &v->qp; }
 void orc_vehicle_get_ws(const orc_vehicle* v, int* ws) { orc_qpws_get_ws(v->ws, ws); }
+/* last closed-loop QP solution: x [n], lam_a [m] (conic scheme signs) */
+void orc_vehicle_get_sol(const orc_vehicle* v, double* x, double* lam_a)
+{
+    for (int i = 0; i < v->qp.n; ++i) x[i] = v->x[i];
+    for (int i = 0; i < v->qp.m; ++i) lam_a[i] = v->lam_a[i];
+}
 
 int orc_vehicle_step(orc_vehicle* V, double s_tv_k, double v_tv_k, double* out)
 {

@@ -100,6 +100,7 @@ int orc_vehicle_step(orc_vehicle* v, double s_tv_k, double v_tv_k, double* out);
 /* last built QP / working set of the vehicle (for parity tests) */
 const orc_qp* orc_vehicle_qp(const orc_vehicle* v);
 void orc_vehicle_get_ws(const orc_vehicle* v, int* ws);
+void orc_vehicle_get_sol(const orc_vehicle* v, double* x, double* lam_a);
 /* run n_steps for one vehicle: lead[n_steps][2]; log[n_steps][12]; kpi[EEPACC_N_KPI] */
 int orc_run(int ctrl, const eepacc_params* p, const eepacc_route* r, const double* lead,
             int lead_stride, int n_steps, double* log, double* kpi);

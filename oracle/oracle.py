@@ -57,6 +57,7 @@ def lib():
         L.orc_run.argtypes = [C.c_int, C.POINTER(Params), C.POINTER(Route), _dp, C.c_int, C.c_int,
                               _dp, _dp]
         L.orc_qpws_new.restype = C.c_void_p
+        L.orc_vehicle_get_sol.argtypes = [C.c_void_p, _dp, _dp]
         L.orc_qpws_new.argtypes = [C.c_int, C.c_int]
         L.orc_qpws_free.argtypes = [C.c_void_p]
         L.orc_qpws_reset.argtypes = [C.c_void_p]
@@ -105,6 +106,13 @@ class Vehicle:
 
     def qp(self):
         return self.L.orc_vehicle_qp(self.h).contents
+
+    def solution(self):
+        """(x, lam_a) of the last closed-loop QP."""
+        q = self.qp()
+        x, lam = np.zeros(q.n), np.zeros(q.m)
+        self.L.orc_vehicle_get_sol(self.h, _p(x), _p(lam))
+        return x, lam
 
     def working_set(self):
         q = self.qp()

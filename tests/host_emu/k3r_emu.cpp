@@ -31,13 +31,15 @@ extern "C" int k3r_emu_solve(const eepacc_params* p, const eep_qp_io* io_in)
     const int rc = k3r_build_rowtab(io.ctrl, *p, io.m, tab, consts);
     if (rc) { free(tab); return 100 + rc; }
     io.rowtab = tab; io.rowc = consts;
+    double* hs = (double*)calloc((size_t)io.B * 4 * (size_t)(io.n + io.m) + 1, 8);
+    io.hscr = hs;
     const size_t sm = eep_qpr_smem_bytes(io.n, io.m, io.fc);
     unsigned char* buf = (unsigned char*)calloc(sm + 64, 1);
     if (!buf) { free(tab); return -1; }
     if (io.ctrl == EEPACC_FB) k3r_qp_kernel<6, 2>(io, buf);
     else if (io.ctrl == EEPACC_AB) k3r_qp_kernel<5, 1>(io, buf);
     else k3r_qp_kernel<2, 1>(io, buf);
-    free(buf); free(tab);
+    free(buf); free(tab); free(hs);
     return 0;
 }
 extern "C" long long k3r_emu_sizeof_io(void) { return (long long)sizeof(eep_qp_io); }
