@@ -67,6 +67,7 @@ struct Mem {
     DBuf hscr;                  // [B][4 (n + m)] homotopy state of the reduced-space QP kernel
     DBuf defer_list2;           // second hand-over list: reduced-space kernel at full capacity -> full-space kernel
     int qp_fc2 = 0;             // capacity of the second-level reduced-space launch (0: none)
+    int qp_fbgrid = 16;         // CTAs of a hand-over launch past the cold-start step
     int qp_mode = 0;            // 0: reduced-space kernel + full-space fallback, 1: full-space kernel only
     int qp_fc = 48;             // capacity (free variables) of the reduced factorisation
     long long deferred_total = 0;
@@ -287,7 +288,12 @@ int device_step_slice(Mem* M, int g, size_t v0, long long nb, cudaStream_t st, i
     if (rc) return fail(EEPACC_ERR_CUDA, "k2_build launch", (cudaError_t)rc);
     eep_qp_io qio = make_qp_io(M);
     slice_io(qio, v0, nb);
+    bool need_full = true;      // does anything remain for the full-space kernel?
     if (M->qp_mode == 0) {
+        // Hand-over launches (second level, full space) take a whole SM's shared memory per CTA: a CTA of theirs
+        // cannot start before an SM has drained, and the slice waits for the whole grid.  Past the cold-start
+        // step the hand-over lists hold well under 1 % of the vehicles, so a handful of CTAs walks them.
+        qio.todo_grid = (kk == 0) ? 148 : M->qp_fbgrid;
         // reduced-space kernel first; whatever it cannot hold goes to the full-space kernel
         int* cnt = M->defer_cnt.as<int>() + 4 * g;
         CK(cudaMemsetAsync(cnt, 0, 2 * sizeof(int), st));
@@ -310,10 +316,15 @@ int device_step_slice(Mem* M, int g, size_t v0, long long nb, cudaStream_t st, i
             if (rc) return fail(EEPACC_ERR_CUDA, "k3r_qp second-level launch", (cudaError_t)rc);
             qio.todo_list = q2.defer_list; qio.todo_cnt = cnt + 1;
             M->launches += 1;
+            if (M->qp_fc2 >= M->n) need_full = false;     // every variable may be free: the second level never hands over
         }
+        if (M->qp_fc >= M->n) need_full = false;
     }
-    rc = eep_launch_qp(&M->p, &qio, st);
-    if (rc) return fail(EEPACC_ERR_CUDA, "k3_qp launch", (cudaError_t)rc);
+    if (need_full) {
+        rc = eep_launch_qp(&M->p, &qio, st);
+        if (rc) return fail(EEPACC_ERR_CUDA, "k3_qp launch", (cudaError_t)rc);
+        M->launches += 1;
+    }
     if (ev) CK(cudaEventRecord(ev[2], st));
     eep_post_io pio;
     memset(&pio, 0, sizeof pio);
@@ -330,7 +341,7 @@ int device_step_slice(Mem* M, int g, size_t v0, long long nb, cudaStream_t st, i
     rc = eep_launch_post(&M->p, &pio, st);
     if (rc) return fail(EEPACC_ERR_CUDA, "k4_post launch", (cudaError_t)rc);
     if (ev) CK(cudaEventRecord(ev[3], st));
-    M->launches += 3;
+    M->launches += 2;
     return EEPACC_OK;
 }
 
@@ -474,8 +485,12 @@ int eepacc_mem_setup(int mem, int ctrl, const eepacc_params* p, const eepacc_rou
         // largest capacity whose shared memory still fits one CTA per SM (227 KB opt-in limit)
         int f2 = M->n;
         while (f2 > M->qp_fc && eep_qpr_smem_bytes(M->n, M->m, f2) > 227 * 1024) --f2;
-        M->qp_fc2 = f2 > M->qp_fc ? f2 : 0;
+        // OFF by default: the cold-start step of FBMPC sits on a flat direction of an indefinite objective, where the
+        // path through the working sets decides which KKT point is reached; only the full-space kernel walks the
+        // oracle's path there (golden run of the ABO tree: Fm = 6131 N at step 0).  It also measured no faster.
+        M->qp_fc2 = 0;
         if (const char* e = getenv("EEPACC_QP_FC2")) { int v = atoi(e); M->qp_fc2 = (v > M->qp_fc && v <= f2) ? v : 0; }
+        if (const char* e = getenv("EEPACC_QP_FBGRID")) { int v = atoi(e); if (v >= 1 && v <= 148) M->qp_fbgrid = v; }
     }
     M->ready = true;
     {

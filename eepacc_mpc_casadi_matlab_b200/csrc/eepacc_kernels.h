@@ -68,6 +68,8 @@ struct eep_qp_io {
     const unsigned long long* rowtab;   // [m] packed constraint rows of the controller (eep_qpr_build_rowtab)
     const double* rowc;                 // [96] their coefficient tables
     double* hscr;                       // [B][4 (n + m)] homotopy state of the reduced-space kernel (a x, current bounds, a dx)
+    int todo_grid;                      // CTAs that walk todo_list (0: 148).  These launches need a whole SM's shared
+                                        // memory per CTA; a wide grid stalls the slice until that many SMs have drained
 };
 
 // post kernel (k4_post.cu): z recovery, force allocation, logging, KPI accumulation

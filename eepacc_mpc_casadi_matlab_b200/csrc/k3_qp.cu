@@ -1300,7 +1300,7 @@ extern "C" int eep_launch_qp(const eepacc_params* p, const eep_qp_io* io, cudaSt
         attr_for = sm;
     }
     long long g = io->B;               // one CTA per vehicle: the hardware scheduler balances uneven solves
-    if (io->todo_list && g > 148) g = 148;      // fallback mode: a few persistent CTAs walk the (short) hand-over list
+    if (io->todo_list && g > (io->todo_grid > 0 ? io->todo_grid : 148)) g = (io->todo_grid > 0 ? io->todo_grid : 148);      // fallback mode: a few persistent CTAs walk the (short) hand-over list
     if (g < 1) g = 1;
     if (g > 2147483647LL) g = 2147483647LL;
     k3_qp_kernel<<<(int)g, NT, sm, st>>>(*p, *io);

@@ -1735,7 +1735,10 @@ static int launch_qpr(const eep_qp_io* io, cudaStream_t st)
         attr_for = sm;
     }
     long long g = io->B;               // one CTA per vehicle: the hardware scheduler balances uneven solves
-    if (io->todo_list && g > 148) g = 148;      // hand-over list: a few persistent CTAs walk it
+    if (io->todo_list) {                         // hand-over list: a few persistent CTAs walk it
+        const long long cap = io->todo_grid > 0 ? io->todo_grid : 148;
+        if (g > cap) g = cap;
+    }
     if (g < 1) g = 1;
     if (g > 2147483647LL) g = 2147483647LL;
     k3r_qp_kernel<NU, NB><<<(int)g, NT, sm, st>>>(*io);

@@ -23,7 +23,7 @@ class QpIO(C.Structure):
                 ("x", _dp), ("cost", _dp), ("lam_a", _dp), ("lam_x", _dp), ("status", _dp), ("iter", _dp),
                 ("counters", C.POINTER(C.c_ulonglong)), ("dbg", _dp), ("dbg_cap", C.c_int), ("fc", C.c_int),
                 ("defer_list", _ip), ("defer_cnt", _ip), ("todo_list", _ip), ("todo_cnt", _ip),
-                ("rowtab", C.c_void_p), ("rowc", _dp), ("hscr", _dp)]
+                ("rowtab", C.c_void_p), ("rowc", _dp), ("hscr", _dp), ("todo_grid", C.c_int)]
 
 
 def cuda_include():
