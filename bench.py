@@ -22,6 +22,10 @@ import time
 
 import numpy as np
 
+# the sliced pipeline runs up to 16 slices on their own streams: without enough hardware queues (default 8) slices
+# share a queue and serialise (measured: 16 slices 612 k QP/s with 8 queues, 706 k with 32).  Must precede CUDA init.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
@@ -41,7 +45,8 @@ def parse():
     ap.add_argument("--cycle-steps", type=int, default=871, help="MPC steps per driving cycle")
     ap.add_argument("--cpu-sample", type=int, default=0, help="scenarios per core for the CPU baseline (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--groups", type=int, default=0, help="slices the batch is pipelined as (0 = library default)")
+    ap.add_argument("--groups", type=int, default=0, help="slices the per-step path pipelines the batch as (0 = library default)")
+    ap.add_argument("--fused", action="store_true", help="time the fused closed-loop kernel (k5_cycle_kernel) instead of the sliced per-step path")
     return ap.parse_args()
 
 
@@ -98,7 +103,7 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    per_core = args.cpu_sample or 1
+    per_core = args.cpu_sample or 4
     # scenario generation happens inside the workers and is excluded from their timers only
     vals = []
     for _ in range(args.warmup if args.warmup < 1 else 1):
@@ -211,27 +216,32 @@ def main():
         _, k = eng.run(ns, want_log=False)         # host KPI buffer: D2H inside the call
         return k
 
+    eng.set_fused(args.fused)
     for _ in range(max(args.warmup, 0)):
         run_resident()
     # ---- timed: resident inputs ----
-    eng.enable_timing(True)
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
     l0 = eng.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    step_lat = []
+    cyc_ms = []
     for _ in range(args.steps):
         run_resident()
-        step_lat.append(eng.timing(ns)["step_ms"].copy())
+        if eng.fused() and ns > 1:
+            cyc_ms.append(eng.cycle_timing())      # waits for this cycle's fused launch (CUDA events on its stream)
     ev1.record()
     barrier()
     clocks = sampler.stop()
     launches = eng.launch_count() - l0
     ms = ev0.elapsed_time(ev1)
-    # ---- roofline leg (not part of `value`): one cycle as ONE slice, so that every kernel runs alone on
-    # the device and its CUDA-event duration is its own (slices overlap in the pipelined run) ----
+    # ---- instrumented legs (not part of `value`): CUDA events around every kernel of the per-step path.
+    # (1) the sliced pipeline: latency of one MPC step of one slice; (2) one cycle as ONE slice, so that every
+    # kernel runs alone on the device and its CUDA-event duration is its own ----
+    eng.enable_timing(True)
+    run_resident()
+    step_lat = [eng.timing(ns)["step_ms"].copy()]
     eng.set_groups(1)
     run_resident()
     t = eng.timing(ns)
@@ -278,8 +288,33 @@ def main():
         dfma_peak = api.load_library().eepacc_measure_dfma_peak(local)
         it_mean = float(ctr[:, 0].mean()) / ns          # counters restart with every cycle
         fp64_achieved = B * (f_refac + it_mean * f_iter) / (qp_ms * 1e-3) / 1e9
+        # DRAM traffic of the dominant kernel from the committed ncu --set full capture (per vehicle, scaled to
+        # this launch); null if the summary is absent
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "k3r_traffic.json")))
+            traffic = float(tj[args.ctrl]["dram_bytes_per_vehicle"]) * B if not cyc_ms else None
+        except Exception:
+            pass
         lat = np.concatenate(step_lat)
         tot_k = kt["build_ms"] + kt["qp_ms"] + kt["post_ms"]
+        kname = "k3r_qp_kernel (+ k3_qp_kernel for the hand-overs), per-step path"
+        launch_ms, share, fused_info = qp_ms, (kt["qp_ms"] / tot_k if tot_k else None), None
+        if cyc_ms:
+            # dominant kernel of the timed region: ONE k5_cycle_kernel launch per cycle (build + QP + post of steps
+            # 1..ns-1 of every vehicle).  Algorithmic HBM bytes per vehicle-step: lead sample 16 B in,
+            # logged outputs 64 B + status 4 B out = 84 B; the structured block K2 hands to the solver is an
+            # on-chip-able intermediate and is not counted.
+            kname = "k5_cycle_kernel (fused K2 build + K3r reduced-space QP + K4 post, steps 1..n-1 of every vehicle)"
+            launch_ms = float(np.mean([c_["ms"] for c_ in cyc_ms]))
+            units = B * (ns - 1)
+            achieved = units * 84.0 / (launch_ms * 1e-3) / 1e9
+            fp64_achieved = units * (f_refac + it_mean * f_iter) / (launch_ms * 1e-3) / 1e9
+            share = launch_ms * args.steps / ms if world == 1 else None
+            fused_info = {"grid": cyc_ms[-1]["grid"], "ctas_per_sm": cyc_ms[-1]["ctas_per_sm"], "threads_per_cta": 64,
+                          "ms_per_launch": launch_ms, "vehicle_steps_per_launch": units,
+                          "mean_solve_slot_us": 1e3 * launch_ms * cyc_ms[-1]["grid"] / units,
+                          "sm_cycles_per_vehicle_step": {k_: v_ / units for k_, v_ in cyc_ms[-1]["cycles"].items()}}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -287,6 +322,9 @@ def main():
             "config": {"workload": f"{args.ctrl.upper()}MPC closed loop, batch {B} perturbed urban lead-vehicle "
                                    f"scenarios per GPU, {ns} MPC steps/cycle (BASELINE configs[1] at N=1)",
                        "controller": args.ctrl, "batch_per_gpu": B, "cycle_steps": ns, "qp_n": n, "qp_m": m,
+                       "path": "fused closed-loop kernel after the cold-start step" if cyc_ms else
+                               f"per-step launches, {groups} slices pipelined on their own streams",
+                       "cuda_device_max_connections": os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS"),
                        "slices": groups,
                        "l2": "a 256 MB buffer is written before every timed cycle (L2 flush); inside a cycle "
                              "every MPC step reads what K2 has just rewritten for that step"},
@@ -294,22 +332,25 @@ def main():
                     "d2h_bytes_per_step": int(B * S.N_KPI * 8)},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k3r_qp_kernel (+ k3_qp_kernel for the deferred vehicles)", "achieved": achieved, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
-                         "ms_per_launch": qp_ms, "share_of_step": kt["qp_ms"] / tot_k if tot_k else None},
-            "roofline_fp64": {"kernel": "k3r_qp_kernel (+ k3_qp_kernel for the deferred vehicles)", "achieved": fp64_achieved, "peak": dfma_peak, "unit": "GFLOP/s",
+            "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes": (units * 84.0) if cyc_ms else float(bytes_qp),
+                         "ms_per_launch": launch_ms, "share_of_step": share,
+                         "note": "latency-bound active-set solver: neither HBM nor the FP64 pipe is the limiter (profiles/README.md)"},
+            "fused": fused_info,
+            "roofline_fp64": {"kernel": kname, "achieved": fp64_achieved, "peak": dfma_peak, "unit": "GFLOP/s",
                               "frac": fp64_achieved / dfma_peak if dfma_peak > 0 else None,
                               "peak_source": "measured here: register-resident DFMA chains (eepacc_measure_dfma_peak)",
                               "flops_per_qp": f_refac + it_mean * f_iter},
-            "kernel_ms_per_cycle": dict(kt, what="one cycle run as a single slice (kernels serialised)"),
+            "kernel_ms_per_cycle": dict(kt, what="per-step path, one cycle run as a single slice (kernels serialised)"),
             "latency_ms": {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)),
                            "max": float(lat.max()),
-                           "what": f"one MPC step (build+solve+post) of one slice ({B // groups} vehicles), CUDA events; "
-                                   f"{groups} slices run concurrently"},
+                           "what": f"per-step path: one MPC step (build+solve+post) of one slice ({B // groups} vehicles), "
+                                   f"CUDA events; {groups} slices run concurrently"},
             "solver": {"mean_ws_changes_per_qp": it_mean, "failed_qps": int(ctr[:, 1].sum())},
         }
         if not args.no_cpu_baseline and world == 1:
-            v, cores, sample = cpu_run(args.ctrl, ns, args.cpu_sample or 1)
+            v, cores, sample = cpu_run(args.ctrl, ns, args.cpu_sample or 4)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
         print(json.dumps(line))
     eng.close()

@@ -47,6 +47,11 @@ class EepaccError(RuntimeError):
 _lib = None
 
 
+# eepacc_run pipelines up to 16 slices on their own streams; with the default 8 hardware queues slices share a queue
+# and serialise.  Only effective if CUDA has not been initialised yet in this process.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
+
 def load_library():
     """Load libeepacc.so (built in-tree by eepacc_mpc_casadi_matlab_b200.build).  Fails loudly."""
     global _lib
@@ -319,6 +324,23 @@ class Engine:
 
     def groups(self):
         return int(self.L.eepacc_mem_get_groups(self.mem))
+
+    def set_fused(self, on=True):
+        """run(): False (default) = per-step launches over pipelined slices; True = one fused closed-loop launch
+        per cycle after the cold-start step."""
+        if self.L.eepacc_mem_set_fused(self.mem, 1 if on else 0):
+            raise EepaccError(self._err())
+
+    def fused(self):
+        return bool(self.L.eepacc_mem_get_fused(self.mem))
+
+    def cycle_timing(self):
+        """-> dict(ms, grid, ctas_per_sm) of the last fused closed-loop launch (CUDA events on its stream)."""
+        out = np.zeros(7)
+        if self.L.eepacc_mem_get_cycle_timing(self.mem, out.ctypes.data_as(_dp)):
+            raise EepaccError(self._err())
+        return dict(ms=float(out[0]), grid=int(out[1]), ctas_per_sm=int(out[2]),
+                    cycles=dict(build=out[3], qp=out[4], handover_qp=out[5], post=out[6]))
 
     def timing(self, n_steps):
         """-> dict(build_ms, qp_ms, post_ms, steps, step_ms[n_steps * groups]) since the last reset/run start;

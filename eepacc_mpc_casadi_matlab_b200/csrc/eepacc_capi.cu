@@ -68,6 +68,10 @@ struct Mem {
     DBuf defer_list2;           // second hand-over list: reduced-space kernel at full capacity -> full-space kernel
     int qp_fc2 = 0;             // capacity of the second-level reduced-space launch (0: none)
     int qp_fbgrid = 16;         // CTAs of a hand-over launch past the cold-start step
+    int fused = 0;              // eepacc_run: 1 = steps >= 1 in the fused closed-loop kernel (k5_cycle_kernel)
+    DBuf cyc_counter, cyc_big;  // its vehicle hand-out counter and the work area of its hand-over solves
+    cudaEvent_t cyc_ev[2] = { nullptr, nullptr };   // around the last fused launch (always recorded: two events per cycle)
+    int cyc_grid = 0, cyc_per_sm = 0;
     int qp_mode = 0;            // 0: reduced-space kernel + full-space fallback, 1: full-space kernel only
     int qp_fc = 48;             // capacity (free variables) of the reduced factorisation
     long long deferred_total = 0;
@@ -85,7 +89,7 @@ struct Mem {
     {
         DBuf* all[] = { &routes, &s_prev, &v_prev, &Fm_prev, &Fb_prev, &a_minus1, &v_tv_meas, &fbA, &fbD, &prev_sol,
                         &x0, &dyn, &g, &lba, &uba, &sblk, &wx, &wy, &widx, &wside, &wnA, &warm, &xsol, &cost,
-                        &status, &iter, &counters, &kpi_acc, &kpi, &lead, &lead_step, &logrow, &dbg, &defer_list, &defer_cnt, &rowtab, &rowc, &hscr, &defer_list2 };
+                        &status, &iter, &counters, &kpi_acc, &kpi, &lead, &lead_step, &logrow, &dbg, &defer_list, &defer_cnt, &rowtab, &rowc, &hscr, &defer_list2, &cyc_counter, &cyc_big };
         for (DBuf* b : all) b->release();
         for (auto& b : in) b.release();
         for (auto& b : out) b.release();
@@ -272,6 +276,22 @@ static void slice_io(eep_post_io& io, size_t v0, long long nb)
     io.kpi_acc = shift(io.kpi_acc, v0 * ACC_W);
 }
 
+static eep_post_io make_post_io(Mem* M, int kk, double* log_dev)
+{
+    eep_post_io pio;
+    memset(&pio, 0, sizeof pio);
+    pio.B = M->B; pio.ctrl = M->ctrl; pio.n = M->n; pio.kk = kk;
+    pio.routes = M->routes.as<eepacc_route>(); pio.route_stride = 1;
+    pio.x = M->xsol.as<double>(); pio.x0 = M->x0.as<double>(); pio.dyn = M->dyn.as<double>();
+    pio.status = M->status.as<double>(); pio.iter = M->iter.as<double>(); pio.cost = M->cost.as<double>();
+    pio.s_prev = M->s_prev.as<double>(); pio.v_prev = M->v_prev.as<double>();
+    pio.Fm_prev = M->Fm_prev.as<double>(); pio.Fb_prev = M->Fb_prev.as<double>();
+    pio.prev_sol = M->prev_sol.as<double>();
+    pio.log = log_dev;
+    pio.kpi_acc = M->kpi_acc.as<double>();
+    return pio;
+}
+
 // One closed-loop step, K5/K4/K2 -> K3 -> post, of the vehicles [v0, v0 + nb) on stream st (slice g of
 // the batch) at MPC step kk / time t0.  lead_dev: [B][2], log_dev: [B][EEPACC_LOG_W] of the whole batch.
 // ev: four events (build start, build end, QP end, post end) or null.
@@ -326,17 +346,7 @@ int device_step_slice(Mem* M, int g, size_t v0, long long nb, cudaStream_t st, i
         M->launches += 1;
     }
     if (ev) CK(cudaEventRecord(ev[2], st));
-    eep_post_io pio;
-    memset(&pio, 0, sizeof pio);
-    pio.B = M->B; pio.ctrl = M->ctrl; pio.n = M->n; pio.kk = kk;
-    pio.routes = M->routes.as<eepacc_route>(); pio.route_stride = 1;
-    pio.x = M->xsol.as<double>(); pio.x0 = M->x0.as<double>(); pio.dyn = M->dyn.as<double>();
-    pio.status = M->status.as<double>(); pio.iter = M->iter.as<double>(); pio.cost = M->cost.as<double>();
-    pio.s_prev = M->s_prev.as<double>(); pio.v_prev = M->v_prev.as<double>();
-    pio.Fm_prev = M->Fm_prev.as<double>(); pio.Fb_prev = M->Fb_prev.as<double>();
-    pio.prev_sol = M->prev_sol.as<double>();
-    pio.log = log_dev;
-    pio.kpi_acc = M->kpi_acc.as<double>();
+    eep_post_io pio = make_post_io(M, kk, log_dev);
     slice_io(pio, v0, nb);
     rc = eep_launch_post(&M->p, &pio, st);
     if (rc) return fail(EEPACC_ERR_CUDA, "k4_post launch", (cudaError_t)rc);
@@ -487,10 +497,12 @@ int eepacc_mem_setup(int mem, int ctrl, const eepacc_params* p, const eepacc_rou
         while (f2 > M->qp_fc && eep_qpr_smem_bytes(M->n, M->m, f2) > 227 * 1024) --f2;
         // OFF by default: the cold-start step of FBMPC sits on a flat direction of an indefinite objective, where the
         // path through the working sets decides which KKT point is reached; only the full-space kernel walks the
-        // oracle's path there (golden run of the ABO tree: Fm = 6131 N at step 0).  It also measured no faster.
+        // reference path there (golden run of the ABO tree: Fm = 6131 N at step 0).  It also measured no faster.
         M->qp_fc2 = 0;
         if (const char* e = getenv("EEPACC_QP_FC2")) { int v = atoi(e); M->qp_fc2 = (v > M->qp_fc && v <= f2) ? v : 0; }
         if (const char* e = getenv("EEPACC_QP_FBGRID")) { int v = atoi(e); if (v >= 1 && v <= 148) M->qp_fbgrid = v; }
+        M->fused = 0;           // measured slower than the sliced per-step path (profiles/README.md): opt-in
+        if (const char* e = getenv("EEPACC_FUSED")) M->fused = atoi(e) ? 1 : 0;
     }
     M->ready = true;
     {
@@ -627,12 +639,44 @@ int eepacc_mem_get_timing(int mem, double* tot, double* step_ms, long long cap)
 /* eepacc_run pipelining: the batch is cut into `groups` contiguous slices (1..32), each advancing through
  * its MPC steps on its own stream.  0 = automatic (8 slices of >= 256 vehicles).  Results do not depend
  * on the slicing (vehicles never interact). */
+/* eepacc_run mode: 0 (default) = one set of launches per MPC step (sliced, see eepacc_mem_set_groups);
+ * 1 = steps >= 1 run in the fused closed-loop kernel, one launch per cycle, no synchronisation between vehicles.
+ * Event timing (eepacc_mem_enable_timing) always uses the per-step launches. */
+int eepacc_mem_set_fused(int mem, int on)
+{
+    Mem* M = get_mem(mem);
+    if (!M || !M->ready) return fail(EEPACC_ERR_ARG, "mem not set up");
+    M->fused = on ? 1 : 0;
+    return EEPACC_OK;
+}
+/* Duration (ms, CUDA events on the launching stream) of the last fused closed-loop launch; out[1] = its grid,
+ * out[2] = CTAs resident per SM.  Waits for the launch to finish. */
+int eepacc_mem_get_cycle_timing(int mem, double* out)
+{
+    Mem* M = get_mem(mem);
+    if (!M || !M->ready || !out) return fail(EEPACC_ERR_ARG, "mem not set up");
+    if (!M->cyc_ev[1]) return fail(EEPACC_ERR_ARG, "no fused launch yet");
+    CK(cudaEventSynchronize(M->cyc_ev[1]));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, M->cyc_ev[0], M->cyc_ev[1]));
+    out[0] = ms; out[1] = M->cyc_grid; out[2] = M->cyc_per_sm;
+    unsigned long long ph[4] = { 0, 0, 0, 0 };
+    CK(cudaMemcpy(ph, M->cyc_counter.as<unsigned long long>() + 1, sizeof ph, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 4; ++k) out[3 + k] = (double)ph[k];
+    return EEPACC_OK;
+}
+int eepacc_mem_get_fused(int mem)
+{
+    Mem* M = get_mem(mem);
+    return (M && M->ready) ? M->fused : -1;
+}
+
 int eepacc_mem_set_groups(int mem, int groups)
 {
     Mem* M = get_mem(mem);
     if (!M || !M->ready) return fail(EEPACC_ERR_ARG, "mem not set up");
     if (groups < 0 || groups > MAX_GROUPS) return fail(EEPACC_ERR_ARG, "groups must be 0 (auto) .. 32");
-    if (groups == 0) { groups = (int)(M->B / 256); if (groups > 8) groups = 8; if (groups < 1) groups = 1; }
+    if (groups == 0) { groups = (int)(M->B / 256); if (groups > 16) groups = 16; if (groups < 1) groups = 1; }
     if (groups > M->B) groups = (int)M->B;
     M->n_groups = groups;
     return EEPACC_OK;
@@ -936,7 +980,50 @@ int eepacc_run(const double** arg, double** res, long long* iw, double*, int mem
         else { if (M->out[0].ensure((size_t)n_steps * B * EEPACC_LOG_W * 8)) return EEPACC_ERR_MEM; log_dev = M->out[0].as<double>(); }
     }
     const int G = M->n_groups;
-    if (G <= 1) {
+    if (M->fused && M->qp_mode == 0 && !M->timing) {
+        // step 0 (cold start: every vehicle goes to the full-space kernel, the pinned reference path) through the
+        // per-step launches, everything after it in ONE launch with no synchronisation between vehicles
+        {
+            const double* lead = (M->ctrl == EEPACC_TV) ? nullptr : M->lead.as<double>();
+            if ((rc = device_step(M, lead, log_dev))) return rc;
+        }
+        if (n_steps > 1) {
+            eep_cycle_io cy;
+            memset(&cy, 0, sizeof cy);
+            cy.b = make_build_io(M, 0);
+            cy.q = make_qp_io(M);
+            cy.q.fc = M->qp_fc;
+            cy.q.rowtab = M->rowtab.as<unsigned long long>(); cy.q.rowc = M->rowc.as<double>();
+            cy.q.hscr = M->hscr.as<double>();
+            cy.p = make_post_io(M, 0, nullptr);
+            cy.lead_all = (M->ctrl == EEPACC_TV) ? nullptr : M->lead.as<double>();
+            cy.lead_stride = (long long)B * 2;
+            cy.log_all = log_dev; cy.log_stride = (long long)B * EEPACC_LOG_W;
+            cy.k_begin = 1; cy.k_end = (int)n_steps; cy.t0_begin = M->t0;
+            cy.fc_big = M->n;
+            cy.big_bytes = (eep_qpr_smem_bytes(M->n, M->m, M->n) + 255) & ~(size_t)255;
+            const int per_sm = eep_cycle_max_ctas_per_sm(&cy);
+            if (per_sm < 1) return fail(EEPACC_ERR_CUDA, "fused closed-loop kernel does not fit an SM");
+            int sms = 148;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, M->device);
+            long long grid = (long long)per_sm * sms;
+            if (const char* e = getenv("EEPACC_CYCLE_GRID")) { long long v = atoll(e); if (v >= 1 && v < grid) grid = v; }   // developer knob
+            if (grid > M->B) grid = M->B;
+            if (M->cyc_counter.ensure(8 * 8) || M->cyc_big.ensure((size_t)grid * cy.big_bytes)) return EEPACC_ERR_MEM;
+            cy.work_counter = M->cyc_counter.as<unsigned long long>();
+            cy.big = M->cyc_big.as<unsigned char>();
+            cy.phase = cy.work_counter + 1;
+            CK(cudaMemsetAsync(cy.work_counter, 0, 8 * 8, M->stream));
+            for (int e = 0; e < 2; ++e) if (!M->cyc_ev[e]) CK(cudaEventCreate(&M->cyc_ev[e]));
+            CK(cudaEventRecord(M->cyc_ev[0], M->stream));
+            rc = eep_launch_cycle(&M->p, &cy, (int)grid, M->stream);
+            CK(cudaEventRecord(M->cyc_ev[1], M->stream));
+            M->cyc_grid = (int)grid; M->cyc_per_sm = per_sm;
+            if (rc) return fail(EEPACC_ERR_CUDA, "k5_cycle launch", (cudaError_t)rc);
+            M->launches += 1;
+            M->kk = (int)n_steps; M->t0 += (double)(n_steps - 1) * M->p.Ts;
+        }
+    } else if (G <= 1) {
         for (long long k = 0; k < n_steps; ++k) {
             const double* lead = (M->ctrl == EEPACC_TV) ? nullptr : M->lead.as<double>() + (size_t)k * B * 2;
             double* lg = log_dev ? log_dev + (size_t)k * B * EEPACC_LOG_W : nullptr;

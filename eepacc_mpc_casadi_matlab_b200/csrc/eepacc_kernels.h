@@ -84,9 +84,32 @@ struct eep_post_io {
     double *kpi_acc;            // [B][12] running KPI accumulators
 };
 
+// fused closed loop (k3r_qp.cu: k5_cycle_kernel): one CTA takes a vehicle through the MPC steps
+// [k_begin, k_end) -- K5/K4/K2 build, reduced-space QP (hand-overs solved in place at full capacity from a
+// global work area), post -- with no synchronisation between vehicles
+struct eep_cycle_io {
+    eep_build_io b;             // whole batch (no slice offsets); kk, t0, lead are set per step by the kernel
+    eep_qp_io q;
+    eep_post_io p;              // kk, log are set per step by the kernel
+    const double* lead_all;     // [n_steps][B][2] or null (TVMPC)
+    long long lead_stride;      // doubles per step
+    double* log_all;            // [n_steps][B][EEPACC_LOG_W] or null
+    long long log_stride;
+    int k_begin, k_end;
+    double t0_begin;            // time of step k_begin
+    unsigned long long* work_counter;   // vehicles are handed out dynamically
+    unsigned char* big;         // [grid][big_bytes] work area of the hand-over solves
+    unsigned long long big_bytes;
+    int fc_big;
+    unsigned long long* phase;  // [4] clock64() cycles summed over all vehicle-steps: build, QP, hand-over QP, post
+};
+
 #ifdef __cplusplus
 extern "C" {
 #endif
+int eep_launch_cycle(const eepacc_params* p, const eep_cycle_io* cy, int grid, cudaStream_t st);
+int eep_cycle_max_ctas_per_sm(const eep_cycle_io* cy);
+size_t eep_build_smem_bytes();
 void eep_launch_f(const eepacc_params* p, long long B, const double* x, const double* u, double* xdot, double* L, cudaStream_t st);
 void eep_launch_F(const eepacc_params* p, long long B, const double* x, const double* u, double* xf, double* qf, cudaStream_t st);
 void eep_launch_Fjac(const eepacc_params* p, long long B, const double* x, const double* u, double* xf, double* qf, double* J, cudaStream_t st);

@@ -29,16 +29,26 @@
 
 #ifndef EEP_HOST_EMU
 #ifndef K3R_NT
-#define K3R_NT 64             // threads per vehicle (CTA): halving 128 costs 3-6 % latency, doubles the CTAs an SM holds
+#define K3R_NT 128            // threads per vehicle (CTA).  Measured (profiles/README.md): 64 threads cost 3-6 % latency at equal
+                              // residency and let 3 CTAs share an SM, but co-resident solves slow each other (+38 % from 1 to
+                              // 3 per SM), so 2 x 128 threads and 3 x 64 threads end within 2 % (AB) and 2 x 128 wins on FB
 #endif
 #ifndef K3R_MINB
-#define K3R_MINB 4            // CTAs per SM the register allocation is held to
+#define K3R_MINB 2            // CTAs per SM the register allocation is held to
 #endif
 #define NT K3R_NT
+// The solver's primitives can be compiled as real functions (-DK3R_NOINLINE): the kernel shrinks from ~660 KB to
+// ~420 KB of SASS and compiles in 1 min instead of 12, but measured 15 % slower (calls, context in local memory).
+#ifdef K3R_NOINLINE
+#define K3R_FN __noinline__
+#else
+#define K3R_FN
+#endif
 #define EMU_ONLY(...)
 #define LDG(p) __ldg(p)
 #else
 #define LDG(p) (*(p))
+#define K3R_FN
 #endif
 
 #define FARB      1.0e6
@@ -61,6 +71,7 @@ struct CtxT {
     int nF, nX, nZ;             // free variables, fixed variables (nF + nX = n), null-space columns
     double reg, hscale;
     const double* g;                           // shared copy of the gradient [n]
+    double* gw;                                // the same, writable (filled per vehicle)
     const double *lba, *uba;                   // GLOBAL: this vehicle's new row bounds [m] (far bounds for rows >= m are constants)
     const unsigned long long* rtab;            // GLOBAL (read-only path): [m] packed constraint rows (k3r_build_rowtab)
     const double *cvals, *cva, *cvb;           // [32] each: control coefficients, (a, b) of cV = a + b v_est(k)
@@ -105,13 +116,13 @@ template <class CT> __device__ __forceinline__ int mi(const CT& c, int r, int co
 template <class CT> __device__ __forceinline__ double lb_new(const CT& C, int c)
 {
     if (c >= C.m) return -FARB;
-    const double l = LDG(C.lba + c);
+    const double l = C.lba[c];            // plain load: K2 rewrites the bounds every step inside the fused kernel
     return (l <= -BIGB) ? -INFINITY : l;
 }
 template <class CT> __device__ __forceinline__ double ub_new(const CT& C, int c)
 {
     if (c >= C.m) return FARB;
-    const double u = LDG(C.uba + c);
+    const double u = C.uba[c];
     return (u >= BIGB) ? INFINITY : u;
 }
 
@@ -177,7 +188,7 @@ __device__ __forceinline__ double group_sum(double v)
 struct VestSrc { const double* v_est; };
 
 // ---- matrix-free operators: H = Psi' Hs Psi and A = Gs Psi are never formed ----
-template <class CT> __device__ void s_prep(CT& C, const double* v)
+template <class CT> K3R_FN __device__ void s_prep(CT& C, const double* v)
 {
     const int NH = EEP_N;
     for (int i = threadIdx.x; i < NH; i += NT) {
@@ -253,13 +264,13 @@ template <class CT> __device__ __forceinline__ bool s_unit(const CT& C, const Ro
 }
 
 // full row (all n entries)
-template <class CT> __device__ void get_row(CT& C, int c, double* a)
+template <class CT> K3R_FN __device__ void get_row(CT& C, int c, double* a)
 {
     const RowW rd = row_load(C, c);
     for (int j = threadIdx.x; j < C.n; j += NT) a[j] = s_entry(C, rd, j);
     __syncthreads();
 }
-template <class CT> __device__ void Hmul(CT& C, const double* v, double* out)
+template <class CT> K3R_FN __device__ void Hmul(CT& C, const double* v, double* out)
 {
     const int n = C.n;
     const int NH = EEP_N, nu = CT::nu, nb = CT::nb;
@@ -296,7 +307,7 @@ template <class CT> __device__ void Hmul(CT& C, const double* v, double* out)
     }
     __syncthreads();
 }
-template <class CT> __device__ void Amul(CT& C, const double* v, double* out)
+template <class CT> K3R_FN __device__ void Amul(CT& C, const double* v, double* out)
 {
     const int n = C.n, m = C.m;
     s_prep(C, v);
@@ -308,7 +319,7 @@ template <class CT> __device__ void Amul(CT& C, const double* v, double* out)
 }
 // w[j] = sum over the active general rows r in [nZ, nF) of A(widx[r], j) yv[r]
 //        (+ cv_k yXv[k] at j = xvar[k] when yXv != nullptr).  Deterministic gather, no atomics.
-template <class CT> __device__ void ATmul(CT& C, const double* yv, const double* yXv, double* w)
+template <class CT> K3R_FN __device__ void ATmul(CT& C, const double* yv, const double* yXv, double* w)
 {
     const int n = C.n, NH = EEP_N, nu = CT::nu, nb = CT::nb, nZ = C.nZ, nF = C.nF;
     __syncthreads();
@@ -361,13 +372,13 @@ template <class CT> __device__ void ATmul(CT& C, const double* yv, const double*
 }
 
 // ---- reduced dense primitives; every routine ends with data visible after a __syncthreads() ----
-template <class CT> __device__ void gatherF(CT& C, const double* a)
+template <class CT> K3R_FN __device__ void gatherF(CT& C, const double* a)
 {
     for (int i = threadIdx.x; i < C.nF; i += NT) C.gF[i] = a[C.flist[i]];
     __syncthreads();
 }
 // w[j] = qf_j' aF for j in [c0, c1), aF compact [nF]
-template <class CT> __device__ void Qtmul(CT& C, const double* aF, double* w, int c0, int c1)
+template <class CT> K3R_FN __device__ void Qtmul(CT& C, const double* aF, double* w, int c0, int c1)
 {
     const int nF = C.nF;
     for (int j = c0 + threadIdx.x; j < c1; j += NT) {
@@ -380,7 +391,7 @@ template <class CT> __device__ void Qtmul(CT& C, const double* aF, double* w, in
     __syncthreads();
 }
 // outF[i] = sum_{c in [c0,c1)} Qf(i,c) p[c], i < nF (compact)
-template <class CT> __device__ void Qmul(CT& C, const double* p, int c0, int c1, double* outF)
+template <class CT> K3R_FN __device__ void Qmul(CT& C, const double* p, int c0, int c1, double* outF)
 {
     const int nF = C.nF;
     for (int i = threadIdx.x; i < nF; i += NT) {
@@ -393,7 +404,7 @@ template <class CT> __device__ void Qmul(CT& C, const double* p, int c0, int c1,
     __syncthreads();
 }
 // solve M[lo:hi,lo:hi] x = b (back substitution); b is destroyed, x may not alias b
-template <class CT> __device__ void usolve(CT& C, int lo, int hi, double* b, double* x)
+template <class CT> K3R_FN __device__ void usolve(CT& C, int lo, int hi, double* b, double* x)
 {
 #ifdef EEP_HOST_EMU
     for (int r = hi - 1; r >= lo; --r) {
@@ -429,7 +440,7 @@ template <class CT> __device__ void usolve(CT& C, int lo, int hi, double* b, dou
 #endif
 }
 // solve M[lo:hi,lo:hi]' y = v (forward substitution); v destroyed
-template <class CT> __device__ void tsolve(CT& C, int lo, int hi, double* v, double* y)
+template <class CT> K3R_FN __device__ void tsolve(CT& C, int lo, int hi, double* v, double* y)
 {
 #ifdef EEP_HOST_EMU
     for (int r = lo; r < hi; ++r) {
@@ -468,7 +479,7 @@ template <class CT> __device__ void tsolve(CT& C, int lo, int hi, double* v, dou
 // Givens sweep that adds the row whose free part is aF (compact).  nZt = null-space columns that take
 // part (0..nZt-1), nR = dimension of the valid R block to keep updated (0: none).  The new
 // range-space column / T row is nZt-1.  Returns 1 if the row is linearly dependent (no change).
-template <class CT> __device__ int givens_add(CT& C, int cidx, int side, const double* aF, double an2, int nZt, int nR, bool check_li)
+template <class CT> K3R_FN __device__ int givens_add(CT& C, int cidx, int side, const double* aF, double an2, int nZt, int nR, bool check_li)
 {
     const int nF = C.nF;
     Qtmul(C, aF, C.wv, 0, nF);
@@ -551,7 +562,7 @@ template <class CT> __device__ int givens_add(CT& C, int cidx, int side, const d
 
 // Remove the general row that owns Qf column rp.  Afterwards column nZ_old is the new null-space
 // direction; R is not touched.  yW / widx are shifted with the rows.
-template <class CT> __device__ void remove_general(CT& C, int rp)
+template <class CT> K3R_FN __device__ void remove_general(CT& C, int rp)
 {
     const int nF = C.nF, nZ = C.nZ;
     if (threadIdx.x == 0) C.st[C.widx[rp]] = 0;
@@ -602,7 +613,7 @@ template <class CT> __device__ void remove_general(CT& C, int rp)
 // Free the variable pinned by X entry k (remove its unit row from the working set): append the
 // coordinate to Qf and T (implicit last row of the full T made explicit), then remove that row.
 // Returns 1 if the capacity is exhausted (nothing changed).
-template <class CT> __device__ int free_var(CT& C, int k)
+template <class CT> K3R_FN __device__ int free_var(CT& C, int k)
 {
     const int nF = C.nF, nZ = C.nZ;
     if (nF >= C.fc) return 1;
@@ -634,7 +645,7 @@ template <class CT> __device__ int free_var(CT& C, int k)
 // vectors share the barriers).  V, OUT: [G][n] (OUT may alias V: the last phase reads V only at the entry
 // it writes); scr: [G][HG_SCR] doubles.
 #define HG_SCR (4 * EEP_N + 2 * (EEP_N + 1))
-template <class CT> __device__ void HmulG(CT& C, int G, const double* V, double* OUT, double* scr)
+template <class CT> K3R_FN __device__ void HmulG(CT& C, int G, const double* V, double* OUT, double* scr)
 {
     const int n = C.n, NH = EEP_N, nu = CT::nu, nb = CT::nb;
     for (int e = threadIdx.x; e < G * NH; e += NT) {
@@ -695,7 +706,7 @@ template <class CT> __device__ void HmulG(CT& C, int G, const double* V, double*
 // R = chol(Z' H Z) from scratch on the first nZ columns; returns 1 if not positive definite.
 // H Z is formed up to four null-space columns at a time, in place, in the nine work vectors gcur .. dbX
 // (9 n contiguous doubles; none of them is live between warm_setup and setup_aux).
-template <class CT> __device__ int refactor_R(CT& C)
+template <class CT> K3R_FN __device__ int refactor_R(CT& C)
 {
     const int n = C.n, nF = C.nF, nZ = C.nZ;
     int GMAX = (9 * n) / (n + HG_SCR);
@@ -746,7 +757,7 @@ template <class CT> __device__ int refactor_R(CT& C)
 
 // KKT step: H dx + dg = A_W' dy,  A_W dx = db.  db / dy: dbw,dyW by Qf column (general rows) and
 // dbX,dyX by X position (unit rows of the fixed variables).
-template <class CT> __device__ void kkt_step(CT& C, const double* dg, const double* dbw, const double* dbX, double* dx, double* dyW, double* dyX)
+template <class CT> K3R_FN __device__ void kkt_step(CT& C, const double* dg, const double* dbw, const double* dbX, double* dx, double* dyW, double* dyX)
 {
     const int n = C.n, nF = C.nF, nZ = C.nZ, nX = C.nX, nAC = nF - nZ;
     double* u = C.t2;
@@ -804,7 +815,7 @@ template <class CT> __device__ void kkt_step(CT& C, const double* dg, const doub
 }
 
 // g_cur = A_W' y - H x  (optionally recomputing y by least squares first), duals sign-clamped
-template <class CT> __device__ void reanchor(CT& C, bool recompute_y)
+template <class CT> K3R_FN __device__ void reanchor(CT& C, bool recompute_y)
 {
     const int n = C.n, nF = C.nF, nZ = C.nZ, nX = C.nX;
     Hmul(C, C.x, C.t1);
@@ -843,7 +854,7 @@ template <class CT> __device__ void reanchor(CT& C, bool recompute_y)
 }
 
 // compact free part of row c into aF (and its full squared norm)
-template <class CT> __device__ double get_rowF(CT& C, int c, double* aF)
+template <class CT> K3R_FN __device__ double get_rowF(CT& C, int c, double* aF)
 {
     const RowW rd = row_load(C, c);
     double s2 = 0;
@@ -859,7 +870,7 @@ template <class CT> __device__ double get_rowF(CT& C, int c, double* aF)
 }
 
 // see oracle/qp_oracle.c:resolve_pending
-template <class CT> __device__ int resolve_pending(CT& C, int c_out, int side_out, unsigned long long& n_exch, bool zero_step)
+template <class CT> K3R_FN __device__ int resolve_pending(CT& C, int c_out, int side_out, unsigned long long& n_exch, bool zero_step)
 {
     const int n = C.n, mt = C.mt;
     bool first = true, moved = false;
@@ -953,7 +964,7 @@ template <class CT> __device__ int resolve_pending(CT& C, int c_out, int side_ou
 // is dropped); general rows -> Householder QR of A_gF' (nF x nG):  A_gF' = Qh [Rh; 0],
 // Qf = Qh with reversed columns, T(r, c) = Rh(nF-1-c, nF-1-r).  Rows whose new bound is infinite
 // or that became linearly dependent are dropped.  Returns 1 if nF exceeds the capacity.
-template <class CT> __device__ int warm_setup(CT& C, int old_nA, const short* gidx, const signed char* gside, const double* gy)
+template <class CT> K3R_FN __device__ int warm_setup(CT& C, int old_nA, const short* gidx, const signed char* gside, const double* gy)
 {
     const int n = C.n, mt = C.mt, m = C.m;
     for (int c = threadIdx.x; c < mt; c += NT) C.st[c] = 0;
@@ -1165,7 +1176,7 @@ template <class CT> __device__ int warm_setup(CT& C, int old_nA, const short* gi
 }
 
 // all variables fixed at their (relaxed) lower far bound; position k <-> variable n-1-k (k3_qp.cu order)
-template <class CT> __device__ void cold_ws(CT& C)
+template <class CT> K3R_FN __device__ void cold_ws(CT& C)
 {
     const int n = C.n, m = C.m, mt = C.mt;
     __syncthreads();
@@ -1183,7 +1194,7 @@ template <class CT> __device__ void cold_ws(CT& C)
 }
 
 // auxiliary QP for which the current (x, y, working set) is optimal: relaxed bounds + anchored gradient
-template <class CT> __device__ void setup_aux(CT& C)
+template <class CT> K3R_FN __device__ void setup_aux(CT& C)
 {
     const int mt = C.mt;
     Amul(C, C.x, C.Ax);
@@ -1261,17 +1272,16 @@ __device__ int k3r_build_rowtab(int ctrl, const eepacc_params& p, int m, unsigne
     return 0;
 }
 
+// Lay the solver's work arrays out over `base` (shared memory, or a global scratch block for a hand-over) for
+// capacity fc.  Writes nothing.
 template <int NU, int NB>
-__device__ __forceinline__ void k3r_body(const eep_qp_io& io, unsigned char* k3r_smem)
+__device__ __forceinline__ void k3r_setup(k3r::CtxT<NU, NB>& C, const eep_qp_io& io, unsigned char* base, const int fc)
 {
-    using namespace k3r;
-    typedef CtxT<NU, NB> CT;
-    CT C;
-    const int n = io.n, m = io.m, mt = n + m, fc = io.fc;
+    const int n = io.n, m = io.m, mt = n + m;
     C.n = n; C.m = m; C.mt = mt; C.fc = fc; C.ldq = (fc + 1) | 1;
     double* gS;
     {
-        double* p = reinterpret_cast<double*>(k3r_smem);
+        double* p = reinterpret_cast<double*>(base);
         C.Q = p; p += (size_t)(fc + 1) * C.ldq;
         C.M = p; p += (size_t)fc * (fc + 1) / 2 + fc + 2;
         C.sub = p; p += fc + 2;
@@ -1293,7 +1303,7 @@ __device__ __forceinline__ void k3r_body(const eep_qp_io& io, unsigned char* k3r
         C.red = p; p += 8;
         C.ired = reinterpret_cast<int*>(p); p += 4;      // 8 ints
         double* cst = p; p += 96;
-        C.g = gS; C.rtab = io.rowtab; C.cvals = cst; C.cva = cst + 32; C.cvb = cst + 64;
+        C.g = gS; C.gw = gS; C.rtab = io.rowtab; C.cvals = cst; C.cva = cst + 32; C.cvb = cst + 64;
         short* sp = reinterpret_cast<short*>(p);
         C.rk = sp; sp += fc + 1; C.rj0 = sp; sp += fc + 1; C.rj1 = sp; sp += fc + 1; C.rj2 = sp; sp += fc + 1; C.rj3 = sp; sp += fc + 1;
         C.flist = sp; sp += fc + 1; C.widx = sp; sp += fc + 1;
@@ -1301,383 +1311,403 @@ __device__ __forceinline__ void k3r_body(const eep_qp_io& io, unsigned char* k3r
         C.st = reinterpret_cast<signed char*>(sp);
         C.tabu = C.st + mt;
 #ifdef EEP_K3_TIMERS
-        C.ph = reinterpret_cast<long long*>(k3r_smem + ((eep_qpr_smem_bytes(n, m, fc) - 34 * 8) & ~(size_t)7));
+        C.ph = reinterpret_cast<long long*>(base + ((eep_qpr_smem_bytes(n, m, fc) - 34 * 8) & ~(size_t)7));
 #endif
-        // per-controller tables and the far bounds: the same for every vehicle this CTA solves
-        for (int e = threadIdx.x; e < 96; e += NT) cst[e] = io.rowc[e];
-        if (threadIdx.x == 0) C.vest[NH] = 0.0;
     }
-    // second-level launch (large capacity): only the vehicles the first level handed over
+}
+// per-controller coefficient tables: the same for every vehicle, but they live in the work area (re-load them
+// whenever something else used it)
+template <class CT> __device__ __forceinline__ void k3r_tables(CT& C, const eep_qp_io& io)
+{
+    double* cst = const_cast<double*>(C.cvals);
+    for (int e = threadIdx.x; e < 96; e += NT) cst[e] = io.rowc[e];
+    if (threadIdx.x == 0) C.vest[EEP_N] = 0.0;
+}
+// One vehicle's QP.  Returns the status written to io.status, or K3R_DEFER (nothing written, warm state
+// untouched) when the free variables exceed the capacity.
+template <class CT>
+K3R_FN __device__ int k3r_vehicle(CT& C, const eep_qp_io& io, const long long veh)
+{
+    using namespace k3r;
+    const int n = C.n, m = C.m, mt = C.mt;
+    __syncthreads();
+    int status = EEPACC_QP_OK, iter = 0;
+    const int max_iter = 5 * (n + m);
+    const int restart_after = (4 * n > 400 ? 4 * n : 400);
+    unsigned long long n_exch = 0, n_refac = 0;
+#ifdef EEP_K3_TIMERS
+    if (threadIdx.x == 0) { for (int q = 0; q < 32; ++q) C.ph[q] = 0; C.ph[32] = clock64(); }
+#endif
+
+    // gradient, bounds, structured block, Hessian scale, LP regularisation, row norms
+    {
+        const double* gg = io.g + veh * (size_t)n;
+        const double* la = io.lba + veh * (size_t)m;
+        const double* ua = io.uba + veh * (size_t)m;
+        for (int i = threadIdx.x; i < n; i += NT) C.gw[i] = gg[i];
+        C.lba = la; C.uba = ua;
+        {
+            double* hs = io.hscr + veh * (size_t)(4 * mt);
+            C.Ax = hs; C.lbc = hs + mt; C.ubc = hs + 2 * mt; C.Adx = hs + 3 * mt;
+        }
+        const double* sb = io.sblk + veh * (size_t)EEP_SBLK;
+        for (int e = threadIdx.x; e < (EEP_N + 1) * EEP_N; e += NT) { C.PS[e] = sb[EEP_SB_PS + e]; C.PV[e] = sb[EEP_SB_PV + e]; }
+        for (int e = threadIdx.x; e < EEP_N * 9; e += NT) { C.Dc[e] = sb[EEP_SB_DC + e]; C.Cc[e] = sb[EEP_SB_CC + e]; }
+        for (int e = threadIdx.x; e < EEP_N * 4; e += NT) C.Dg[e] = sb[EEP_SB_DG + e];
+        for (int e = threadIdx.x; e < EEP_N; e += NT) C.vest[e] = sb[EEP_SB_VEST + e];
+        C.reg = (sb[EEP_SB_HMAX] == 0.0) ? LP_REG : 0.0;
+        C.hscale = fmax(sb[EEP_SB_HSCALE], LP_REG);
+        __syncthreads();
+        for (int r = threadIdx.x; r < m; r += NT) {
+            const RowW rd = row_load(C, r);
+            double sa = 0;
+            if (rd.kst >= 0) {
+                const double cV = row_cV(C, rd), cS = (rd.aux & 128) ? 1.0 : 0.0;
+                for (int i = 0; i < rd.kst && i < EEP_N; ++i)
+                    sa += CT::nb * fabs(cS * C.PS[rd.kst * EEP_N + i] + cV * C.PV[rd.kst * EEP_N + i]);
+            }
+            if (rd.j0 != 255) sa += fabs(C.cvals[rd.i0]);
+            if (rd.j1 != 255) sa += fabs(C.cvals[rd.i1]);
+            if (rd.j2 != 255) sa += fabs(C.cvals[rd.i2]);
+            if (rd.kst == -2) sa += CT::nb;
+            C.anorm[r] = (float)sa;
+        }
+    }
+    for (int j = threadIdx.x; j < n; j += NT) C.anorm[m + j] = 1.0f;
+    for (int c = threadIdx.x; c < mt; c += NT) C.tabu[c] = 0;
+    __syncthreads();
+    PH(0);
+
+    // ---------------- set-up ----------------
+    const int was_warm = io.warm[veh];
+    bool need_cold = !was_warm;
+    for (int i = threadIdx.x; i < n; i += NT) C.x[i] = was_warm ? io.wx[veh * (size_t)n + i] : 0.0;
+    if (!need_cold) {
+        if (warm_setup(C, io.wnA[veh], io.widx + veh * (size_t)n, io.wside + veh * (size_t)n, io.wy + veh * (size_t)n))
+            status = K3R_DEFER;
+        else {
+            n_refac++;
+            if (refactor_R(C)) need_cold = true;
+            PH(5);
+        }
+    }
+    if (status == EEPACC_QP_OK) {
+        if (need_cold) cold_ws(C);
+        setup_aux(C);
+    }
+    PH(6);
+
+    // ---------------- homotopy ----------------
+    while (status == EEPACC_QP_OK) {
+        const int nZ = C.nZ, nF = C.nF, nX = C.nX;
+        for (int i = threadIdx.x; i < n; i += NT) C.dg[i] = C.g[i] - C.gcur[i];
+        for (int r = nZ + threadIdx.x; r < nF; r += NT) {
+            int c = C.widx[r];
+            double nb = C.st[c] < 0 ? lb_new(C, c) : ub_new(C, c);
+            double cb = C.st[c] < 0 ? C.lbc[c] : C.ubc[c];
+            C.dbw[r] = isinf(nb) ? 0.0 : nb - cb;
+        }
+        for (int k = threadIdx.x; k < nX; k += NT) {
+            int c = C.xcon[k];
+            double nb = C.st[c] < 0 ? lb_new(C, c) : ub_new(C, c);
+            double cb = C.st[c] < 0 ? C.lbc[c] : C.ubc[c];
+            C.dbX[k] = isinf(nb) ? 0.0 : nb - cb;
+        }
+        __syncthreads();
+        PH(14);
+        kkt_step(C, C.dg, C.dbw, C.dbX, C.dx, C.dyW, C.dyX);
+        Amul(C, C.dx, C.Adx);
+        PH(13);
+
+        double dxmax = 0;
+        for (int i = threadIdx.x; i < n; i += NT) dxmax = fmax(dxmax, fabs(C.dx[i]));
+        dxmax = block_max(C, dxmax);
+        double tau = 1.0; int key = 0x7fffffff;
+        for (int c = threadIdx.x; c < mt; c += NT) {
+            if (C.st[c] != 0 || C.anorm[c] == 0.0f) continue;      // all-zero rows can never be added
+            if (C.tabu[c] == 2) continue;                          // left during this run of zero steps: no re-entry
+            double adx = C.Adx[c];
+            const double rz = EPS_ROW * C.anorm[c] * dxmax;
+            if (!isinf(C.lbc[c])) {
+                double ln = lb_new(C, c);
+                double dlb = isinf(ln) ? 0.0 : ln - C.lbc[c];
+                double rate = adx - dlb;
+                double sl = C.Ax[c] - C.lbc[c]; if (sl < 0) sl = 0;
+                if (rate < -(EPS_RATE * (1.0 + fabs(adx) + fabs(dlb)) + rz) &&
+                    -rate - sl > FEAS_TOL * (1.0 + fabs(ln))) {
+                    double t = sl / (-rate);
+                    int k = 2 * c;
+                    if (t < tau || (t == tau && k < key && t < 1.0)) { tau = t; key = k; }
+                }
+            }
+            if (!isinf(C.ubc[c])) {
+                double un = ub_new(C, c);
+                double dub = isinf(un) ? 0.0 : un - C.ubc[c];
+                double rate = dub - adx;
+                double sl = C.ubc[c] - C.Ax[c]; if (sl < 0) sl = 0;
+                if (rate < -(EPS_RATE * (1.0 + fabs(adx) + fabs(dub)) + rz) &&
+                    -rate - sl > FEAS_TOL * (1.0 + fabs(un))) {
+                    double t = sl / (-rate);
+                    int k = 2 * c + 1;
+                    if (t < tau || (t == tau && k < key && t < 1.0)) { tau = t; key = k; }
+                }
+            }
+        }
+        double dys = 0;
+        for (int r = nZ + threadIdx.x; r < nF; r += NT) dys = fmax(dys, fabs(C.dyW[r]));
+        for (int k = threadIdx.x; k < nX; k += NT) dys = fmax(dys, fabs(C.dyX[k]));
+        dys = block_max(C, dys);
+        const double thr = EPS_RATE * (1.0 + dys);
+        // dual ratio test; key = 2*mt + position (X entries are positions 0..nX-1, the general
+        // row of Qf column r is position nX + nF-1-r)
+        for (int q = threadIdx.x; q < nX + (nF - nZ); q += NT) {
+            int c; double yc, dy;
+            if (q < nX) { c = C.xcon[q]; yc = C.yX[q]; dy = C.dyX[q]; }
+            else { const int r = nF - 1 - (q - nX); c = C.widx[r]; yc = C.yW[r]; dy = C.dyW[r]; }
+            if (lb_new(C, c) == ub_new(C, c)) continue;
+            if (C.tabu[c] == 1) continue;            // entered during this run of zero steps: stays
+            int k = 2 * mt + q;
+            if (C.st[c] < 0 && dy < -thr) {
+                double t = (yc > 0 ? yc : 0) / (-dy);
+                if (t < tau || (t == tau && k < key && t < 1.0)) { tau = t; key = k; }
+            } else if (C.st[c] > 0 && dy > thr) {
+                double t = (yc < 0 ? -yc : 0) / dy;
+                if (t < tau || (t == tau && k < key && t < 1.0)) { tau = t; key = k; }
+            }
+        }
+        block_argmin(C, tau, key);
+        const bool full = !(tau < 1.0) || key == 0x7fffffff;
+        if (full) tau = 1.0;
+        // anti-cycling (see oracle/qp_oracle.c): constraints that enter while the homotopy makes no
+        // progress may not leave through the dual test until it does
+        const bool zero_step = !(tau > 1e-14);
+        if (!zero_step) for (int c = threadIdx.x; c < mt; c += NT) C.tabu[c] = 0;
+
+        // take the step
+        for (int i = threadIdx.x; i < n; i += NT) {
+            C.x[i] += tau * C.dx[i];
+            C.gcur[i] = full ? C.g[i] : C.gcur[i] + tau * C.dg[i];
+        }
+        for (int r = nZ + threadIdx.x; r < nF; r += NT) C.yW[r] += tau * C.dyW[r];
+        for (int k = threadIdx.x; k < nX; k += NT) C.yX[k] += tau * C.dyX[k];
+        for (int c = threadIdx.x; c < mt; c += NT) {
+            C.Ax[c] += tau * C.Adx[c];
+            double ln = lb_new(C, c), un = ub_new(C, c);
+            if (!isinf(ln)) C.lbc[c] = full ? ln : C.lbc[c] + tau * (ln - C.lbc[c]);
+            if (!isinf(un)) C.ubc[c] = full ? un : C.ubc[c] + tau * (un - C.ubc[c]);
+        }
+        __syncthreads();
+        PH(14);
+        if (full) break;
+        if (++iter > max_iter) { status = EEPACC_QP_MAXITER; break; }
+        if (iter == restart_after) {
+            // the warm-started path wanders (degenerate / non-convex stretches): start over from an
+            // all-fixed working set at the current point -- the cold-start path
+            cold_ws(C);
+            setup_aux(C);
+            for (int c = threadIdx.x; c < mt; c += NT) C.tabu[c] = 0;
+            __syncthreads();
+            continue;
+        }
+        if (io.dbg && veh == 0 && threadIdx.x == 0 && iter <= io.dbg_cap) {
+            double* o = io.dbg + (size_t)(iter - 1) * 4;
+            o[0] = tau; o[1] = (double)key; o[2] = (double)(C.nX + C.nF - C.nZ); o[3] = (double)n_exch;
+        }
+
+        if (key < 2 * mt) {
+            // ---------- primal blocking: add constraint ----------
+            const int blk = key >> 1, side = (key & 1) ? 1 : -1;
+            if (threadIdx.x == 0) {
+                if (side < 0) C.lbc[blk] = C.Ax[blk]; else C.ubc[blk] = C.Ax[blk];
+                if (zero_step) C.tabu[blk] = 1;
+            }
+            get_row(C, blk, C.t4);                      // full row (the exchange needs its fixed part)
+            double an2 = 0;
+            for (int j = threadIdx.x; j < n; j += NT) an2 += C.t4[j] * C.t4[j];
+            an2 = block_sum(C, an2);
+            gatherF(C, C.t4);
+            const int nZc = C.nZ;
+            if (givens_add(C, blk, side, C.gF, an2, nZc, nZc, true) == 0) {
+                if (threadIdx.x == 0) C.yW[nZc - 1] = 0.0;
+                __syncthreads();
+            } else {
+                // linearly dependent: a = A_W' lam (general rows and fixed variables), exchange by a dual ratio test
+                const int nFc = C.nF, nXc = C.nX;
+                double* lamG = C.dyW;                   // by Qf column (dyW / dyX are recomputed by the next KKT step)
+                double* lamX = C.dyX;
+                for (int r = nZc + threadIdx.x; r < nFc; r += NT) C.tF[r] = C.wv[r];
+                __syncthreads();
+                tsolve(C, nZc, nFc, C.tF, lamG);
+                ATmul(C, lamG, nullptr, C.t3);
+                for (int k = threadIdx.x; k < nXc; k += NT) { const int j = C.xvar[k]; lamX[k] = (C.t4[j] - C.t3[j]) / C.xcv[k]; }
+                __syncthreads();
+                double lmax = 0;
+                for (int r = nZc + threadIdx.x; r < nFc; r += NT) lmax = fmax(lmax, fabs(lamG[r]));
+                for (int k = threadIdx.x; k < nXc; k += NT) lmax = fmax(lmax, fabs(lamX[k]));
+                lmax = block_max(C, lmax);
+                double theta = INFINITY; int kk = 0x7fffffff;
+                for (int q = threadIdx.x; q < nXc + (nFc - nZc); q += NT) {
+                    int c; double yc, lr;
+                    if (q < nXc) { c = C.xcon[q]; yc = C.yX[q]; lr = lamX[q]; }
+                    else { const int r = nFc - 1 - (q - nXc); c = C.widx[r]; yc = C.yW[r]; lr = lamG[r]; }
+                    if (lb_new(C, c) == ub_new(C, c)) continue;
+                    double l = (side < 0) ? lr : -lr;
+                    if (fabs(l) <= 1e-11 * (1.0 + lmax)) continue;
+                    if (C.st[c] < 0 && l > 0) {
+                        double th = (yc > 0 ? yc : 0) / l;
+                        if (th < theta || (th == theta && q < kk)) { theta = th; kk = q; }
+                    } else if (C.st[c] > 0 && l < 0) {
+                        double th = (yc < 0 ? yc : 0) / l;
+                        if (th < theta || (th == theta && q < kk)) { theta = th; kk = q; }
+                    }
+                }
+                block_argmin(C, theta, kk);
+                if (kk == 0x7fffffff) { status = EEPACC_QP_INFEASIBLE; break; }
+                for (int r = nZc + threadIdx.x; r < nFc; r += NT) C.yW[r] -= theta * ((side < 0) ? lamG[r] : -lamG[r]);
+                for (int k = threadIdx.x; k < nXc; k += NT) C.yX[k] -= theta * ((side < 0) ? lamX[k] : -lamX[k]);
+                __syncthreads();
+                if (kk < nXc) {
+                    if (threadIdx.x == 0 && zero_step) C.tabu[C.xcon[kk]] = 2;
+                    __syncthreads();
+                    if (free_var(C, kk)) { status = K3R_DEFER; break; }
+                } else {
+                    const int rp = nFc - 1 - (kk - nXc);
+                    if (threadIdx.x == 0 && zero_step) C.tabu[C.widx[rp]] = 2;
+                    __syncthreads();
+                    remove_general(C, rp);
+                }
+                // new T row over the range space of the freed column; R untouched
+                const int rn = C.nZ - 1;                 // freed column
+                gatherF(C, C.t4);
+                Qtmul(C, C.gF, C.tF, rn, C.nF);
+                for (int c = rn + threadIdx.x; c < C.nF; c += NT) MM(rn, c) = C.tF[c];
+                if (threadIdx.x == 0) {
+                    C.widx[rn] = (short)blk; C.st[blk] = (signed char)side;
+                    C.yW[rn] = (side < 0) ? theta : -theta;
+                }
+                C.nZ = rn;
+                __syncthreads();
+                n_exch++;
+            }
+            PH(15);
+        } else {
+            // ---------- dual blocking: remove constraint ----------
+            const int q = key - 2 * mt;
+            int c, side;
+            __syncthreads();
+            if (q < nX) {
+                c = C.xcon[q]; side = C.st[c];
+                __syncthreads();
+                if (threadIdx.x == 0 && zero_step) C.tabu[c] = 2;
+                if (free_var(C, q)) { status = K3R_DEFER; break; }
+            } else {
+                const int rp = nF - 1 - (q - nX);
+                c = C.widx[rp]; side = C.st[c];
+                __syncthreads();
+                if (threadIdx.x == 0 && zero_step) C.tabu[c] = 2;
+                remove_general(C, rp);
+            }
+            int rc = resolve_pending(C, c, side, n_exch, zero_step);
+            PH(16);
+            if (rc) { status = rc; break; }
+        }
+    }
+
+    if (status == K3R_DEFER) return K3R_DEFER;      // untouched warm state: the caller hands the vehicle over
+
+    // ---------------- iterative refinement on the final working set ----------------
+    if (status == EEPACC_QP_OK) {
+        const int nZ = C.nZ, nF = C.nF, nX = C.nX;
+        Amul(C, C.x, C.Adx);
+        Hmul(C, C.x, C.t4);
+        ATmul(C, C.yW, C.yX, C.t3);
+        // rg = Hx + g - A_W' y ; rb = bound - a'x
+        for (int j = threadIdx.x; j < n; j += NT) C.dg[j] = C.t4[j] + C.g[j] - C.t3[j];
+        for (int r = nZ + threadIdx.x; r < nF; r += NT) {
+            const int c = C.widx[r];
+            C.dbw[r] = (C.st[c] < 0 ? C.lbc[c] : C.ubc[c]) - C.Adx[c];
+        }
+        for (int k = threadIdx.x; k < nX; k += NT) {
+            const int c = C.xcon[k];
+            C.dbX[k] = (C.st[c] < 0 ? C.lbc[c] : C.ubc[c]) - C.Adx[c];
+        }
+        __syncthreads();
+        PH(17);
+        kkt_step(C, C.dg, C.dbw, C.dbX, C.dx, C.dyW, C.dyX);
+        for (int i = threadIdx.x; i < n; i += NT) C.x[i] += C.dx[i];
+        for (int r = nZ + threadIdx.x; r < nF; r += NT) C.yW[r] += C.dyW[r];
+        for (int k = threadIdx.x; k < nX; k += NT) C.yX[k] += C.dyX[k];
+        __syncthreads();
+    }
+    PH(17);
+
+    // ---------------- outputs + warm-start state ----------------
+    {
+        Hmul(C, C.x, C.t1);
+        double s = 0;
+        for (int i = threadIdx.x; i < n; i += NT) s += C.x[i] * (0.5 * (C.t1[i] - C.reg * C.x[i]) + C.g[i]);
+        s = block_sum(C, s);
+        const int nZ = C.nZ, nF = C.nF, nX = C.nX, nA = nX + nF - nZ;
+        if (status == EEPACC_QP_OK) {
+            int far = 0;
+            for (int r = nZ + threadIdx.x; r < nF; r += NT) { int c = C.widx[r]; if (c >= m && fabs(C.x[c - m]) >= FARB) far = 1; }
+            for (int k = threadIdx.x; k < nX; k += NT) { int c = C.xcon[k]; if (c >= m && fabs(C.x[c - m]) >= FARB) far = 1; }
+            if (block_max(C, (double)far) > 0) status = EEPACC_QP_UNBOUNDED;
+            int zr = 0;         // an all-zero row with inconsistent bounds: infeasible QP
+            for (int c = threadIdx.x; c < m; c += NT)
+                if (C.anorm[c] == 0.0 && (lb_new(C, c) > 1e-8 || ub_new(C, c) < -1e-8)) zr = 1;
+            if (block_max(C, (double)zr) > 0) status = EEPACC_QP_INFEASIBLE;
+        }
+        // warm-start state in the layout of k3_qp.cu: position q lives at index n-1-q
+        for (int i = threadIdx.x; i < n; i += NT) {
+            io.x[veh * (size_t)n + i] = C.x[i];
+            io.wx[veh * (size_t)n + i] = C.x[i];
+            const int q = n - 1 - i;
+            double yv = 0.0; short ci = -1; signed char sd = 0;
+            if (q < nX) { yv = C.yX[q]; ci = C.xcon[q]; sd = C.st[ci]; }
+            else if (q < nA) { const int r = nF - 1 - (q - nX); yv = C.yW[r]; ci = C.widx[r]; sd = C.st[ci]; }
+            io.wy[veh * (size_t)n + i] = yv;
+            io.widx[veh * (size_t)n + i] = ci;
+            io.wside[veh * (size_t)n + i] = sd;
+        }
+        if (threadIdx.x == 0) {
+            io.cost[veh] = s;
+            io.status[veh] = (double)status;
+            io.iter[veh] = (double)iter;
+            io.wnA[veh] = nA;
+            io.warm[veh] = (status == EEPACC_QP_OK) ? 1 : 0;
+#ifdef EEP_K3_TIMERS
+            PH(18);
+            if (io.dbg && veh == 0) for (int q = 0; q < 28; ++q) io.dbg[(size_t)io.dbg_cap * 4 + q] = (double)C.ph[q];
+#endif
+            if (io.counters) {
+                io.counters[veh * 4 + 0] += (unsigned long long)iter;
+                io.counters[veh * 4 + 1] += (status != EEPACC_QP_OK);
+                io.counters[veh * 4 + 2] += n_exch;
+                io.counters[veh * 4 + 3] += n_refac;
+            }
+        }
+    }
+    return status;
+}
+
+template <int NU, int NB>
+__device__ __forceinline__ void k3r_body(const eep_qp_io& io, unsigned char* k3r_smem)
+{
+    typedef k3r::CtxT<NU, NB> CT;
+    CT C;
+    k3r_setup<NU, NB>(C, io, k3r_smem, io.fc);
+    k3r_tables(C, io);
+    // hand-over launch (large capacity): only the vehicles the first level could not hold
     const long long n_work = io.todo_list ? (long long)*io.todo_cnt : io.B;
     for (long long wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
         const long long veh = io.todo_list ? (long long)io.todo_list[wi] : wi;
-        __syncthreads();
-        int status = EEPACC_QP_OK, iter = 0;
-        const int max_iter = 5 * (n + m);
-        const int restart_after = (4 * n > 400 ? 4 * n : 400);
-        unsigned long long n_exch = 0, n_refac = 0;
-#ifdef EEP_K3_TIMERS
-        if (threadIdx.x == 0) { for (int q = 0; q < 32; ++q) C.ph[q] = 0; C.ph[32] = clock64(); }
-#endif
-
-        // gradient, bounds, structured block, Hessian scale, LP regularisation, row norms
-        {
-            const double* gg = io.g + veh * (size_t)n;
-            const double* la = io.lba + veh * (size_t)m;
-            const double* ua = io.uba + veh * (size_t)m;
-            for (int i = threadIdx.x; i < n; i += NT) gS[i] = gg[i];
-            C.lba = la; C.uba = ua;
-            {
-                double* hs = io.hscr + veh * (size_t)(4 * mt);
-                C.Ax = hs; C.lbc = hs + mt; C.ubc = hs + 2 * mt; C.Adx = hs + 3 * mt;
-            }
-            const double* sb = io.sblk + veh * (size_t)EEP_SBLK;
-            for (int e = threadIdx.x; e < (EEP_N + 1) * EEP_N; e += NT) { C.PS[e] = sb[EEP_SB_PS + e]; C.PV[e] = sb[EEP_SB_PV + e]; }
-            for (int e = threadIdx.x; e < EEP_N * 9; e += NT) { C.Dc[e] = sb[EEP_SB_DC + e]; C.Cc[e] = sb[EEP_SB_CC + e]; }
-            for (int e = threadIdx.x; e < EEP_N * 4; e += NT) C.Dg[e] = sb[EEP_SB_DG + e];
-            for (int e = threadIdx.x; e < EEP_N; e += NT) C.vest[e] = sb[EEP_SB_VEST + e];
-            C.reg = (sb[EEP_SB_HMAX] == 0.0) ? LP_REG : 0.0;
-            C.hscale = fmax(sb[EEP_SB_HSCALE], LP_REG);
-            __syncthreads();
-            for (int r = threadIdx.x; r < m; r += NT) {
-                const RowW rd = row_load(C, r);
-                double sa = 0;
-                if (rd.kst >= 0) {
-                    const double cV = row_cV(C, rd), cS = (rd.aux & 128) ? 1.0 : 0.0;
-                    for (int i = 0; i < rd.kst && i < EEP_N; ++i)
-                        sa += CT::nb * fabs(cS * C.PS[rd.kst * EEP_N + i] + cV * C.PV[rd.kst * EEP_N + i]);
-                }
-                if (rd.j0 != 255) sa += fabs(C.cvals[rd.i0]);
-                if (rd.j1 != 255) sa += fabs(C.cvals[rd.i1]);
-                if (rd.j2 != 255) sa += fabs(C.cvals[rd.i2]);
-                if (rd.kst == -2) sa += CT::nb;
-                C.anorm[r] = (float)sa;
-            }
-        }
-        for (int j = threadIdx.x; j < n; j += NT) C.anorm[m + j] = 1.0f;
-        for (int c = threadIdx.x; c < mt; c += NT) C.tabu[c] = 0;
-        __syncthreads();
-        PH(0);
-
-        // ---------------- set-up ----------------
-        const int was_warm = io.warm[veh];
-        bool need_cold = !was_warm;
-        for (int i = threadIdx.x; i < n; i += NT) C.x[i] = was_warm ? io.wx[veh * (size_t)n + i] : 0.0;
-        if (!need_cold) {
-            if (warm_setup(C, io.wnA[veh], io.widx + veh * (size_t)n, io.wside + veh * (size_t)n, io.wy + veh * (size_t)n))
-                status = K3R_DEFER;
-            else {
-                n_refac++;
-                if (refactor_R(C)) need_cold = true;
-                PH(5);
-            }
-        }
-        if (status == EEPACC_QP_OK) {
-            if (need_cold) cold_ws(C);
-            setup_aux(C);
-        }
-        PH(6);
-
-        // ---------------- homotopy ----------------
-        while (status == EEPACC_QP_OK) {
-            const int nZ = C.nZ, nF = C.nF, nX = C.nX;
-            for (int i = threadIdx.x; i < n; i += NT) C.dg[i] = C.g[i] - C.gcur[i];
-            for (int r = nZ + threadIdx.x; r < nF; r += NT) {
-                int c = C.widx[r];
-                double nb = C.st[c] < 0 ? lb_new(C, c) : ub_new(C, c);
-                double cb = C.st[c] < 0 ? C.lbc[c] : C.ubc[c];
-                C.dbw[r] = isinf(nb) ? 0.0 : nb - cb;
-            }
-            for (int k = threadIdx.x; k < nX; k += NT) {
-                int c = C.xcon[k];
-                double nb = C.st[c] < 0 ? lb_new(C, c) : ub_new(C, c);
-                double cb = C.st[c] < 0 ? C.lbc[c] : C.ubc[c];
-                C.dbX[k] = isinf(nb) ? 0.0 : nb - cb;
-            }
-            __syncthreads();
-            PH(14);
-            kkt_step(C, C.dg, C.dbw, C.dbX, C.dx, C.dyW, C.dyX);
-            Amul(C, C.dx, C.Adx);
-            PH(13);
-
-            double dxmax = 0;
-            for (int i = threadIdx.x; i < n; i += NT) dxmax = fmax(dxmax, fabs(C.dx[i]));
-            dxmax = block_max(C, dxmax);
-            double tau = 1.0; int key = 0x7fffffff;
-            for (int c = threadIdx.x; c < mt; c += NT) {
-                if (C.st[c] != 0 || C.anorm[c] == 0.0f) continue;      // all-zero rows can never be added
-                if (C.tabu[c] == 2) continue;                          // left during this run of zero steps: no re-entry
-                double adx = C.Adx[c];
-                const double rz = EPS_ROW * C.anorm[c] * dxmax;
-                if (!isinf(C.lbc[c])) {
-                    double ln = lb_new(C, c);
-                    double dlb = isinf(ln) ? 0.0 : ln - C.lbc[c];
-                    double rate = adx - dlb;
-                    double sl = C.Ax[c] - C.lbc[c]; if (sl < 0) sl = 0;
-                    if (rate < -(EPS_RATE * (1.0 + fabs(adx) + fabs(dlb)) + rz) &&
-                        -rate - sl > FEAS_TOL * (1.0 + fabs(ln))) {
-                        double t = sl / (-rate);
-                        int k = 2 * c;
-                        if (t < tau || (t == tau && k < key && t < 1.0)) { tau = t; key = k; }
-                    }
-                }
-                if (!isinf(C.ubc[c])) {
-                    double un = ub_new(C, c);
-                    double dub = isinf(un) ? 0.0 : un - C.ubc[c];
-                    double rate = dub - adx;
-                    double sl = C.ubc[c] - C.Ax[c]; if (sl < 0) sl = 0;
-                    if (rate < -(EPS_RATE * (1.0 + fabs(adx) + fabs(dub)) + rz) &&
-                        -rate - sl > FEAS_TOL * (1.0 + fabs(un))) {
-                        double t = sl / (-rate);
-                        int k = 2 * c + 1;
-                        if (t < tau || (t == tau && k < key && t < 1.0)) { tau = t; key = k; }
-                    }
-                }
-            }
-            double dys = 0;
-            for (int r = nZ + threadIdx.x; r < nF; r += NT) dys = fmax(dys, fabs(C.dyW[r]));
-            for (int k = threadIdx.x; k < nX; k += NT) dys = fmax(dys, fabs(C.dyX[k]));
-            dys = block_max(C, dys);
-            const double thr = EPS_RATE * (1.0 + dys);
-            // dual ratio test; key = 2*mt + position (X entries are positions 0..nX-1, the general
-            // row of Qf column r is position nX + nF-1-r)
-            for (int q = threadIdx.x; q < nX + (nF - nZ); q += NT) {
-                int c; double yc, dy;
-                if (q < nX) { c = C.xcon[q]; yc = C.yX[q]; dy = C.dyX[q]; }
-                else { const int r = nF - 1 - (q - nX); c = C.widx[r]; yc = C.yW[r]; dy = C.dyW[r]; }
-                if (lb_new(C, c) == ub_new(C, c)) continue;
-                if (C.tabu[c] == 1) continue;            // entered during this run of zero steps: stays
-                int k = 2 * mt + q;
-                if (C.st[c] < 0 && dy < -thr) {
-                    double t = (yc > 0 ? yc : 0) / (-dy);
-                    if (t < tau || (t == tau && k < key && t < 1.0)) { tau = t; key = k; }
-                } else if (C.st[c] > 0 && dy > thr) {
-                    double t = (yc < 0 ? -yc : 0) / dy;
-                    if (t < tau || (t == tau && k < key && t < 1.0)) { tau = t; key = k; }
-                }
-            }
-            block_argmin(C, tau, key);
-            const bool full = !(tau < 1.0) || key == 0x7fffffff;
-            if (full) tau = 1.0;
-            // anti-cycling (see oracle/qp_oracle.c): constraints that enter while the homotopy makes no
-            // progress may not leave through the dual test until it does
-            const bool zero_step = !(tau > 1e-14);
-            if (!zero_step) for (int c = threadIdx.x; c < mt; c += NT) C.tabu[c] = 0;
-
-            // take the step
-            for (int i = threadIdx.x; i < n; i += NT) {
-                C.x[i] += tau * C.dx[i];
-                C.gcur[i] = full ? C.g[i] : C.gcur[i] + tau * C.dg[i];
-            }
-            for (int r = nZ + threadIdx.x; r < nF; r += NT) C.yW[r] += tau * C.dyW[r];
-            for (int k = threadIdx.x; k < nX; k += NT) C.yX[k] += tau * C.dyX[k];
-            for (int c = threadIdx.x; c < mt; c += NT) {
-                C.Ax[c] += tau * C.Adx[c];
-                double ln = lb_new(C, c), un = ub_new(C, c);
-                if (!isinf(ln)) C.lbc[c] = full ? ln : C.lbc[c] + tau * (ln - C.lbc[c]);
-                if (!isinf(un)) C.ubc[c] = full ? un : C.ubc[c] + tau * (un - C.ubc[c]);
-            }
-            __syncthreads();
-            PH(14);
-            if (full) break;
-            if (++iter > max_iter) { status = EEPACC_QP_MAXITER; break; }
-            if (iter == restart_after) {
-                // the warm-started path wanders (degenerate / non-convex stretches): start over from an
-                // all-fixed working set at the current point -- the cold-start path
-                cold_ws(C);
-                setup_aux(C);
-                for (int c = threadIdx.x; c < mt; c += NT) C.tabu[c] = 0;
-                __syncthreads();
-                continue;
-            }
-            if (io.dbg && veh == 0 && threadIdx.x == 0 && iter <= io.dbg_cap) {
-                double* o = io.dbg + (size_t)(iter - 1) * 4;
-                o[0] = tau; o[1] = (double)key; o[2] = (double)(C.nX + C.nF - C.nZ); o[3] = (double)n_exch;
-            }
-
-            if (key < 2 * mt) {
-                // ---------- primal blocking: add constraint ----------
-                const int blk = key >> 1, side = (key & 1) ? 1 : -1;
-                if (threadIdx.x == 0) {
-                    if (side < 0) C.lbc[blk] = C.Ax[blk]; else C.ubc[blk] = C.Ax[blk];
-                    if (zero_step) C.tabu[blk] = 1;
-                }
-                get_row(C, blk, C.t4);                      // full row (the exchange needs its fixed part)
-                double an2 = 0;
-                for (int j = threadIdx.x; j < n; j += NT) an2 += C.t4[j] * C.t4[j];
-                an2 = block_sum(C, an2);
-                gatherF(C, C.t4);
-                const int nZc = C.nZ;
-                if (givens_add(C, blk, side, C.gF, an2, nZc, nZc, true) == 0) {
-                    if (threadIdx.x == 0) C.yW[nZc - 1] = 0.0;
-                    __syncthreads();
-                } else {
-                    // linearly dependent: a = A_W' lam (general rows and fixed variables), exchange by a dual ratio test
-                    const int nFc = C.nF, nXc = C.nX;
-                    double* lamG = C.dyW;                   // by Qf column (dyW / dyX are recomputed by the next KKT step)
-                    double* lamX = C.dyX;
-                    for (int r = nZc + threadIdx.x; r < nFc; r += NT) C.tF[r] = C.wv[r];
-                    __syncthreads();
-                    tsolve(C, nZc, nFc, C.tF, lamG);
-                    ATmul(C, lamG, nullptr, C.t3);
-                    for (int k = threadIdx.x; k < nXc; k += NT) { const int j = C.xvar[k]; lamX[k] = (C.t4[j] - C.t3[j]) / C.xcv[k]; }
-                    __syncthreads();
-                    double lmax = 0;
-                    for (int r = nZc + threadIdx.x; r < nFc; r += NT) lmax = fmax(lmax, fabs(lamG[r]));
-                    for (int k = threadIdx.x; k < nXc; k += NT) lmax = fmax(lmax, fabs(lamX[k]));
-                    lmax = block_max(C, lmax);
-                    double theta = INFINITY; int kk = 0x7fffffff;
-                    for (int q = threadIdx.x; q < nXc + (nFc - nZc); q += NT) {
-                        int c; double yc, lr;
-                        if (q < nXc) { c = C.xcon[q]; yc = C.yX[q]; lr = lamX[q]; }
-                        else { const int r = nFc - 1 - (q - nXc); c = C.widx[r]; yc = C.yW[r]; lr = lamG[r]; }
-                        if (lb_new(C, c) == ub_new(C, c)) continue;
-                        double l = (side < 0) ? lr : -lr;
-                        if (fabs(l) <= 1e-11 * (1.0 + lmax)) continue;
-                        if (C.st[c] < 0 && l > 0) {
-                            double th = (yc > 0 ? yc : 0) / l;
-                            if (th < theta || (th == theta && q < kk)) { theta = th; kk = q; }
-                        } else if (C.st[c] > 0 && l < 0) {
-                            double th = (yc < 0 ? yc : 0) / l;
-                            if (th < theta || (th == theta && q < kk)) { theta = th; kk = q; }
-                        }
-                    }
-                    block_argmin(C, theta, kk);
-                    if (kk == 0x7fffffff) { status = EEPACC_QP_INFEASIBLE; break; }
-                    for (int r = nZc + threadIdx.x; r < nFc; r += NT) C.yW[r] -= theta * ((side < 0) ? lamG[r] : -lamG[r]);
-                    for (int k = threadIdx.x; k < nXc; k += NT) C.yX[k] -= theta * ((side < 0) ? lamX[k] : -lamX[k]);
-                    __syncthreads();
-                    if (kk < nXc) {
-                        if (threadIdx.x == 0 && zero_step) C.tabu[C.xcon[kk]] = 2;
-                        __syncthreads();
-                        if (free_var(C, kk)) { status = K3R_DEFER; break; }
-                    } else {
-                        const int rp = nFc - 1 - (kk - nXc);
-                        if (threadIdx.x == 0 && zero_step) C.tabu[C.widx[rp]] = 2;
-                        __syncthreads();
-                        remove_general(C, rp);
-                    }
-                    // new T row over the range space of the freed column; R untouched
-                    const int rn = C.nZ - 1;                 // freed column
-                    gatherF(C, C.t4);
-                    Qtmul(C, C.gF, C.tF, rn, C.nF);
-                    for (int c = rn + threadIdx.x; c < C.nF; c += NT) MM(rn, c) = C.tF[c];
-                    if (threadIdx.x == 0) {
-                        C.widx[rn] = (short)blk; C.st[blk] = (signed char)side;
-                        C.yW[rn] = (side < 0) ? theta : -theta;
-                    }
-                    C.nZ = rn;
-                    __syncthreads();
-                    n_exch++;
-                }
-                PH(15);
-            } else {
-                // ---------- dual blocking: remove constraint ----------
-                const int q = key - 2 * mt;
-                int c, side;
-                __syncthreads();
-                if (q < nX) {
-                    c = C.xcon[q]; side = C.st[c];
-                    __syncthreads();
-                    if (threadIdx.x == 0 && zero_step) C.tabu[c] = 2;
-                    if (free_var(C, q)) { status = K3R_DEFER; break; }
-                } else {
-                    const int rp = nF - 1 - (q - nX);
-                    c = C.widx[rp]; side = C.st[c];
-                    __syncthreads();
-                    if (threadIdx.x == 0 && zero_step) C.tabu[c] = 2;
-                    remove_general(C, rp);
-                }
-                int rc = resolve_pending(C, c, side, n_exch, zero_step);
-                PH(16);
-                if (rc) { status = rc; break; }
-            }
-        }
-
-        if (status == K3R_DEFER) {
-            // untouched warm state: the full-space kernel solves this vehicle from scratch
-            if (threadIdx.x == 0) {
+        if (k3r_vehicle(C, io, veh) == K3R_DEFER && threadIdx.x == 0) {
 #ifdef EEP_HOST_EMU
-                io.defer_list[(*io.defer_cnt)++] = (int)veh;
+            io.defer_list[(*io.defer_cnt)++] = (int)veh;
 #else
-                io.defer_list[atomicAdd(io.defer_cnt, 1)] = (int)veh;
+            io.defer_list[atomicAdd(io.defer_cnt, 1)] = (int)veh;
 #endif
-            }
-            continue;
-        }
-
-        // ---------------- iterative refinement on the final working set ----------------
-        if (status == EEPACC_QP_OK) {
-            const int nZ = C.nZ, nF = C.nF, nX = C.nX;
-            Amul(C, C.x, C.Adx);
-            Hmul(C, C.x, C.t4);
-            ATmul(C, C.yW, C.yX, C.t3);
-            // rg = Hx + g - A_W' y ; rb = bound - a'x
-            for (int j = threadIdx.x; j < n; j += NT) C.dg[j] = C.t4[j] + C.g[j] - C.t3[j];
-            for (int r = nZ + threadIdx.x; r < nF; r += NT) {
-                const int c = C.widx[r];
-                C.dbw[r] = (C.st[c] < 0 ? C.lbc[c] : C.ubc[c]) - C.Adx[c];
-            }
-            for (int k = threadIdx.x; k < nX; k += NT) {
-                const int c = C.xcon[k];
-                C.dbX[k] = (C.st[c] < 0 ? C.lbc[c] : C.ubc[c]) - C.Adx[c];
-            }
-            __syncthreads();
-            PH(17);
-            kkt_step(C, C.dg, C.dbw, C.dbX, C.dx, C.dyW, C.dyX);
-            for (int i = threadIdx.x; i < n; i += NT) C.x[i] += C.dx[i];
-            for (int r = nZ + threadIdx.x; r < nF; r += NT) C.yW[r] += C.dyW[r];
-            for (int k = threadIdx.x; k < nX; k += NT) C.yX[k] += C.dyX[k];
-            __syncthreads();
-        }
-        PH(17);
-
-        // ---------------- outputs + warm-start state ----------------
-        {
-            Hmul(C, C.x, C.t1);
-            double s = 0;
-            for (int i = threadIdx.x; i < n; i += NT) s += C.x[i] * (0.5 * (C.t1[i] - C.reg * C.x[i]) + C.g[i]);
-            s = block_sum(C, s);
-            const int nZ = C.nZ, nF = C.nF, nX = C.nX, nA = nX + nF - nZ;
-            if (status == EEPACC_QP_OK) {
-                int far = 0;
-                for (int r = nZ + threadIdx.x; r < nF; r += NT) { int c = C.widx[r]; if (c >= m && fabs(C.x[c - m]) >= FARB) far = 1; }
-                for (int k = threadIdx.x; k < nX; k += NT) { int c = C.xcon[k]; if (c >= m && fabs(C.x[c - m]) >= FARB) far = 1; }
-                if (block_max(C, (double)far) > 0) status = EEPACC_QP_UNBOUNDED;
-                int zr = 0;         // an all-zero row with inconsistent bounds: infeasible QP
-                for (int c = threadIdx.x; c < m; c += NT)
-                    if (C.anorm[c] == 0.0 && (lb_new(C, c) > 1e-8 || ub_new(C, c) < -1e-8)) zr = 1;
-                if (block_max(C, (double)zr) > 0) status = EEPACC_QP_INFEASIBLE;
-            }
-            // warm-start state in the layout of k3_qp.cu: position q lives at index n-1-q
-            for (int i = threadIdx.x; i < n; i += NT) {
-                io.x[veh * (size_t)n + i] = C.x[i];
-                io.wx[veh * (size_t)n + i] = C.x[i];
-                const int q = n - 1 - i;
-                double yv = 0.0; short ci = -1; signed char sd = 0;
-                if (q < nX) { yv = C.yX[q]; ci = C.xcon[q]; sd = C.st[ci]; }
-                else if (q < nA) { const int r = nF - 1 - (q - nX); yv = C.yW[r]; ci = C.widx[r]; sd = C.st[ci]; }
-                io.wy[veh * (size_t)n + i] = yv;
-                io.widx[veh * (size_t)n + i] = ci;
-                io.wside[veh * (size_t)n + i] = sd;
-            }
-            if (threadIdx.x == 0) {
-                io.cost[veh] = s;
-                io.status[veh] = (double)status;
-                io.iter[veh] = (double)iter;
-                io.wnA[veh] = nA;
-                io.warm[veh] = (status == EEPACC_QP_OK) ? 1 : 0;
-#ifdef EEP_K3_TIMERS
-                PH(18);
-                if (io.dbg && veh == 0) for (int q = 0; q < 28; ++q) io.dbg[(size_t)io.dbg_cap * 4 + q] = (double)C.ph[q];
-#endif
-                if (io.counters) {
-                    io.counters[veh * 4 + 0] += (unsigned long long)iter;
-                    io.counters[veh * 4 + 1] += (status != EEPACC_QP_OK);
-                    io.counters[veh * 4 + 2] += n_exch;
-                    io.counters[veh * 4 + 3] += n_refac;
-                }
-            }
         }
     }
 }
@@ -1742,6 +1772,108 @@ static int launch_qpr(const eep_qp_io* io, cudaStream_t st)
     if (g < 1) g = 1;
     if (g > 2147483647LL) g = 2147483647LL;
     k3r_qp_kernel<NU, NB><<<(int)g, NT, sm, st>>>(*io);
+    return (int)cudaGetLastError();
+}
+
+// =====================================================================================================
+// K5: fused closed loop.  The per-step path (K2 launch -> K3r launch -> hand-over launches -> K4 launch)
+// synchronises ALL vehicles of a slice at every kernel boundary, so every MPC step costs the slice its slowest
+// vehicle (ncu, step 41 of a cycle: SMs 21 % active inside a K3r launch, the rest is the tail).  Here a CTA
+// takes ONE vehicle through all its MPC steps; vehicles are handed out by an atomic counter; a solve that
+// outgrows the shared-memory capacity is repeated in place at full capacity from a global work area.
+// =====================================================================================================
+#include "k2_build.cuh"
+#include "k4_post.cuh"
+
+template <int NU, int NB>
+__global__ void __launch_bounds__(NT, K3R_MINB) k5_cycle_kernel(const eepacc_params p, const eep_cycle_io cy)
+{
+    typedef k3r::CtxT<NU, NB> CT;
+    CT C;
+    k3r_setup<NU, NB>(C, cy.q, k3r_smem, cy.q.fc);
+    BuildSmem& S = *reinterpret_cast<BuildSmem*>(k3r_smem);        // K2's work area overlays the solver's
+    __shared__ long long s_veh;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_veh = (long long)atomicAdd(cy.work_counter, 1ULL);
+        __syncthreads();
+        const long long veh = s_veh;
+        if (veh >= cy.q.B) break;
+        eep_build_io b = cy.b;
+        eep_post_io po = cy.p;
+        double t0 = cy.t0_begin;
+        long long c_build = 0, c_qp = 0, c_big = 0, c_post = 0;     // thread 0: where this vehicle's cycles go
+        for (int k = cy.k_begin; k < cy.k_end; ++k) {
+            const long long tk0 = clock64();
+            b.kk = k; b.t0 = t0;
+            b.lead = cy.lead_all ? cy.lead_all + (size_t)k * cy.lead_stride : nullptr;
+            k2_vehicle<NT>(p, b, veh, S);
+            __syncthreads();                                       // K2's outputs (global) are visible to the CTA
+            const long long tk1 = clock64();
+            k3r_tables(C, cy.q);
+            int st = k3r_vehicle(C, cy.q, veh);
+            const long long tk2 = clock64();
+            if (st == K3R_DEFER) {
+                k3r_setup<NU, NB>(C, cy.q, cy.big + (size_t)blockIdx.x * cy.big_bytes, cy.fc_big);
+                __syncthreads();
+                k3r_tables(C, cy.q);
+                st = k3r_vehicle(C, cy.q, veh);                    // capacity n: cannot hand over again
+                k3r_setup<NU, NB>(C, cy.q, k3r_smem, cy.q.fc);
+            }
+            __syncthreads();
+            const long long tk3 = clock64();
+            if (threadIdx.x == 0) {
+                po.kk = k;
+                po.log = cy.log_all ? cy.log_all + (size_t)k * cy.log_stride : nullptr;
+                k4_vehicle(p, po, veh);
+                c_build += tk1 - tk0; c_qp += tk2 - tk1; c_big += tk3 - tk2; c_post += clock64() - tk3;
+            }
+            t0 += p.Ts;
+        }
+        if (threadIdx.x == 0 && cy.phase) {
+            atomicAdd(cy.phase + 0, (unsigned long long)c_build); atomicAdd(cy.phase + 1, (unsigned long long)c_qp);
+            atomicAdd(cy.phase + 2, (unsigned long long)c_big); atomicAdd(cy.phase + 3, (unsigned long long)c_post);
+        }
+    }
+}
+
+static size_t cycle_smem(const eep_cycle_io* cy)
+{
+    size_t sm = eep_qpr_smem_bytes(cy->q.n, cy->q.m, cy->q.fc);
+    if (sm < sizeof(BuildSmem)) sm = sizeof(BuildSmem);
+    return sm;
+}
+template <int NU, int NB>
+static int cycle_prepare(const eep_cycle_io* cy, int* ctas_per_sm)
+{
+    const size_t sm = cycle_smem(cy);
+    cudaError_t e = cudaFuncSetAttribute(k5_cycle_kernel<NU, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return (int)e;
+    int nb = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k5_cycle_kernel<NU, NB>, NT, sm);
+    if (e != cudaSuccess) return (int)e;
+    *ctas_per_sm = nb;
+    return 0;
+}
+extern "C" int eep_cycle_max_ctas_per_sm(const eep_cycle_io* cy)
+{
+    int nb = 0, rc;
+    switch (cy->q.ctrl) {
+    case EEPACC_FB: rc = cycle_prepare<6, 2>(cy, &nb); break;
+    case EEPACC_AB: rc = cycle_prepare<5, 1>(cy, &nb); break;
+    default: rc = cycle_prepare<2, 1>(cy, &nb); break;
+    }
+    return rc ? -1 : nb;
+}
+extern "C" int eep_launch_cycle(const eepacc_params* p, const eep_cycle_io* cy, int grid, cudaStream_t st)
+{
+    if (!cy->q.rowtab || !cy->q.rowc || !cy->q.sblk || !cy->q.hscr || !cy->work_counter || !cy->big) return (int)cudaErrorInvalidValue;
+    const size_t sm = cycle_smem(cy);
+    switch (cy->q.ctrl) {
+    case EEPACC_FB: k5_cycle_kernel<6, 2><<<grid, NT, sm, st>>>(*p, *cy); break;
+    case EEPACC_AB: k5_cycle_kernel<5, 1><<<grid, NT, sm, st>>>(*p, *cy); break;
+    default: k5_cycle_kernel<2, 1><<<grid, NT, sm, st>>>(*p, *cy); break;
+    }
     return (int)cudaGetLastError();
 }
 

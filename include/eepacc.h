@@ -159,6 +159,14 @@ int eepacc_mem_set_qp_mode(int mem, int mode, int fc);
  * 0 = automatic (up to 8 slices of >= 256 vehicles).  With G slices eepacc_mem_get_timing reports one latency
  * per (step, slice), step-major. */
 int eepacc_mem_set_groups(int mem, int groups);
+/* eepacc_run: 0 (default) = per-step launches over pipelined slices; 1 = after the cold-start step every vehicle
+ * runs its remaining MPC steps inside ONE fused kernel launch (no synchronisation between vehicles). */
+int eepacc_mem_set_fused(int mem, int on);
+int eepacc_mem_get_fused(int mem);
+/* out[7]: [0] duration in ms (CUDA events on the launching stream) of the last fused closed-loop launch, [1] its
+ * grid, [2] CTAs resident per SM, [3..6] SM clock cycles summed over all vehicle-steps spent in the build, the QP
+ * solve, the hand-over solves and the post stage. */
+int eepacc_mem_get_cycle_timing(int mem, double* out);
 int eepacc_mem_get_groups(int mem);
 /* Developer aid: copy a per-step device buffer of the closed loop to the host (0 sblk, 1 g, 2 lba, 3 uba,
  * 4 x, 5 status, 6 iter, 7 cost, 8 deferred-vehicle count); returns the number of doubles written or < 0. */
