@@ -73,7 +73,7 @@ struct Mem {
     cudaEvent_t cyc_ev[2] = { nullptr, nullptr };   // around the last fused launch (always recorded: two events per cycle)
     int cyc_grid = 0, cyc_per_sm = 0;
     int qp_mode = 0;            // 0: reduced-space kernel + full-space fallback, 1: full-space kernel only
-    int qp_fc = 48;             // capacity (free variables) of the reduced factorisation
+    int qp_fc = 56;             // capacity (free variables) of the reduced factorisation (measured: 48 -> 56 +1 % AB, +3 % FB; 64, 72 slower)
     long long deferred_total = 0;
     DBuf in[12], out[8];        // staging for host-pointer calls
     bool timing = false;        // CUDA-event timing of every kernel launch (bench.py roofline leg)
@@ -487,7 +487,7 @@ int eepacc_mem_setup(int mem, int ctrl, const eepacc_params* p, const eepacc_rou
         if (rc) return fail(EEPACC_ERR_CUDA, "constraint-row table of the reduced-space QP kernel", rc < 100000 ? (cudaError_t)rc : cudaSuccess);
     }
     // developer knobs (A/B runs): EEPACC_QP_MODE=1 forces the full-space kernel, EEPACC_QP_FC sets the capacity
-    M->qp_mode = 0; M->qp_fc = 48;
+    M->qp_mode = 0; M->qp_fc = 56;
     if (const char* e = getenv("EEPACC_QP_MODE")) M->qp_mode = atoi(e) ? 1 : 0;
     if (const char* e = getenv("EEPACC_QP_FC")) { int v = atoi(e); if (v >= 8 && v <= EEPACC_MAX_NVAR) M->qp_fc = v; }
     if (M->qp_fc > M->n) M->qp_fc = M->n;
@@ -521,7 +521,7 @@ int eepacc_mem_set_qp_mode(int mem, int mode, int fc)
     Mem* M = get_mem(mem);
     if (!M || !M->ready) return fail(EEPACC_ERR_ARG, "mem not set up");
     if (mode < 0 || mode > 1) return fail(EEPACC_ERR_ARG, "mode must be 0 or 1");
-    if (fc <= 0) fc = 48;
+    if (fc <= 0) fc = 56;
     if (fc < 8) fc = 8;
     if (fc > M->n) fc = M->n;
     M->qp_mode = mode; M->qp_fc = fc;

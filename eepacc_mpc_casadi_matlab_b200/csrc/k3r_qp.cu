@@ -39,6 +39,13 @@
 #define NT K3R_NT
 // The solver's primitives can be compiled as real functions (-DK3R_NOINLINE): the kernel shrinks from ~660 KB to
 // ~420 KB of SASS and compiles in 1 min instead of 12, but measured 15 % slower (calls, context in local memory).
+// thread-strided loops run 1-4 trips (n <= 120, m + n <= 642 over 128 threads): the default 4x unrolling only bloats
+// the code (-DK3R_UNROLL1 keeps them rolled)
+#ifdef K3R_UNROLL1
+#define K3R_LOOP _Pragma("unroll 1")
+#else
+#define K3R_LOOP
+#endif
 #ifdef K3R_NOINLINE
 #define K3R_FN __noinline__
 #else
@@ -49,6 +56,7 @@
 #else
 #define LDG(p) (*(p))
 #define K3R_FN
+#define K3R_LOOP
 #endif
 
 #define FARB      1.0e6
@@ -191,13 +199,13 @@ struct VestSrc { const double* v_est; };
 template <class CT> K3R_FN __device__ void s_prep(CT& C, const double* v)
 {
     const int NH = EEP_N;
-    for (int i = threadIdx.x; i < NH; i += NT) {
+    K3R_LOOP for (int i = threadIdx.x; i < NH; i += NT) {
         double d = v[i * CT::nu];
         if (CT::nb == 2) d += v[i * CT::nu + 1];
         C.drv[i] = d;
     }
     __syncthreads();
-    for (int k = threadIdx.x; k <= NH; k += NT) {
+    K3R_LOOP for (int k = threadIdx.x; k <= NH; k += NT) {
         double a = 0, b = 0;
         for (int i = 0; i < k && i < NH; ++i) { a += C.PS[k * NH + i] * C.drv[i]; b += C.PV[k * NH + i] * C.drv[i]; }
         C.sv[k] = a; C.vv[k] = b;
@@ -267,7 +275,7 @@ template <class CT> __device__ __forceinline__ bool s_unit(const CT& C, const Ro
 template <class CT> K3R_FN __device__ void get_row(CT& C, int c, double* a)
 {
     const RowW rd = row_load(C, c);
-    for (int j = threadIdx.x; j < C.n; j += NT) a[j] = s_entry(C, rd, j);
+    K3R_LOOP for (int j = threadIdx.x; j < C.n; j += NT) a[j] = s_entry(C, rd, j);
     __syncthreads();
 }
 template <class CT> K3R_FN __device__ void Hmul(CT& C, const double* v, double* out)
@@ -276,7 +284,7 @@ template <class CT> K3R_FN __device__ void Hmul(CT& C, const double* v, double* 
     const int NH = EEP_N, nu = CT::nu, nb = CT::nb;
     s_prep(C, v);
     // y_k on the core [v, driven]: D_k w_k + C_k w_{k-1} + C_{k+1}' w_{k+1}
-    for (int k = threadIdx.x; k < NH; k += NT) {
+    K3R_LOOP for (int k = threadIdx.x; k < NH; k += NT) {
         double w0[3] = { C.vv[k], v[k * nu], nb == 2 ? v[k * nu + 1] : 0.0 };
         double y[3] = { 0, 0, 0 };
         const double* D = C.Dc + k * 9;
@@ -294,7 +302,7 @@ template <class CT> K3R_FN __device__ void Hmul(CT& C, const double* v, double* 
         C.yc[k * 3] = y[0]; C.yc[k * 3 + 1] = y[1]; C.yc[k * 3 + 2] = y[2];
     }
     __syncthreads();
-    for (int j = threadIdx.x; j < n; j += NT) {
+    K3R_LOOP for (int j = threadIdx.x; j < n; j += NT) {
         const int i = j / nu, cj = j % nu;
         double val;
         if (cj < nb) {
@@ -311,10 +319,10 @@ template <class CT> K3R_FN __device__ void Amul(CT& C, const double* v, double* 
 {
     const int n = C.n, m = C.m;
     s_prep(C, v);
-    for (int r = threadIdx.x; r < m; r += NT) {
+    K3R_LOOP for (int r = threadIdx.x; r < m; r += NT) {
         out[r] = s_rowdot(C, row_load(C, r), v);
     }
-    for (int j = threadIdx.x; j < n; j += NT) out[m + j] = v[j];
+    K3R_LOOP for (int j = threadIdx.x; j < n; j += NT) out[m + j] = v[j];
     __syncthreads();
 }
 // w[j] = sum over the active general rows r in [nZ, nF) of A(widx[r], j) yv[r]
@@ -323,7 +331,7 @@ template <class CT> K3R_FN __device__ void ATmul(CT& C, const double* yv, const 
 {
     const int n = C.n, NH = EEP_N, nu = CT::nu, nb = CT::nb, nZ = C.nZ, nF = C.nF;
     __syncthreads();
-    for (int r = nZ + threadIdx.x; r < nF; r += NT) {
+    K3R_LOOP for (int r = nZ + threadIdx.x; r < nF; r += NT) {
         const RowW rd = row_load(C, C.widx[r]);
         const double y = yv[r];
         C.rk[r] = (short)rd.kst;
@@ -338,7 +346,7 @@ template <class CT> K3R_FN __device__ void ATmul(CT& C, const double* yv, const 
     }
     __syncthreads();
     // per-stage accumulators: thread k gathers its stage (oldest row first)
-    for (int k = threadIdx.x; k <= NH; k += NT) {
+    K3R_LOOP for (int k = threadIdx.x; k <= NH; k += NT) {
         double s = 0, v = 0, d = 0;
         for (int r = nF - 1; r >= nZ; --r) {
             const int kr = C.rk[r];
@@ -349,7 +357,7 @@ template <class CT> K3R_FN __device__ void ATmul(CT& C, const double* yv, const 
         if (k < NH) C.aD[k] = d;
     }
     __syncthreads();
-    for (int j = threadIdx.x; j < n; j += NT) {
+    K3R_LOOP for (int j = threadIdx.x; j < n; j += NT) {
         const int i = j / nu, cj = j % nu;
         double val = 0.0;
         for (int r = nF - 1; r >= nZ; --r) {           // oldest first
@@ -366,7 +374,7 @@ template <class CT> K3R_FN __device__ void ATmul(CT& C, const double* yv, const 
     }
     __syncthreads();
     if (yXv) {
-        for (int k = threadIdx.x; k < C.nX; k += NT) w[C.xvar[k]] += C.xcv[k] * yXv[k];
+        K3R_LOOP for (int k = threadIdx.x; k < C.nX; k += NT) w[C.xvar[k]] += C.xcv[k] * yXv[k];
         __syncthreads();
     }
 }
@@ -374,14 +382,14 @@ template <class CT> K3R_FN __device__ void ATmul(CT& C, const double* yv, const 
 // ---- reduced dense primitives; every routine ends with data visible after a __syncthreads() ----
 template <class CT> K3R_FN __device__ void gatherF(CT& C, const double* a)
 {
-    for (int i = threadIdx.x; i < C.nF; i += NT) C.gF[i] = a[C.flist[i]];
+    K3R_LOOP for (int i = threadIdx.x; i < C.nF; i += NT) C.gF[i] = a[C.flist[i]];
     __syncthreads();
 }
 // w[j] = qf_j' aF for j in [c0, c1), aF compact [nF]
 template <class CT> K3R_FN __device__ void Qtmul(CT& C, const double* aF, double* w, int c0, int c1)
 {
     const int nF = C.nF;
-    for (int j = c0 + threadIdx.x; j < c1; j += NT) {
+    K3R_LOOP for (int j = c0 + threadIdx.x; j < c1; j += NT) {
         double s0 = 0, s1 = 0;
         int i = 0;
         for (; i + 1 < nF; i += 2) { s0 += QF(i, j) * aF[i]; s1 += QF(i + 1, j) * aF[i + 1]; }
@@ -394,7 +402,7 @@ template <class CT> K3R_FN __device__ void Qtmul(CT& C, const double* aF, double
 template <class CT> K3R_FN __device__ void Qmul(CT& C, const double* p, int c0, int c1, double* outF)
 {
     const int nF = C.nF;
-    for (int i = threadIdx.x; i < nF; i += NT) {
+    K3R_LOOP for (int i = threadIdx.x; i < nF; i += NT) {
         double s0 = 0, s1 = 0;
         int c = c0;
         for (; c + 1 < c1; c += 2) { s0 += QF(i, c) * p[c]; s1 += QF(i, c + 1) * p[c + 1]; }
@@ -428,7 +436,7 @@ template <class CT> K3R_FN __device__ void usolve(CT& C, int lo, int hi, double*
             }
         }
         __syncthreads();
-        for (int i = lo + threadIdx.x; i < b0; i += NT) {
+        K3R_LOOP for (int i = lo + threadIdx.x; i < b0; i += NT) {
             double s0 = 0, s1 = 0;
             int c = b0;
             for (; c + 1 < b1; c += 2) { s0 += MM(i, c) * x[c]; s1 += MM(i, c + 1) * x[c + 1]; }
@@ -464,7 +472,7 @@ template <class CT> K3R_FN __device__ void tsolve(CT& C, int lo, int hi, double*
             }
         }
         __syncthreads();
-        for (int i = b1 + threadIdx.x; i < hi; i += NT) {
+        K3R_LOOP for (int i = b1 + threadIdx.x; i < hi; i += NT) {
             double s0 = 0, s1 = 0;
             int c = b0;
             for (; c + 1 < b1; c += 2) { s0 += MM(c, i) * y[c]; s1 += MM(c + 1, i) * y[c + 1]; }
@@ -485,7 +493,7 @@ template <class CT> K3R_FN __device__ int givens_add(CT& C, int cidx, int side, 
     Qtmul(C, aF, C.wv, 0, nF);
     if (check_li) {
         double zn = 0;
-        for (int j = threadIdx.x; j < nZt; j += NT) zn += C.wv[j] * C.wv[j];
+        K3R_LOOP for (int j = threadIdx.x; j < nZt; j += NT) zn += C.wv[j] * C.wv[j];
         zn = block_sum(C, zn);
         const double san = sqrt(an2);
         if (nZt == 0 || sqrt(zn) <= EPS_LI * (san > 1.0 ? san : 1.0)) return 1;
@@ -504,7 +512,7 @@ template <class CT> K3R_FN __device__ int givens_add(CT& C, int cidx, int side, 
     }
     __syncthreads();
     // Qf: one row per thread, rotations applied left to right with the carry in a register
-    for (int i = threadIdx.x; i < nF; i += NT) {
+    K3R_LOOP for (int i = threadIdx.x; i < nF; i += NT) {
         double u = QF(i, 0);
         for (int k = 0; k < nZt - 1; ++k) {
             double v = QF(i, k + 1);
@@ -516,7 +524,7 @@ template <class CT> K3R_FN __device__ int givens_add(CT& C, int cidx, int side, 
     }
     if (nR > 1) {
         // R phase A: column rotations k = 0..nR-2, one row of R per thread
-        for (int i = threadIdx.x; i < nR; i += NT) {
+        K3R_LOOP for (int i = threadIdx.x; i < nR; i += NT) {
             int k0 = i > 0 ? i - 1 : 0;
             double u;
             if (i > 0) {        // rotation k = i-1 mixes (i,i-1)=0 with (i,i)
@@ -541,7 +549,7 @@ template <class CT> K3R_FN __device__ int givens_add(CT& C, int cidx, int side, 
             __syncthreads();
             if (rr != 0.0) {
                 double c2 = pa / rr, s2 = pb / rr;
-                for (int j = k + threadIdx.x; j < nR; j += NT) {
+                K3R_LOOP for (int j = k + threadIdx.x; j < nR; j += NT) {
                     double u = MM(k, j);
                     double v = (j == k) ? pb : MM(k + 1, j);
                     MM(k, j) = c2 * u + s2 * v;
@@ -553,7 +561,7 @@ template <class CT> K3R_FN __device__ int givens_add(CT& C, int cidx, int side, 
     __syncthreads();
     // new T row = M row nZt-1 (columns >= nZt-1)
     const int rn = nZt - 1;
-    for (int c = rn + threadIdx.x; c < nF; c += NT) MM(rn, c) = C.wv[c];
+    K3R_LOOP for (int c = rn + threadIdx.x; c < nF; c += NT) MM(rn, c) = C.wv[c];
     if (threadIdx.x == 0) { C.widx[rn] = (short)cidx; C.st[cidx] = (signed char)side; }
     C.nZ = rn;
     __syncthreads();
@@ -568,7 +576,7 @@ template <class CT> K3R_FN __device__ void remove_general(CT& C, int rp)
     if (threadIdx.x == 0) C.st[C.widx[rp]] = 0;
     __syncthreads();
     // shift rows nZ..rp-1 one row down the diagonal (row r-1 -> row r); one column per thread
-    for (int c = nZ + threadIdx.x; c < nF; c += NT) {
+    K3R_LOOP for (int c = nZ + threadIdx.x; c < nF; c += NT) {
         if (c < rp) C.sub[c + 1] = MM(c, c);
         int rtop = c < rp ? c : rp;
         for (int r = rtop; r > nZ; --r) MM(r, c) = MM(r - 1, c);
@@ -586,7 +594,7 @@ template <class CT> K3R_FN __device__ void remove_general(CT& C, int rp)
         __syncthreads();
         if (threadIdx.x == 0) { C.csA[r] = cs; C.snA[r] = sn; }
         // rows r' in [nZ+1, r]: elements (r', r-1) and (r', r)
-        for (int rr = nZ + 1 + threadIdx.x; rr <= r; rr += NT) {
+        K3R_LOOP for (int rr = nZ + 1 + threadIdx.x; rr <= r; rr += NT) {
             double u = (rr == r) ? a : MM(rr, r - 1);
             double v = MM(rr, r);
             if (rr < r) MM(rr, r - 1) = cs * u - sn * v;
@@ -594,7 +602,7 @@ template <class CT> K3R_FN __device__ void remove_general(CT& C, int rp)
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < nF; i += NT) {
+    K3R_LOOP for (int i = threadIdx.x; i < nF; i += NT) {
         if (rp > nZ) {
             double v = QF(i, rp);
             for (int r = rp; r > nZ; --r) {
@@ -621,8 +629,8 @@ template <class CT> K3R_FN __device__ int free_var(CT& C, int k)
     const int j = C.xvar[k], c = C.xcon[k];
     const double cv = C.xcv[k], yk = C.yX[k];
     __syncthreads();
-    for (int i = threadIdx.x; i <= nF; i += NT) { QF(i, nF) = (i == nF) ? 1.0 : 0.0; QF(nF, i) = (i == nF) ? 1.0 : 0.0; }
-    for (int r = nZ + threadIdx.x; r < nF; r += NT) {
+    K3R_LOOP for (int i = threadIdx.x; i <= nF; i += NT) { QF(i, nF) = (i == nF) ? 1.0 : 0.0; QF(nF, i) = (i == nF) ? 1.0 : 0.0; }
+    K3R_LOOP for (int r = nZ + threadIdx.x; r < nF; r += NT) {
         const RowW rd = row_load(C, C.widx[r]);
         MM(r, nF) = s_entry(C, rd, j);
     }
@@ -648,7 +656,7 @@ template <class CT> K3R_FN __device__ int free_var(CT& C, int k)
 template <class CT> K3R_FN __device__ void HmulG(CT& C, int G, const double* V, double* OUT, double* scr)
 {
     const int n = C.n, NH = EEP_N, nu = CT::nu, nb = CT::nb;
-    for (int e = threadIdx.x; e < G * NH; e += NT) {
+    K3R_LOOP for (int e = threadIdx.x; e < G * NH; e += NT) {
         const int g = e / NH, i = e - g * NH;
         const double* v = V + g * n;
         double d = v[i * nu];
@@ -656,7 +664,7 @@ template <class CT> K3R_FN __device__ void HmulG(CT& C, int G, const double* V, 
         scr[g * HG_SCR + i] = d;                                    // drv
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < G * (NH + 1); e += NT) {
+    K3R_LOOP for (int e = threadIdx.x; e < G * (NH + 1); e += NT) {
         const int g = e / (NH + 1), k = e - g * (NH + 1);
         const double* drv = scr + g * HG_SCR;
         double a = 0, b = 0;
@@ -664,7 +672,7 @@ template <class CT> K3R_FN __device__ void HmulG(CT& C, int G, const double* V, 
         scr[g * HG_SCR + NH + k] = b;                               // vv (sv does not enter H v)
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < G * NH; e += NT) {
+    K3R_LOOP for (int e = threadIdx.x; e < G * NH; e += NT) {
         const int g = e / NH, k = e - g * NH;
         const double* v = V + g * n;
         const double* vv = scr + g * HG_SCR + NH;
@@ -686,7 +694,7 @@ template <class CT> K3R_FN __device__ void HmulG(CT& C, int G, const double* V, 
         yc[k * 3] = y[0]; yc[k * 3 + 1] = y[1]; yc[k * 3 + 2] = y[2];
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < G * n; e += NT) {
+    K3R_LOOP for (int e = threadIdx.x; e < G * n; e += NT) {
         const int g = e / n, j = e - g * n;
         const double* v = V + g * n;
         const double* yc = scr + g * HG_SCR + 2 * NH + 1;
@@ -715,9 +723,9 @@ template <class CT> K3R_FN __device__ int refactor_R(CT& C)
     double* scr = V + GMAX * n;
     for (int j0 = 0; j0 < nZ; j0 += GMAX) {
         const int G = (nZ - j0 < GMAX) ? nZ - j0 : GMAX;
-        for (int e = threadIdx.x; e < G * n; e += NT) V[e] = 0.0;
+        K3R_LOOP for (int e = threadIdx.x; e < G * n; e += NT) V[e] = 0.0;
         __syncthreads();
-        for (int e = threadIdx.x; e < G * nF; e += NT) {
+        K3R_LOOP for (int e = threadIdx.x; e < G * nF; e += NT) {
             const int g = e / nF, i = e - g * nF;
             V[g * n + C.flist[i]] = QF(i, j0 + g);
         }
@@ -725,7 +733,7 @@ template <class CT> K3R_FN __device__ int refactor_R(CT& C)
         HmulG(C, G, V, V, scr);
         // M(i, j0 + g) = z_i' (H z_(j0+g)),  i <= j0 + g
         const int rows = j0 + G;
-        for (int e = threadIdx.x; e < G * rows; e += NT) {
+        K3R_LOOP for (int e = threadIdx.x; e < G * rows; e += NT) {
             const int g = e / rows, i = e - g * rows;
             if (i > j0 + g) continue;
             const double* hz = V + g * n;
@@ -744,12 +752,12 @@ template <class CT> K3R_FN __device__ int refactor_R(CT& C)
         if (!(d > thr)) return 1;
         double rk = sqrt(d), inv = 1.0 / rk;
         const int w = nZ - 1 - k;                 // trailing dimension
-        for (int e = threadIdx.x; e < w * w; e += NT) {
+        K3R_LOOP for (int e = threadIdx.x; e < w * w; e += NT) {
             int i = k + 1 + e / w, j = k + 1 + e % w;
             if (j >= i) MM(i, j) -= (MM(k, i) * inv) * (MM(k, j) * inv);
         }
         __syncthreads();
-        for (int j = k + threadIdx.x; j < nZ; j += NT) MM(k, j) = (j == k) ? rk : MM(k, j) * inv;
+        K3R_LOOP for (int j = k + threadIdx.x; j < nZ; j += NT) MM(k, j) = (j == k) ? rk : MM(k, j) * inv;
     }
     __syncthreads();
     return 0;
@@ -761,42 +769,42 @@ template <class CT> K3R_FN __device__ void kkt_step(CT& C, const double* dg, con
 {
     const int n = C.n, nF = C.nF, nZ = C.nZ, nX = C.nX, nAC = nF - nZ;
     double* u = C.t2;
-    for (int i = threadIdx.x; i < n; i += NT) dx[i] = 0.0;
+    K3R_LOOP for (int i = threadIdx.x; i < n; i += NT) dx[i] = 0.0;
     __syncthreads();
-    for (int k = threadIdx.x; k < nX; k += NT) dx[C.xvar[k]] = dbX[k] / C.xcv[k];
+    K3R_LOOP for (int k = threadIdx.x; k < nX; k += NT) dx[C.xvar[k]] = dbX[k] / C.xcv[k];
     __syncthreads();
     if (nAC > 0) {
         s_prep(C, dx);
-        for (int r = nZ + threadIdx.x; r < nF; r += NT) {
+        K3R_LOOP for (int r = nZ + threadIdx.x; r < nF; r += NT) {
             const RowW rd = row_load(C, C.widx[r]);
             C.tF[r] = dbw[r] - s_rowdot(C, rd, dx);
         }
         __syncthreads();
         usolve(C, nZ, nF, C.tF, C.pF);
         Qmul(C, C.pF, nZ, nF, C.uF);
-        for (int i = threadIdx.x; i < nF; i += NT) dx[C.flist[i]] = C.uF[i];
+        K3R_LOOP for (int i = threadIdx.x; i < nF; i += NT) dx[C.flist[i]] = C.uF[i];
         __syncthreads();
     }
     PH(7);
     Hmul(C, dx, u);
-    for (int i = threadIdx.x; i < n; i += NT) u[i] += dg[i];
+    K3R_LOOP for (int i = threadIdx.x; i < n; i += NT) u[i] += dg[i];
     __syncthreads();
     PH(8);
     if (nZ > 0) {
         gatherF(C, u);
         Qtmul(C, C.gF, C.tF, 0, nZ);
-        for (int j = threadIdx.x; j < nZ; j += NT) C.tF[j] = -C.tF[j];
+        K3R_LOOP for (int j = threadIdx.x; j < nZ; j += NT) C.tF[j] = -C.tF[j];
         __syncthreads();
         tsolve(C, 0, nZ, C.tF, C.pF);
         usolve(C, 0, nZ, C.pF, C.tF);
         Qmul(C, C.tF, 0, nZ, C.uF);              // p = Z q (compact)
-        for (int i = threadIdx.x; i < n; i += NT) C.t1[i] = 0.0;
+        K3R_LOOP for (int i = threadIdx.x; i < n; i += NT) C.t1[i] = 0.0;
         __syncthreads();
-        for (int i = threadIdx.x; i < nF; i += NT) { const int j = C.flist[i]; C.t1[j] = C.uF[i]; dx[j] += C.uF[i]; }
+        K3R_LOOP for (int i = threadIdx.x; i < nF; i += NT) { const int j = C.flist[i]; C.t1[j] = C.uF[i]; dx[j] += C.uF[i]; }
         __syncthreads();
         PH(9);
         Hmul(C, C.t1, C.t3);
-        for (int i = threadIdx.x; i < n; i += NT) u[i] += C.t3[i];
+        K3R_LOOP for (int i = threadIdx.x; i < n; i += NT) u[i] += C.t3[i];
         __syncthreads();
         PH(10);
     }
@@ -808,7 +816,7 @@ template <class CT> K3R_FN __device__ void kkt_step(CT& C, const double* dg, con
     PH(11);
     if (nX > 0) {
         ATmul(C, dyW, nullptr, C.t3);
-        for (int k = threadIdx.x; k < nX; k += NT) { const int j = C.xvar[k]; dyX[k] = (u[j] - C.t3[j]) / C.xcv[k]; }
+        K3R_LOOP for (int k = threadIdx.x; k < nX; k += NT) { const int j = C.xvar[k]; dyX[k] = (u[j] - C.t3[j]) / C.xcv[k]; }
         __syncthreads();
     }
     PH(12);
@@ -820,7 +828,7 @@ template <class CT> K3R_FN __device__ void reanchor(CT& C, bool recompute_y)
     const int n = C.n, nF = C.nF, nZ = C.nZ, nX = C.nX;
     Hmul(C, C.x, C.t1);
     if (recompute_y && (nX + nF - nZ) > 0) {
-        for (int i = threadIdx.x; i < n; i += NT) C.t2[i] = C.t1[i] + C.gcur[i];
+        K3R_LOOP for (int i = threadIdx.x; i < n; i += NT) C.t2[i] = C.t1[i] + C.gcur[i];
         __syncthreads();
         if (nF > nZ) {
             gatherF(C, C.t2);
@@ -829,18 +837,18 @@ template <class CT> K3R_FN __device__ void reanchor(CT& C, bool recompute_y)
         }
         if (nX > 0) {
             ATmul(C, C.yW, nullptr, C.t3);
-            for (int k = threadIdx.x; k < nX; k += NT) { const int j = C.xvar[k]; C.yX[k] = (C.t2[j] - C.t3[j]) / C.xcv[k]; }
+            K3R_LOOP for (int k = threadIdx.x; k < nX; k += NT) { const int j = C.xvar[k]; C.yX[k] = (C.t2[j] - C.t3[j]) / C.xcv[k]; }
             __syncthreads();
         }
     }
-    for (int r = nZ + threadIdx.x; r < nF; r += NT) {
+    K3R_LOOP for (int r = nZ + threadIdx.x; r < nF; r += NT) {
         int c = C.widx[r];
         if (lb_new(C, c) != ub_new(C, c)) {
             if (C.st[c] < 0 && C.yW[r] < 0) C.yW[r] = 0;
             if (C.st[c] > 0 && C.yW[r] > 0) C.yW[r] = 0;
         }
     }
-    for (int k = threadIdx.x; k < nX; k += NT) {
+    K3R_LOOP for (int k = threadIdx.x; k < nX; k += NT) {
         int c = C.xcon[k];
         if (lb_new(C, c) != ub_new(C, c)) {
             if (C.st[c] < 0 && C.yX[k] < 0) C.yX[k] = 0;
@@ -849,7 +857,7 @@ template <class CT> K3R_FN __device__ void reanchor(CT& C, bool recompute_y)
     }
     __syncthreads();
     ATmul(C, C.yW, C.yX, C.t3);
-    for (int j = threadIdx.x; j < n; j += NT) C.gcur[j] = C.t3[j] - C.t1[j];
+    K3R_LOOP for (int j = threadIdx.x; j < n; j += NT) C.gcur[j] = C.t3[j] - C.t1[j];
     __syncthreads();
 }
 
@@ -858,7 +866,7 @@ template <class CT> K3R_FN __device__ double get_rowF(CT& C, int c, double* aF)
 {
     const RowW rd = row_load(C, c);
     double s2 = 0;
-    for (int j = threadIdx.x; j < C.n; j += NT) {
+    K3R_LOOP for (int j = threadIdx.x; j < C.n; j += NT) {
         const double v = s_entry(C, rd, j);
         s2 += v * v;
         const int f = C.fpos[j];
@@ -879,53 +887,53 @@ template <class CT> K3R_FN __device__ int resolve_pending(CT& C, int c_out, int 
         if (kpd < 0) break;
         const int nF = C.nF;
         double *zf = C.t4, *hz = C.t1, *d = C.dx;
-        for (int i = threadIdx.x; i < n; i += NT) zf[i] = 0.0;
+        K3R_LOOP for (int i = threadIdx.x; i < n; i += NT) zf[i] = 0.0;
         __syncthreads();
-        for (int i = threadIdx.x; i < nF; i += NT) zf[C.flist[i]] = QF(i, kpd);
+        K3R_LOOP for (int i = threadIdx.x; i < nF; i += NT) zf[C.flist[i]] = QF(i, kpd);
         __syncthreads();
         Hmul(C, zf, hz);
         double zhz = 0;
-        for (int i = threadIdx.x; i < n; i += NT) zhz += zf[i] * hz[i];
+        K3R_LOOP for (int i = threadIdx.x; i < n; i += NT) zhz += zf[i] * hz[i];
         zhz = block_sum(C, zhz);
         gatherF(C, hz);
         Qtmul(C, C.gF, C.tF, 0, kpd);
         tsolve(C, 0, kpd, C.tF, C.pF);           // r = R'^-1 Z'Hz
         double rr = 0;
-        for (int j = threadIdx.x; j < kpd; j += NT) rr += C.pF[j] * C.pF[j];
+        K3R_LOOP for (int j = threadIdx.x; j < kpd; j += NT) rr += C.pF[j] * C.pF[j];
         rr = block_sum(C, rr);
         double rho2 = zhz - rr;
         if (rho2 > EPS_PD * C.hscale) {
-            for (int j = threadIdx.x; j < kpd; j += NT) MM(j, kpd) = C.pF[j];
+            K3R_LOOP for (int j = threadIdx.x; j < kpd; j += NT) MM(j, kpd) = C.pF[j];
             if (threadIdx.x == 0) MM(kpd, kpd) = sqrt(rho2);
             __syncthreads();
             break;
         }
-        for (int j = threadIdx.x; j < kpd; j += NT) C.tF[j] = C.pF[j];
+        K3R_LOOP for (int j = threadIdx.x; j < kpd; j += NT) C.tF[j] = C.pF[j];
         __syncthreads();
         usolve(C, 0, kpd, C.tF, C.uF);           // q
         Qmul(C, C.uF, 0, kpd, C.pF);             // Z q (compact)
-        for (int i = threadIdx.x; i < n; i += NT) d[i] = 0.0;
+        K3R_LOOP for (int i = threadIdx.x; i < n; i += NT) d[i] = 0.0;
         __syncthreads();
-        for (int i = threadIdx.x; i < nF; i += NT) { const int j = C.flist[i]; d[j] = zf[j] - C.pF[i]; }
+        K3R_LOOP for (int i = threadIdx.x; i < nF; i += NT) { const int j = C.flist[i]; d[j] = zf[j] - C.pF[i]; }
         __syncthreads();
         double sgn = 0;
         if (first) {
             get_row(C, c_out, C.t2);
-            for (int i = threadIdx.x; i < n; i += NT) sgn += C.t2[i] * d[i];
+            K3R_LOOP for (int i = threadIdx.x; i < n; i += NT) sgn += C.t2[i] * d[i];
             sgn = block_sum(C, sgn);
             if (side_out > 0) sgn = -sgn;
         } else {
             Hmul(C, C.x, hz);
-            for (int i = threadIdx.x; i < n; i += NT) sgn -= (hz[i] + C.gcur[i]) * d[i];
+            K3R_LOOP for (int i = threadIdx.x; i < n; i += NT) sgn -= (hz[i] + C.gcur[i]) * d[i];
             sgn = block_sum(C, sgn);
         }
         if (sgn < 0) { __syncthreads(); for (int i = threadIdx.x; i < n; i += NT) d[i] = -d[i]; __syncthreads(); }
         Amul(C, d, C.Adx);
         double dn = 0;
-        for (int i = threadIdx.x; i < n; i += NT) dn += d[i] * d[i];
+        K3R_LOOP for (int i = threadIdx.x; i < n; i += NT) dn += d[i] * d[i];
         dn = sqrt(block_sum(C, dn));
         double tmin = INFINITY; int key = 0x7fffffff;
-        for (int cc = threadIdx.x; cc < mt; cc += NT) {
+        K3R_LOOP for (int cc = threadIdx.x; cc < mt; cc += NT) {
             if (C.st[cc] != 0 || C.anorm[cc] == 0.0f) continue;
             double adx = C.Adx[cc];
             const double rz = EPS_ROW * C.anorm[cc] * dn;
@@ -944,8 +952,8 @@ template <class CT> K3R_FN __device__ int resolve_pending(CT& C, int c_out, int 
         block_argmin(C, tmin, key);
         if (key == 0x7fffffff) return EEPACC_QP_UNBOUNDED;
         const int j = key >> 1, jside = (key & 1) ? 1 : -1;
-        for (int i = threadIdx.x; i < n; i += NT) C.x[i] += tmin * d[i];
-        for (int cc = threadIdx.x; cc < mt; cc += NT) C.Ax[cc] += tmin * C.Adx[cc];
+        K3R_LOOP for (int i = threadIdx.x; i < n; i += NT) C.x[i] += tmin * d[i];
+        K3R_LOOP for (int cc = threadIdx.x; cc < mt; cc += NT) C.Ax[cc] += tmin * C.Adx[cc];
         __syncthreads();
         if (threadIdx.x == 0) { if (jside < 0) C.lbc[j] = C.Ax[j]; else C.ubc[j] = C.Ax[j]; }
         const double an2 = get_rowF(C, j, C.gF);
@@ -967,7 +975,7 @@ template <class CT> K3R_FN __device__ int resolve_pending(CT& C, int c_out, int 
 template <class CT> K3R_FN __device__ int warm_setup(CT& C, int old_nA, const short* gidx, const signed char* gside, const double* gy)
 {
     const int n = C.n, mt = C.mt, m = C.m;
-    for (int c = threadIdx.x; c < mt; c += NT) C.st[c] = 0;
+    K3R_LOOP for (int c = threadIdx.x; c < mt; c += NT) C.st[c] = 0;
     short* cand = reinterpret_cast<short*>(C.t1);        // [n] constraint index of general candidates
     short* tmpc = reinterpret_cast<short*>(C.t3);        // classification scratch: [3n] shorts
     double* tmpv = C.t2;                                 // [n] unit coefficient
@@ -979,7 +987,7 @@ template <class CT> K3R_FN __device__ int warm_setup(CT& C, int old_nA, const sh
     double* cn2 = C.dbw;                                 // squared norm of the original row
     __syncthreads();
     // 1. classify the stored working set in parallel (position k was stored at index n-1-k)
-    for (int k = threadIdx.x; k < old_nA; k += NT) {
+    K3R_LOOP for (int k = threadIdx.x; k < old_nA; k += NT) {
         const int r = n - 1 - k;
         const int c = gidx[r], sd = gside[r];
         const double bnd = sd < 0 ? lb_new(C, c) : ub_new(C, c);
@@ -992,7 +1000,7 @@ template <class CT> K3R_FN __device__ int warm_setup(CT& C, int old_nA, const sh
         tmpv[k] = cv;
         tmpy[k] = gy[r];                                  // coalesced: thread 0 below never touches global memory
     }
-    for (int j = threadIdx.x; j < n; j += NT) C.fpos[j] = 0;
+    K3R_LOOP for (int j = threadIdx.x; j < n; j += NT) C.fpos[j] = 0;
     __syncthreads();
     // thread 0: X list, general candidates, free list
     if (threadIdx.x == 0) {
@@ -1024,7 +1032,7 @@ template <class CT> K3R_FN __device__ int warm_setup(CT& C, int old_nA, const sh
     if (nF > C.fc) return 1;
     if (cnt > nF) {                                       // more general rows than free variables: the tail is dependent
         __syncthreads();
-        for (int k = nF + threadIdx.x; k < cnt; k += NT) C.st[cand[k]] = 0;
+        K3R_LOOP for (int k = nF + threadIdx.x; k < cnt; k += NT) C.st[cand[k]] = 0;
         cnt = nF;
         __syncthreads();
     }
@@ -1055,7 +1063,7 @@ template <class CT> K3R_FN __device__ int warm_setup(CT& C, int old_nA, const sh
     while (k < cnt) {
         if (!have_s2) {
             double a2 = 0;
-            for (int i = k + threadIdx.x; i < nF; i += NT) a2 += QF(i, k) * QF(i, k);
+            K3R_LOOP for (int i = k + threadIdx.x; i < nF; i += NT) a2 += QF(i, k) * QF(i, k);
             s2 = block_sum(C, a2);
         }
         have_s2 = false;
@@ -1066,7 +1074,7 @@ template <class CT> K3R_FN __device__ int warm_setup(CT& C, int old_nA, const sh
             if (threadIdx.x == 0) C.st[cand[k]] = 0;
             __syncthreads();
             if (k != last) {
-                for (int i = threadIdx.x; i < nF; i += NT) QF(i, k) = QF(i, last);
+                K3R_LOOP for (int i = threadIdx.x; i < nF; i += NT) QF(i, k) = QF(i, last);
                 if (threadIdx.x == 0) { cand[k] = cand[last]; ycand[k] = ycand[last]; cn2[k] = cn2[last]; }
             }
             cnt = last;
@@ -1111,7 +1119,7 @@ template <class CT> K3R_FN __device__ int warm_setup(CT& C, int old_nA, const sh
     PH(3);
     const int nAC = cnt, nZ = nF - nAC;
     // 4. T block of M from Rh:  M(r, c) = Rh(nF-1-c, nF-1-r),  c >= r >= nZ
-    for (int r = nZ + threadIdx.x; r < nF; r += NT) {
+    K3R_LOOP for (int r = nZ + threadIdx.x; r < nF; r += NT) {
         const int b = nF - 1 - r;
         for (int c = r; c < nF; ++c) {
             const int a = nF - 1 - c;
@@ -1120,7 +1128,7 @@ template <class CT> K3R_FN __device__ int warm_setup(CT& C, int old_nA, const sh
     }
     __syncthreads();
     // 5. form Qh: backward accumulation of the reflectors
-    for (int j = nAC + threadIdx.x; j < nF; j += NT)
+    K3R_LOOP for (int j = nAC + threadIdx.x; j < nF; j += NT)
         for (int i = 0; i < nF; ++i) QF(i, j) = (i == j) ? 1.0 : 0.0;
     __syncthreads();
     // Reflector kk is applied to the columns right of it by LPC lanes per column.  Column kk+1 still holds
@@ -1156,19 +1164,19 @@ template <class CT> K3R_FN __device__ int warm_setup(CT& C, int old_nA, const sh
     }
     if (nAC > 0) {
         const double v0 = v0a[0], bt = beta[0];
-        for (int i = threadIdx.x; i < nF; i += NT) {
+        K3R_LOOP for (int i = threadIdx.x; i < nF; i += NT) {
             const double vi = QF(i, 0);
             QF(i, 0) = (i == 0) ? 1.0 - bt * v0 * v0 : -bt * v0 * vi;
         }
         __syncthreads();
     }
     // 6. reverse the columns, 7. working-set bookkeeping by Qf column
-    for (int e = threadIdx.x; e < nF * (nF / 2); e += NT) {
+    K3R_LOOP for (int e = threadIdx.x; e < nF * (nF / 2); e += NT) {
         const int c = e / nF, i = e - c * nF;
         const double a = QF(i, c), b2 = QF(i, nF - 1 - c);
         QF(i, c) = b2; QF(i, nF - 1 - c) = a;
     }
-    for (int kq = threadIdx.x; kq < nAC; kq += NT) { C.yW[nF - 1 - kq] = ycand[kq]; C.widx[nF - 1 - kq] = cand[kq]; }
+    K3R_LOOP for (int kq = threadIdx.x; kq < nAC; kq += NT) { C.yW[nF - 1 - kq] = ycand[kq]; C.widx[nF - 1 - kq] = cand[kq]; }
     C.nZ = nZ;
     __syncthreads();
     PH(4);
@@ -1180,9 +1188,9 @@ template <class CT> K3R_FN __device__ void cold_ws(CT& C)
 {
     const int n = C.n, m = C.m, mt = C.mt;
     __syncthreads();
-    for (int c = threadIdx.x; c < mt; c += NT) C.st[c] = 0;
+    K3R_LOOP for (int c = threadIdx.x; c < mt; c += NT) C.st[c] = 0;
     __syncthreads();
-    for (int k = threadIdx.x; k < n; k += NT) {
+    K3R_LOOP for (int k = threadIdx.x; k < n; k += NT) {
         const int v = n - 1 - k;
         C.xvar[k] = (short)v; C.xcon[k] = (short)(m + v); C.xcv[k] = 1.0;
         C.fpos[v] = (short)(-1 - k);
@@ -1198,7 +1206,7 @@ template <class CT> K3R_FN __device__ void setup_aux(CT& C)
 {
     const int mt = C.mt;
     Amul(C, C.x, C.Ax);
-    for (int c = threadIdx.x; c < mt; c += NT) {
+    K3R_LOOP for (int c = threadIdx.x; c < mt; c += NT) {
         int s = C.st[c];
         double ax = C.Ax[c], ln = lb_new(C, c), un = ub_new(C, c);
         bool eq = ln == un;
@@ -1320,7 +1328,7 @@ __device__ __forceinline__ void k3r_setup(k3r::CtxT<NU, NB>& C, const eep_qp_io&
 template <class CT> __device__ __forceinline__ void k3r_tables(CT& C, const eep_qp_io& io)
 {
     double* cst = const_cast<double*>(C.cvals);
-    for (int e = threadIdx.x; e < 96; e += NT) cst[e] = io.rowc[e];
+    K3R_LOOP for (int e = threadIdx.x; e < 96; e += NT) cst[e] = io.rowc[e];
     if (threadIdx.x == 0) C.vest[EEP_N] = 0.0;
 }
 // One vehicle's QP.  Returns the status written to io.status, or K3R_DEFER (nothing written, warm state
@@ -1344,21 +1352,21 @@ K3R_FN __device__ int k3r_vehicle(CT& C, const eep_qp_io& io, const long long ve
         const double* gg = io.g + veh * (size_t)n;
         const double* la = io.lba + veh * (size_t)m;
         const double* ua = io.uba + veh * (size_t)m;
-        for (int i = threadIdx.x; i < n; i += NT) C.gw[i] = gg[i];
+        K3R_LOOP for (int i = threadIdx.x; i < n; i += NT) C.gw[i] = gg[i];
         C.lba = la; C.uba = ua;
         {
             double* hs = io.hscr + veh * (size_t)(4 * mt);
             C.Ax = hs; C.lbc = hs + mt; C.ubc = hs + 2 * mt; C.Adx = hs + 3 * mt;
         }
         const double* sb = io.sblk + veh * (size_t)EEP_SBLK;
-        for (int e = threadIdx.x; e < (EEP_N + 1) * EEP_N; e += NT) { C.PS[e] = sb[EEP_SB_PS + e]; C.PV[e] = sb[EEP_SB_PV + e]; }
-        for (int e = threadIdx.x; e < EEP_N * 9; e += NT) { C.Dc[e] = sb[EEP_SB_DC + e]; C.Cc[e] = sb[EEP_SB_CC + e]; }
-        for (int e = threadIdx.x; e < EEP_N * 4; e += NT) C.Dg[e] = sb[EEP_SB_DG + e];
-        for (int e = threadIdx.x; e < EEP_N; e += NT) C.vest[e] = sb[EEP_SB_VEST + e];
+        K3R_LOOP for (int e = threadIdx.x; e < (EEP_N + 1) * EEP_N; e += NT) { C.PS[e] = sb[EEP_SB_PS + e]; C.PV[e] = sb[EEP_SB_PV + e]; }
+        K3R_LOOP for (int e = threadIdx.x; e < EEP_N * 9; e += NT) { C.Dc[e] = sb[EEP_SB_DC + e]; C.Cc[e] = sb[EEP_SB_CC + e]; }
+        K3R_LOOP for (int e = threadIdx.x; e < EEP_N * 4; e += NT) C.Dg[e] = sb[EEP_SB_DG + e];
+        K3R_LOOP for (int e = threadIdx.x; e < EEP_N; e += NT) C.vest[e] = sb[EEP_SB_VEST + e];
         C.reg = (sb[EEP_SB_HMAX] == 0.0) ? LP_REG : 0.0;
         C.hscale = fmax(sb[EEP_SB_HSCALE], LP_REG);
         __syncthreads();
-        for (int r = threadIdx.x; r < m; r += NT) {
+        K3R_LOOP for (int r = threadIdx.x; r < m; r += NT) {
             const RowW rd = row_load(C, r);
             double sa = 0;
             if (rd.kst >= 0) {
@@ -1373,15 +1381,15 @@ K3R_FN __device__ int k3r_vehicle(CT& C, const eep_qp_io& io, const long long ve
             C.anorm[r] = (float)sa;
         }
     }
-    for (int j = threadIdx.x; j < n; j += NT) C.anorm[m + j] = 1.0f;
-    for (int c = threadIdx.x; c < mt; c += NT) C.tabu[c] = 0;
+    K3R_LOOP for (int j = threadIdx.x; j < n; j += NT) C.anorm[m + j] = 1.0f;
+    K3R_LOOP for (int c = threadIdx.x; c < mt; c += NT) C.tabu[c] = 0;
     __syncthreads();
     PH(0);
 
     // ---------------- set-up ----------------
     const int was_warm = io.warm[veh];
     bool need_cold = !was_warm;
-    for (int i = threadIdx.x; i < n; i += NT) C.x[i] = was_warm ? io.wx[veh * (size_t)n + i] : 0.0;
+    K3R_LOOP for (int i = threadIdx.x; i < n; i += NT) C.x[i] = was_warm ? io.wx[veh * (size_t)n + i] : 0.0;
     if (!need_cold) {
         if (warm_setup(C, io.wnA[veh], io.widx + veh * (size_t)n, io.wside + veh * (size_t)n, io.wy + veh * (size_t)n))
             status = K3R_DEFER;
@@ -1400,14 +1408,14 @@ K3R_FN __device__ int k3r_vehicle(CT& C, const eep_qp_io& io, const long long ve
     // ---------------- homotopy ----------------
     while (status == EEPACC_QP_OK) {
         const int nZ = C.nZ, nF = C.nF, nX = C.nX;
-        for (int i = threadIdx.x; i < n; i += NT) C.dg[i] = C.g[i] - C.gcur[i];
-        for (int r = nZ + threadIdx.x; r < nF; r += NT) {
+        K3R_LOOP for (int i = threadIdx.x; i < n; i += NT) C.dg[i] = C.g[i] - C.gcur[i];
+        K3R_LOOP for (int r = nZ + threadIdx.x; r < nF; r += NT) {
             int c = C.widx[r];
             double nb = C.st[c] < 0 ? lb_new(C, c) : ub_new(C, c);
             double cb = C.st[c] < 0 ? C.lbc[c] : C.ubc[c];
             C.dbw[r] = isinf(nb) ? 0.0 : nb - cb;
         }
-        for (int k = threadIdx.x; k < nX; k += NT) {
+        K3R_LOOP for (int k = threadIdx.x; k < nX; k += NT) {
             int c = C.xcon[k];
             double nb = C.st[c] < 0 ? lb_new(C, c) : ub_new(C, c);
             double cb = C.st[c] < 0 ? C.lbc[c] : C.ubc[c];
@@ -1420,10 +1428,10 @@ K3R_FN __device__ int k3r_vehicle(CT& C, const eep_qp_io& io, const long long ve
         PH(13);
 
         double dxmax = 0;
-        for (int i = threadIdx.x; i < n; i += NT) dxmax = fmax(dxmax, fabs(C.dx[i]));
+        K3R_LOOP for (int i = threadIdx.x; i < n; i += NT) dxmax = fmax(dxmax, fabs(C.dx[i]));
         dxmax = block_max(C, dxmax);
         double tau = 1.0; int key = 0x7fffffff;
-        for (int c = threadIdx.x; c < mt; c += NT) {
+        K3R_LOOP for (int c = threadIdx.x; c < mt; c += NT) {
             if (C.st[c] != 0 || C.anorm[c] == 0.0f) continue;      // all-zero rows can never be added
             if (C.tabu[c] == 2) continue;                          // left during this run of zero steps: no re-entry
             double adx = C.Adx[c];
@@ -1454,13 +1462,13 @@ K3R_FN __device__ int k3r_vehicle(CT& C, const eep_qp_io& io, const long long ve
             }
         }
         double dys = 0;
-        for (int r = nZ + threadIdx.x; r < nF; r += NT) dys = fmax(dys, fabs(C.dyW[r]));
-        for (int k = threadIdx.x; k < nX; k += NT) dys = fmax(dys, fabs(C.dyX[k]));
+        K3R_LOOP for (int r = nZ + threadIdx.x; r < nF; r += NT) dys = fmax(dys, fabs(C.dyW[r]));
+        K3R_LOOP for (int k = threadIdx.x; k < nX; k += NT) dys = fmax(dys, fabs(C.dyX[k]));
         dys = block_max(C, dys);
         const double thr = EPS_RATE * (1.0 + dys);
         // dual ratio test; key = 2*mt + position (X entries are positions 0..nX-1, the general
         // row of Qf column r is position nX + nF-1-r)
-        for (int q = threadIdx.x; q < nX + (nF - nZ); q += NT) {
+        K3R_LOOP for (int q = threadIdx.x; q < nX + (nF - nZ); q += NT) {
             int c; double yc, dy;
             if (q < nX) { c = C.xcon[q]; yc = C.yX[q]; dy = C.dyX[q]; }
             else { const int r = nF - 1 - (q - nX); c = C.widx[r]; yc = C.yW[r]; dy = C.dyW[r]; }
@@ -1484,13 +1492,13 @@ K3R_FN __device__ int k3r_vehicle(CT& C, const eep_qp_io& io, const long long ve
         if (!zero_step) for (int c = threadIdx.x; c < mt; c += NT) C.tabu[c] = 0;
 
         // take the step
-        for (int i = threadIdx.x; i < n; i += NT) {
+        K3R_LOOP for (int i = threadIdx.x; i < n; i += NT) {
             C.x[i] += tau * C.dx[i];
             C.gcur[i] = full ? C.g[i] : C.gcur[i] + tau * C.dg[i];
         }
-        for (int r = nZ + threadIdx.x; r < nF; r += NT) C.yW[r] += tau * C.dyW[r];
-        for (int k = threadIdx.x; k < nX; k += NT) C.yX[k] += tau * C.dyX[k];
-        for (int c = threadIdx.x; c < mt; c += NT) {
+        K3R_LOOP for (int r = nZ + threadIdx.x; r < nF; r += NT) C.yW[r] += tau * C.dyW[r];
+        K3R_LOOP for (int k = threadIdx.x; k < nX; k += NT) C.yX[k] += tau * C.dyX[k];
+        K3R_LOOP for (int c = threadIdx.x; c < mt; c += NT) {
             C.Ax[c] += tau * C.Adx[c];
             double ln = lb_new(C, c), un = ub_new(C, c);
             if (!isinf(ln)) C.lbc[c] = full ? ln : C.lbc[c] + tau * (ln - C.lbc[c]);
@@ -1505,7 +1513,7 @@ K3R_FN __device__ int k3r_vehicle(CT& C, const eep_qp_io& io, const long long ve
             // all-fixed working set at the current point -- the cold-start path
             cold_ws(C);
             setup_aux(C);
-            for (int c = threadIdx.x; c < mt; c += NT) C.tabu[c] = 0;
+            K3R_LOOP for (int c = threadIdx.x; c < mt; c += NT) C.tabu[c] = 0;
             __syncthreads();
             continue;
         }
@@ -1523,7 +1531,7 @@ K3R_FN __device__ int k3r_vehicle(CT& C, const eep_qp_io& io, const long long ve
             }
             get_row(C, blk, C.t4);                      // full row (the exchange needs its fixed part)
             double an2 = 0;
-            for (int j = threadIdx.x; j < n; j += NT) an2 += C.t4[j] * C.t4[j];
+            K3R_LOOP for (int j = threadIdx.x; j < n; j += NT) an2 += C.t4[j] * C.t4[j];
             an2 = block_sum(C, an2);
             gatherF(C, C.t4);
             const int nZc = C.nZ;
@@ -1535,18 +1543,18 @@ K3R_FN __device__ int k3r_vehicle(CT& C, const eep_qp_io& io, const long long ve
                 const int nFc = C.nF, nXc = C.nX;
                 double* lamG = C.dyW;                   // by Qf column (dyW / dyX are recomputed by the next KKT step)
                 double* lamX = C.dyX;
-                for (int r = nZc + threadIdx.x; r < nFc; r += NT) C.tF[r] = C.wv[r];
+                K3R_LOOP for (int r = nZc + threadIdx.x; r < nFc; r += NT) C.tF[r] = C.wv[r];
                 __syncthreads();
                 tsolve(C, nZc, nFc, C.tF, lamG);
                 ATmul(C, lamG, nullptr, C.t3);
-                for (int k = threadIdx.x; k < nXc; k += NT) { const int j = C.xvar[k]; lamX[k] = (C.t4[j] - C.t3[j]) / C.xcv[k]; }
+                K3R_LOOP for (int k = threadIdx.x; k < nXc; k += NT) { const int j = C.xvar[k]; lamX[k] = (C.t4[j] - C.t3[j]) / C.xcv[k]; }
                 __syncthreads();
                 double lmax = 0;
-                for (int r = nZc + threadIdx.x; r < nFc; r += NT) lmax = fmax(lmax, fabs(lamG[r]));
-                for (int k = threadIdx.x; k < nXc; k += NT) lmax = fmax(lmax, fabs(lamX[k]));
+                K3R_LOOP for (int r = nZc + threadIdx.x; r < nFc; r += NT) lmax = fmax(lmax, fabs(lamG[r]));
+                K3R_LOOP for (int k = threadIdx.x; k < nXc; k += NT) lmax = fmax(lmax, fabs(lamX[k]));
                 lmax = block_max(C, lmax);
                 double theta = INFINITY; int kk = 0x7fffffff;
-                for (int q = threadIdx.x; q < nXc + (nFc - nZc); q += NT) {
+                K3R_LOOP for (int q = threadIdx.x; q < nXc + (nFc - nZc); q += NT) {
                     int c; double yc, lr;
                     if (q < nXc) { c = C.xcon[q]; yc = C.yX[q]; lr = lamX[q]; }
                     else { const int r = nFc - 1 - (q - nXc); c = C.widx[r]; yc = C.yW[r]; lr = lamG[r]; }
@@ -1563,8 +1571,8 @@ K3R_FN __device__ int k3r_vehicle(CT& C, const eep_qp_io& io, const long long ve
                 }
                 block_argmin(C, theta, kk);
                 if (kk == 0x7fffffff) { status = EEPACC_QP_INFEASIBLE; break; }
-                for (int r = nZc + threadIdx.x; r < nFc; r += NT) C.yW[r] -= theta * ((side < 0) ? lamG[r] : -lamG[r]);
-                for (int k = threadIdx.x; k < nXc; k += NT) C.yX[k] -= theta * ((side < 0) ? lamX[k] : -lamX[k]);
+                K3R_LOOP for (int r = nZc + threadIdx.x; r < nFc; r += NT) C.yW[r] -= theta * ((side < 0) ? lamG[r] : -lamG[r]);
+                K3R_LOOP for (int k = threadIdx.x; k < nXc; k += NT) C.yX[k] -= theta * ((side < 0) ? lamX[k] : -lamX[k]);
                 __syncthreads();
                 if (kk < nXc) {
                     if (threadIdx.x == 0 && zero_step) C.tabu[C.xcon[kk]] = 2;
@@ -1580,7 +1588,7 @@ K3R_FN __device__ int k3r_vehicle(CT& C, const eep_qp_io& io, const long long ve
                 const int rn = C.nZ - 1;                 // freed column
                 gatherF(C, C.t4);
                 Qtmul(C, C.gF, C.tF, rn, C.nF);
-                for (int c = rn + threadIdx.x; c < C.nF; c += NT) MM(rn, c) = C.tF[c];
+                K3R_LOOP for (int c = rn + threadIdx.x; c < C.nF; c += NT) MM(rn, c) = C.tF[c];
                 if (threadIdx.x == 0) {
                     C.widx[rn] = (short)blk; C.st[blk] = (signed char)side;
                     C.yW[rn] = (side < 0) ? theta : -theta;
@@ -1622,21 +1630,21 @@ K3R_FN __device__ int k3r_vehicle(CT& C, const eep_qp_io& io, const long long ve
         Hmul(C, C.x, C.t4);
         ATmul(C, C.yW, C.yX, C.t3);
         // rg = Hx + g - A_W' y ; rb = bound - a'x
-        for (int j = threadIdx.x; j < n; j += NT) C.dg[j] = C.t4[j] + C.g[j] - C.t3[j];
-        for (int r = nZ + threadIdx.x; r < nF; r += NT) {
+        K3R_LOOP for (int j = threadIdx.x; j < n; j += NT) C.dg[j] = C.t4[j] + C.g[j] - C.t3[j];
+        K3R_LOOP for (int r = nZ + threadIdx.x; r < nF; r += NT) {
             const int c = C.widx[r];
             C.dbw[r] = (C.st[c] < 0 ? C.lbc[c] : C.ubc[c]) - C.Adx[c];
         }
-        for (int k = threadIdx.x; k < nX; k += NT) {
+        K3R_LOOP for (int k = threadIdx.x; k < nX; k += NT) {
             const int c = C.xcon[k];
             C.dbX[k] = (C.st[c] < 0 ? C.lbc[c] : C.ubc[c]) - C.Adx[c];
         }
         __syncthreads();
         PH(17);
         kkt_step(C, C.dg, C.dbw, C.dbX, C.dx, C.dyW, C.dyX);
-        for (int i = threadIdx.x; i < n; i += NT) C.x[i] += C.dx[i];
-        for (int r = nZ + threadIdx.x; r < nF; r += NT) C.yW[r] += C.dyW[r];
-        for (int k = threadIdx.x; k < nX; k += NT) C.yX[k] += C.dyX[k];
+        K3R_LOOP for (int i = threadIdx.x; i < n; i += NT) C.x[i] += C.dx[i];
+        K3R_LOOP for (int r = nZ + threadIdx.x; r < nF; r += NT) C.yW[r] += C.dyW[r];
+        K3R_LOOP for (int k = threadIdx.x; k < nX; k += NT) C.yX[k] += C.dyX[k];
         __syncthreads();
     }
     PH(17);
@@ -1645,21 +1653,21 @@ K3R_FN __device__ int k3r_vehicle(CT& C, const eep_qp_io& io, const long long ve
     {
         Hmul(C, C.x, C.t1);
         double s = 0;
-        for (int i = threadIdx.x; i < n; i += NT) s += C.x[i] * (0.5 * (C.t1[i] - C.reg * C.x[i]) + C.g[i]);
+        K3R_LOOP for (int i = threadIdx.x; i < n; i += NT) s += C.x[i] * (0.5 * (C.t1[i] - C.reg * C.x[i]) + C.g[i]);
         s = block_sum(C, s);
         const int nZ = C.nZ, nF = C.nF, nX = C.nX, nA = nX + nF - nZ;
         if (status == EEPACC_QP_OK) {
             int far = 0;
-            for (int r = nZ + threadIdx.x; r < nF; r += NT) { int c = C.widx[r]; if (c >= m && fabs(C.x[c - m]) >= FARB) far = 1; }
-            for (int k = threadIdx.x; k < nX; k += NT) { int c = C.xcon[k]; if (c >= m && fabs(C.x[c - m]) >= FARB) far = 1; }
+            K3R_LOOP for (int r = nZ + threadIdx.x; r < nF; r += NT) { int c = C.widx[r]; if (c >= m && fabs(C.x[c - m]) >= FARB) far = 1; }
+            K3R_LOOP for (int k = threadIdx.x; k < nX; k += NT) { int c = C.xcon[k]; if (c >= m && fabs(C.x[c - m]) >= FARB) far = 1; }
             if (block_max(C, (double)far) > 0) status = EEPACC_QP_UNBOUNDED;
             int zr = 0;         // an all-zero row with inconsistent bounds: infeasible QP
-            for (int c = threadIdx.x; c < m; c += NT)
+            K3R_LOOP for (int c = threadIdx.x; c < m; c += NT)
                 if (C.anorm[c] == 0.0 && (lb_new(C, c) > 1e-8 || ub_new(C, c) < -1e-8)) zr = 1;
             if (block_max(C, (double)zr) > 0) status = EEPACC_QP_INFEASIBLE;
         }
         // warm-start state in the layout of k3_qp.cu: position q lives at index n-1-q
-        for (int i = threadIdx.x; i < n; i += NT) {
+        K3R_LOOP for (int i = threadIdx.x; i < n; i += NT) {
             io.x[veh * (size_t)n + i] = C.x[i];
             io.wx[veh * (size_t)n + i] = C.x[i];
             const int q = n - 1 - i;

@@ -151,7 +151,7 @@ int eepacc_mem_debug_trace(int mem, double* out, int cap);
 /* clock64() cycles of vehicle 0's last solve by solver phase, out[8] (tracing must be enabled). */
 int eepacc_mem_debug_phases(int mem, double* out);
 /* Closed-loop QP kernel selection.  mode 0 (default): reduced-space active-set kernel (factorisation over the
- * free variables only, capacity fc of them, default 48) with the full-space kernel as fallback for vehicles
+ * free variables only, capacity fc of them, default 56) with the full-space kernel as fallback for vehicles
  * that do not fit; mode 1: full-space kernel only. */
 int eepacc_mem_set_qp_mode(int mem, int mode, int fc);
 /* eepacc_run pipelining: the batch advances as `groups` contiguous slices (1..32), each on its own CUDA stream
