@@ -6,9 +6,12 @@
 
 One bench "step" = one full closed-loop driving cycle (871 MPC steps, each = K5/K4/K2 build ->
 K3 QP solve -> post) for this rank's batch of synthetic perturbed scenarios:
-    N = 1 : BASELINE config[1]  "ABMPC closed loop, batch 4096 perturbed urban lead-vehicle scenarios"
-    N > 1 : weak scaling, 4096 scenarios per GPU, contiguous block partition of the scenario index,
-            no data-path collective; one NCCL all_gather of the KPI block at the end of each step.
+    default : BASELINE configs[2], the configuration the metric ("batched FBMPC QP solves/sec") is quoted on:
+            FBMPC, 8192 vehicles per GPU (65,536 over the 8 GPUs of a box), perturbed urban + highway scenarios
+            with vehicle-mass scatter, full 871-step cycle.
+    --ctrl ab --batch 4096 : BASELINE configs[1] "ABMPC closed loop, batch 4096 perturbed urban scenarios, 1 B200"
+    N > 1 : weak scaling, the same number of scenarios per GPU, contiguous block partition of the scenario
+            index, no data-path collective; one NCCL all_gather of the KPI block at the end of each step.
 value = closed-loop QP solves / s with the lead traces and route previews resident in HBM;
 e2e   = the same through the C-ABI with HOST buffers (lead upload + KPI download in the timed region).
 """
@@ -40,20 +43,33 @@ def parse():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--ctrl", default="ab", choices=["ab", "fb", "bl", "tv"])
-    ap.add_argument("--batch", type=int, default=4096, help="scenarios per GPU")
+    ap.add_argument("--ctrl", default="fb", choices=["ab", "fb", "bl", "tv"])
+    ap.add_argument("--batch", type=int, default=0, help="scenarios per GPU (0 = 8192 for fb, 4096 otherwise)")
     ap.add_argument("--cycle-steps", type=int, default=871, help="MPC steps per driving cycle")
     ap.add_argument("--cpu-sample", type=int, default=0, help="scenarios per core for the CPU baseline (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--groups", type=int, default=0, help="slices the per-step path pipelines the batch as (0 = library default)")
     ap.add_argument("--fused", action="store_true", help="time the fused closed-loop kernel (k5_cycle_kernel) instead of the sliced per-step path")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.batch <= 0:
+        args.batch = 8192 if args.ctrl == "fb" else 4096
+    return args
 
 
 def lead_2hz():
     d = np.load(os.path.join(GOLDEN, "lead_TO01_EAD.npz"))
     s = d["s_tv"]
     return np.r_[0.0, np.diff(s) / 0.5]
+
+
+def workload_name(ctrl, B, ns):
+    if ctrl == "fb":
+        return (f"FBMPC closed loop, {B} vehicles per GPU, perturbed urban (even b) / highway (odd b) lead-vehicle "
+                f"scenarios with vehicle-mass scatter, {ns} MPC steps/cycle (BASELINE configs[2]: 65,536 vehicles "
+                f"over 8 GPUs = 8192 per GPU)")
+    which = "configs[1]" if ctrl == "ab" else "configs[3], full route preview"
+    return (f"{ctrl.upper()}MPC closed loop, batch {B} perturbed urban lead-vehicle scenarios per GPU, "
+            f"{ns} MPC steps/cycle (BASELINE {which})")
 
 
 def make_workload(ctrl, B, first, n_steps):
@@ -67,6 +83,18 @@ def make_workload(ctrl, B, first, n_steps):
     routes, lead = U.perturbed_scenarios(B, lead_2hz(), highway_v_2hz=hw, mass=(ctrl == "fb"),
                                          full_route=(ctrl in ("bl", "tv")), n_steps=n_steps, first=first)
     return p, routes, lead
+
+
+def synth_inputs(ctrl, B, first):
+    """The same batch as make_workload, as inputs of the device-side lead synthesis (k5_lead_synth_kernel)."""
+    from eepacc_mpc_casadi_matlab_b200 import usecase as U
+    hw = None
+    if ctrl == "fb":
+        w = np.load(os.path.join(GOLDEN, "lead_WLTC.npz"))
+        hw = np.r_[0.0, np.diff(w["s_tv"]) / 0.5]
+    pert, _ = U.perturbation_table(B, highway=hw is not None, mass=(ctrl == "fb"),
+                                   full_route=(ctrl in ("bl", "tv")), first=first)
+    return pert, lead_2hz(), hw
 
 
 # ---------------------------------------------------------------------------------------------
@@ -118,8 +146,8 @@ def reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, args.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.ctrl.upper()}MPC closed loop, perturbed urban lead-vehicle scenarios, "
-                               f"{args.cycle_steps} MPC steps/cycle (bounded CPU sample of the same batch)"},
+        "config": {"workload": workload_name(args.ctrl, args.batch, args.cycle_steps) +
+                               " -- bounded CPU sample of the same batch"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -256,6 +284,22 @@ def main():
         kh = run_e2e()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    # ---- scenario leg (not part of `value`): the lead traces made in HBM from 128 B per scenario instead of
+    # uploaded (k5_lead_synth_kernel); checked against the uploaded traces of the same batch ----
+    synth = None
+    if rank == 0 and ns >= 2 and args.ctrl != "tv":
+        pert, base2, hw2 = synth_inputs(args.ctrl, B, rank * B)
+        ts_ = []
+        for _ in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            eng.synth_lead(pert, base2, hw2, ns)          # returns after the kernel has finished
+            ts_.append(time.perf_counter() - t0)
+        err = float(np.max(np.abs(eng.fetch_lead() - lead)))
+        eng.set_lead(lead_pinned.numpy())
+        synth = {"kernel": "k5_lead_synth_kernel", "ms_per_batch": 1e3 * min(ts_), "bytes_written": int(ns * B * 16),
+                 "gbs_incl_upload_and_sync": ns * B * 16 / min(ts_) / 1e9, "h2d_bytes": int(pert.nbytes + base2.nbytes),
+                 "replaces_h2d_bytes": int(lead_pinned.numel() * 8), "max_abs_diff_vs_host_traces": err}
     # max over ranks
     if world > 1:
         tt = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
@@ -319,8 +363,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.ctrl.upper()}MPC closed loop, batch {B} perturbed urban lead-vehicle "
-                                   f"scenarios per GPU, {ns} MPC steps/cycle (BASELINE configs[1] at N=1)",
+            "config": {"workload": workload_name(args.ctrl, B, ns),
                        "controller": args.ctrl, "batch_per_gpu": B, "cycle_steps": ns, "qp_n": n, "qp_m": m,
                        "path": "fused closed-loop kernel after the cold-start step" if cyc_ms else
                                f"per-step launches, {groups} slices pipelined on their own streams",
@@ -331,6 +374,7 @@ def main():
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(lead_pinned.numel() * 8),
                     "d2h_bytes_per_step": int(B * S.N_KPI * 8)},
             "gpu_launches": int(launches),
+            "lead_synthesis": synth,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": hbm_peak,
                          "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,

@@ -64,6 +64,7 @@ def load_library():
     L.eepacc_last_error.restype = C.c_char_p
     L.eepacc_mem_setup.argtypes = [C.c_int, C.c_int, C.POINTER(S.Params), C.POINTER(S.Route), C.c_longlong, C.c_int]
     L.eepacc_mem_set_lead.argtypes = [C.c_int, _dp, C.c_longlong]
+    L.eepacc_mem_synth_lead.argtypes = [C.c_int, _dp, C.c_longlong, _dp, C.c_longlong, _dp, C.c_longlong, C.c_double]
     L.eepacc_mem_set_step.argtypes = [C.c_int, C.c_int, C.c_double]
     L.eepacc_mem_set_stream.argtypes = [C.c_int, C.c_void_p]
     L.eepacc_mem_launch_count.restype = C.c_longlong
@@ -290,6 +291,27 @@ class Engine:
         rc = self.L.eepacc_mem_set_lead(self.mem, lead.ctypes.data_as(_dp), lead.shape[0])
         if rc:
             raise EepaccError(self._err())
+        self._n_lead = lead.shape[0]
+
+    def synth_lead(self, pert, base_v_2hz, highway_v_2hz=None, n_steps=871, tv_length=4.0):
+        """Make the lead traces of a perturbed scenario batch on the device (k5_lead_synth_kernel) instead of
+        uploading them: pert float64[B, N_PERT] from usecase.perturbation_table, 2 Hz cycle samples as in
+        usecase.synth_lead_host (its host statement)."""
+        pert = np.ascontiguousarray(pert, dtype=np.float64)
+        assert pert.shape == (self.B, S.N_PERT)
+        base = np.ascontiguousarray(base_v_2hz, dtype=np.float64)
+        hw = None if highway_v_2hz is None else np.ascontiguousarray(highway_v_2hz, dtype=np.float64)
+        rc = self.L.eepacc_mem_synth_lead(self.mem, base.ctypes.data_as(_dp), base.size,
+                                          hw.ctypes.data_as(_dp) if hw is not None else None,
+                                          hw.size if hw is not None else 0, pert.ctypes.data_as(_dp),
+                                          int(n_steps), float(tv_length))
+        if rc:
+            raise EepaccError(f"eepacc_mem_synth_lead failed ({rc}): {self._err()}")
+        self._n_lead = int(n_steps)
+
+    def fetch_lead(self):
+        """The lead trace resident on the device (uploaded or synthesised) -> host [n_steps, B, 2]."""
+        return self.debug_fetch(9, self._n_lead * self.B * 2).reshape(self._n_lead, self.B, 2)
 
     def run(self, n_steps, want_log=True, device_out=None):
         """Whole closed loop on the device (lead set by set_lead).  -> (log [n_steps,B,12] | None, kpi [B,8])."""

@@ -61,7 +61,7 @@ struct Mem {
     DBuf routes, s_prev, v_prev, Fm_prev, Fb_prev, a_minus1, v_tv_meas, fbA, fbD, prev_sol, x0, dyn;
     DBuf g, lba, uba, sblk;     // closed loop is matrix-free: no dense H / A is ever stored
     DBuf wx, wy, widx, wside, wnA, warm, xsol, cost, status, iter, counters;
-    DBuf kpi_acc, kpi, lead, lead_step, logrow, dbg;
+    DBuf kpi_acc, kpi, lead, lead_step, logrow, dbg, synth_in;
     DBuf rowtab, rowc;          // packed constraint rows of the controller for the reduced-space QP kernel
     DBuf defer_list, defer_cnt; // vehicles the reduced-space QP kernel hands to the full-space kernel
     DBuf hscr;                  // [B][4 (n + m)] homotopy state of the reduced-space QP kernel
@@ -89,7 +89,7 @@ struct Mem {
     {
         DBuf* all[] = { &routes, &s_prev, &v_prev, &Fm_prev, &Fb_prev, &a_minus1, &v_tv_meas, &fbA, &fbD, &prev_sol,
                         &x0, &dyn, &g, &lba, &uba, &sblk, &wx, &wy, &widx, &wside, &wnA, &warm, &xsol, &cost,
-                        &status, &iter, &counters, &kpi_acc, &kpi, &lead, &lead_step, &logrow, &dbg, &defer_list, &defer_cnt, &rowtab, &rowc, &hscr, &defer_list2, &cyc_counter, &cyc_big };
+                        &status, &iter, &counters, &kpi_acc, &kpi, &lead, &lead_step, &logrow, &dbg, &defer_list, &defer_cnt, &rowtab, &rowc, &hscr, &defer_list2, &cyc_counter, &cyc_big, &synth_in };
         for (DBuf* b : all) b->release();
         for (auto& b : in) b.release();
         for (auto& b : out) b.release();
@@ -559,6 +559,32 @@ int eepacc_mem_set_lead(int mem, const double* lead, long long n_steps)
     return EEPACC_OK;
 }
 
+int eepacc_mem_synth_lead(int mem, const double* base, long long n_base, const double* hw, long long n_hw,
+                          const double* pert, long long n_steps, double tv_length)
+{
+    Mem* M = get_mem(mem);
+    if (!M || !M->ready) return fail(EEPACC_ERR_ARG, "mem not set up");
+    if (!base || n_base <= 0 || !pert || n_steps < 2 || (hw && n_hw <= 0))
+        return fail(EEPACC_ERR_ARG, "bad lead synthesis arguments");
+    CK(cudaSetDevice(M->device));
+    const size_t B = (size_t)M->B;
+    if (M->lead.ensure((size_t)n_steps * B * 2 * 8)) return EEPACC_ERR_MEM;
+    const size_t nb = (size_t)n_base * 8, nh = hw ? (size_t)n_hw * 8 : 0, np_ = B * EEPACC_N_PERT * 8;
+    if (M->synth_in.ensure(nb + nh + np_)) return EEPACC_ERR_MEM;
+    char* d = (char*)M->synth_in.p;
+    CK(cudaMemcpyAsync(d, base, nb, cudaMemcpyHostToDevice, M->stream));
+    if (hw) CK(cudaMemcpyAsync(d + nb, hw, nh, cudaMemcpyHostToDevice, M->stream));
+    CK(cudaMemcpyAsync(d + nb + nh, pert, np_, cudaMemcpyHostToDevice, M->stream));
+    if (eep_launch_lead_synth((long long)B, (int)n_steps, M->p.Ts, tv_length, (const double*)d, (int)n_base,
+                              hw ? (const double*)(d + nb) : nullptr, (int)n_hw, (const double*)(d + nb + nh),
+                              M->lead.as<double>(), M->stream))
+        return fail(EEPACC_ERR_CUDA, "k5_lead_synth_kernel launch");
+    M->launches += 1;
+    CK(cudaStreamSynchronize(M->stream));
+    M->n_lead = n_steps;
+    return EEPACC_OK;
+}
+
 int eepacc_mem_set_stream(int mem, void* stream)
 {
     Mem* M = get_mem(mem);
@@ -726,6 +752,7 @@ long long eepacc_mem_debug_fetch(int mem, int what, double* out, long long cap)
     case 5: src = M->status.p; cnt = B; break;
     case 6: src = M->iter.p; cnt = B; break;
     case 7: src = M->cost.p; cnt = B; break;
+    case 9: src = M->lead.p; cnt = M->n_lead * B * 2; break;
     case 8: src = M->defer_cnt.p; cnt = 2; break;   // int[4]: vehicles deferred to the full-space kernel in the last step
     default: fail(EEPACC_ERR_ARG, "unknown buffer"); return -1;
     }

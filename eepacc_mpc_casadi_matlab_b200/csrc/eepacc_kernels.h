@@ -123,6 +123,8 @@ size_t eep_qpr_smem_bytes(int n, int m, int fc);
 int eep_qpr_build_rowtab(int ctrl, const eepacc_params* p, int m, unsigned long long* tab_dev, double* consts_dev, cudaStream_t st);
 size_t eep_qp_smem_bytes(int n, int m, int smode);
 int eep_launch_post(const eepacc_params* p, const eep_post_io* io, cudaStream_t st);
+int eep_launch_lead_synth(long long B, int n_steps, double ts, double tv_length, const double* base, int n_base,
+                          const double* hw, int n_hw, const double* pert, double* lead, cudaStream_t st);
 int eep_launch_kpi_final(const eepacc_params* p, long long B, int n_steps, const double* kpi_acc, double* kpi, cudaStream_t st);
 double eep_dfma_peak(int device);
 #ifdef __cplusplus

@@ -18,6 +18,7 @@ AB, FB, BL, TV = 0, 1, 2, 3
 CTRL_NAMES = {"ab": AB, "fb": FB, "bl": BL, "tv": TV}
 
 FLAG_DEVICE_PTR = 1
+N_PERT = 16                      # eepacc.h EEPACC_N_PERT
 
 
 class Params(C.Structure):

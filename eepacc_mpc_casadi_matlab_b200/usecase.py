@@ -129,36 +129,31 @@ def _uniform(rng, lo, hi, size=None):
     return lo + (hi - lo) * rng.random(size)
 
 
-def perturbed_scenarios(B, base_v_2hz, seed=0xEE9ACC, highway_v_2hz=None, mass=False,
-                        full_route=False, n_steps=871, ts=0.5, first=0):
-    """Synthetic scenario batch: global scenarios first..first+B-1.
-    Global scenario 0 is the unperturbed golden case.  Returns (routes: Route*B ctypes array, lead: float64[n_steps, B, 2]).
+N_PERT = 16      # eepacc.h EEPACC_N_PERT: scale, delay, gap, 3 x (A, f, phase), highway flag, 3 spare
 
-    base_v_2hz / highway_v_2hz: 2 Hz lead speed samples (after resample + threshold)."""
+
+def perturbation_table(B, seed=0xEE9ACC, highway=False, mass=False, full_route=False, first=0):
+    """The random draws of the synthetic scenario batch, global scenarios
+    first..first+B-1, counter-based (Philox key = seed, counter = b) so that every rank draws its own block.
+    Global scenario 0 is the unperturbed golden case.
+    Returns (pert float64[B, N_PERT] for the lead synthesis, routes: Route*B ctypes array)."""
     routes = (Route * B)()
-    lead = np.zeros((n_steps, B, 2))
-    t = np.arange(n_steps) * ts
+    pert = np.zeros((B, N_PERT))
     for bl in range(B):
         b = first + bl
         rng = np.random.Generator(np.random.Philox(key=seed, counter=[b, 0, 0, 0]))
-        hw = highway_v_2hz is not None and (b % 2 == 1)
-        y = np.array(highway_v_2hz if hw else base_v_2hz, dtype=np.float64)[:n_steps].copy()
-        if len(y) < n_steps:
-            y = np.concatenate([y, np.full(n_steps - len(y), y[-1])])
+        hw = bool(highway) and (b % 2 == 1)
         zones = [[80, 0], [120, 2000], [100, 9000]] if hw else [[60, 0], [50, 1000]]
-        gap = 10.0
+        row = pert[bl]
+        row[0], row[1], row[2], row[12] = 1.0, 0.0, 10.0, float(hw)
         ms = 1.0
         if b > 0:
-            y *= _uniform(rng, 0.85, 1.15)
-            delay = int(rng.integers(0, 21))
-            if delay:
-                y = np.concatenate([np.zeros(delay), y])[:n_steps]
-            gap = _uniform(rng, 6.0, 30.0)
-            for _ in range(3):
-                A, f, ph = _uniform(rng, 0, 0.3), _uniform(rng, 0.01, 0.1), _uniform(rng, 0, 2 * math.pi)
-                y = y + A * np.sin(2 * math.pi * f * t + ph) * (y > 0)
-            y = np.maximum(y, 0.0)
-            y[y < 0.1] = 0.0
+            row[0] = _uniform(rng, 0.85, 1.15)
+            row[1] = int(rng.integers(0, 21))
+            row[2] = _uniform(rng, 6.0, 30.0)
+            for r in range(3):
+                row[3 + 3 * r], row[4 + 3 * r], row[5 + 3 * r] = (_uniform(rng, 0, 0.3), _uniform(rng, 0.01, 0.1),
+                                                                 _uniform(rng, 0, 2 * math.pi))
             zones = [[v + float(rng.choice([-10, 0, 10])), s] for v, s in zones]
             for k in range(1, len(zones)):
                 zones[k][1] = max(zones[k - 1][1] + 50.0, round(zones[k][1] + _uniform(rng, -200, 200)))
@@ -188,10 +183,44 @@ def perturbed_scenarios(B, base_v_2hz, seed=0xEE9ACC, highway_v_2hz=None, mass=F
             routes[bl] = generate_use_case(zones, curves, slopes, stops, tls, ms)
         except ValueError:
             routes[bl] = generate_use_case(zones, None, None, stops, tls, ms)
-        s_tv, v_tv = lead_from_half_hz(y, t_sim=(n_steps - 1) * ts, ts=ts, init_dist=gap)
+    return pert, routes
+
+
+def synth_lead_host(pert, base_v_2hz, highway_v_2hz=None, n_steps=871, ts=0.5, tv_length=4.0):
+    """Host statement of what k5_lead_synth_kernel (csrc/k5_scenario.cu) computes from a perturbation table:
+    scale, delay, ripple and re-threshold the 2 Hz cycle, then Run_DrivingCycle.m:35-46 + Main.m:88.
+    -> lead float64[n_steps, B, 2]."""
+    B = pert.shape[0]
+    lead = np.zeros((n_steps, B, 2))
+    t = np.arange(n_steps) * ts
+    for bl in range(B):
+        row = pert[bl]
+        hw = highway_v_2hz is not None and row[12] != 0.0
+        y = np.array(highway_v_2hz if hw else base_v_2hz, dtype=np.float64)[:n_steps].copy()
+        if len(y) < n_steps:
+            y = np.concatenate([y, np.full(n_steps - len(y), y[-1])])
+        y *= row[0]
+        delay = int(row[1])
+        if delay:
+            y = np.concatenate([np.zeros(delay), y])[:n_steps]
+        for r in range(3):
+            A, f, ph = row[3 + 3 * r], row[4 + 3 * r], row[5 + 3 * r]
+            y = y + A * np.sin(2 * math.pi * f * t + ph) * (y > 0)
+        y = np.maximum(y, 0.0)
+        y[y < 0.1] = 0.0
+        s_tv, v_tv = lead_from_half_hz(y, t_sim=(n_steps - 1) * ts, ts=ts, init_dist=row[2], tv_length=tv_length)
         lead[:, bl, 0] = s_tv
         lead[:, bl, 1] = v_tv
-    return routes, lead
+    return lead
+
+
+def perturbed_scenarios(B, base_v_2hz, seed=0xEE9ACC, highway_v_2hz=None, mass=False,
+                        full_route=False, n_steps=871, ts=0.5, first=0):
+    """Synthetic scenario batch with the lead traces made on the host (tests, CPU baseline, e2e upload path).
+    Returns (routes: Route*B ctypes array, lead: float64[n_steps, B, 2]).  The device path is
+    ``perturbation_table`` + ``Engine.synth_lead``."""
+    pert, routes = perturbation_table(B, seed, highway_v_2hz is not None, mass, full_route, first)
+    return routes, synth_lead_host(pert, base_v_2hz, highway_v_2hz, n_steps, ts)
 
 
 # ---- the reference's named use cases (GetUseCase.m:12-222; use case 0 = Settings.m:146-190) ----
@@ -274,7 +303,7 @@ def get_use_case(num, params, lead_data=None, tv_length=4.0):
 def generate_lead_tvmpc(run_tvmpc, params, route, n_steps, tv_init_dist=10.0, tv_init_vel=0.0, tv_length=4.0):
     """Main.m:84-90 with the commented RunOpt_TVMPC line: the target vehicle drives the same route under the TVMPC
     from TVinitDist/TVinitVel (RunOpt_TVMPC.m:22-23, Settings.m:205-207); the trace is shifted to its rear bumper.
-    ``run_tvmpc(params, route, n_steps) -> (s_opt, v_opt)`` is the engine (api.RunOpt_TVMPC) or, in tests, the oracle."""
+    ``run_tvmpc(params, route, n_steps) -> (s_opt, v_opt)`` is the engine (api.RunOpt_TVMPC) or, in tests, the CPU checker."""
     import copy
     p = copy.copy(params)
     p.s_init, p.v_init = float(tv_init_dist), float(tv_init_vel)

@@ -126,6 +126,13 @@ int eepacc_mem_set_step(int mem, int kk, double t0);
 /* Upload a whole lead trace: host double[n_steps][B][2] = (s_tv, v_tv) per step.  Enables
  * eepacc_run_*(): the whole closed loop without per-step host involvement. */
 int eepacc_mem_set_lead(int mem, const double* lead, long long n_steps);
+/* Synthesise the lead traces of a perturbed scenario batch on the device instead of uploading them
+ * (replaces the host loop Run_DrivingCycle.m:35-46 + Main.m:88 per scenario).
+ * base / hw: host double[n_base] / [n_hw] 2 Hz lead speed samples of the urban / highway cycle (hw may be NULL);
+ * pert: host double[B][EEPACC_N_PERT] = scale, delay (steps), initial gap (m), 3 x (amplitude m/s, frequency Hz,
+ * phase rad), use-highway flag, 3 spare.  Result: the same device buffer eepacc_mem_set_lead fills. */
+int eepacc_mem_synth_lead(int mem, const double* base, long long n_base, const double* hw, long long n_hw,
+                          const double* pert, long long n_steps, double tv_length);
 /* CUDA stream (cudaStream_t as void*) the mem launches on; default stream if never set. */
 int eepacc_mem_set_stream(int mem, void* stream);
 /* Number of kernel launches issued through this mem so far (bench.py's gpu_launches). */
@@ -169,7 +176,7 @@ int eepacc_mem_get_fused(int mem);
 int eepacc_mem_get_cycle_timing(int mem, double* out);
 int eepacc_mem_get_groups(int mem);
 /* Developer aid: copy a per-step device buffer of the closed loop to the host (0 sblk, 1 g, 2 lba, 3 uba,
- * 4 x, 5 status, 6 iter, 7 cost, 8 deferred-vehicle count); returns the number of doubles written or < 0. */
+ * 4 x, 5 status, 6 iter, 7 cost, 8 deferred-vehicle count, 9 the lead trace [n_lead][B][2]); returns the number of doubles written or < 0. */
 long long eepacc_mem_debug_fetch(int mem, int what, double* out, long long cap);
 /* FP64-FMA peak microbenchmark (register-resident DFMA chains); returns GFLOP/s or <0. */
 double eepacc_measure_dfma_peak(int device);
@@ -246,6 +253,7 @@ EEPACC_DECLARE(eepacc_run)
  * [0] E_opt(end) J   [1] s_opt(end) m   [2] travel time at cutOffDist s   [3] E_opt at cut-off J
  * [4] max a   [5] min a   [6] rms a (over 1..distInd)   [7] failed QPs (sum exitMessage)       */
 #define EEPACC_N_KPI 8
+#define EEPACC_N_PERT 16
 
 #ifdef __cplusplus
 }
