@@ -69,6 +69,9 @@ def test_mem_handles_and_loud_failure_without_device():
     iw = (C.c_longlong * 2)(1, 0)
     rc = L.eepacc_step_fb(None, None, iw, None, mem)
     assert rc != 0 and b"not set up" in L.eepacc_last_error()
+    one = (C.c_double * 16)()
+    rc = L.eepacc_mem_synth_lead(mem, one, 16, None, 0, one, 10, 4.0)         # scenario synthesis needs a set-up mem too
+    assert rc != 0 and b"not set up" in L.eepacc_last_error()
     if not torch.cuda.is_available():
         p, r = S.default_params("mc"), U.default_route()
         rc = L.eepacc_mem_setup(mem, S.FB, C.byref(p), C.byref(r), 1, -1)
