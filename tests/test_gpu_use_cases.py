@@ -151,3 +151,31 @@ def test_device_lead_synthesis_matches_host_statement(lead_urban, highway):
     eng.close()
     assert np.max(np.abs(log_d[:, :, :2] - log_h[:, :, :2])) < 1e-6
     assert np.array_equal(log_d[:, :, 9], log_h[:, :, 9])
+
+
+def test_device_lead_synthesis_edge_cases(lead_urban):
+    """Shortest trace (2 steps), one vehicle, a ragged last CTA (130 vehicles), a delay longer than the run,
+    and a base cycle shorter than the run (padded with its last sample, as the host statement does)."""
+    api = _api()
+    p = S.default_params("mc")
+    y = np.r_[0.0, np.diff(lead_urban[:, 0]) / p.Ts][:871]
+    for B, n, base in ((1, 2, y), (130, 15, y), (130, 120, y[:50]), (3, 871, y)):
+        pert, routes = U.perturbation_table(B)
+        if B > 2:
+            pert[1, 1] = 20.0                     # 20 steps of standstill first (longer than the 15-step run)
+            pert[2, 0] = 1.15
+        host = U.synth_lead_host(pert, base, None, n)
+        eng = api.Engine("bl", p, routes, B=B)
+        eng.synth_lead(pert, base, None, n)
+        dev = eng.fetch_lead()
+        eng.close()
+        assert dev.shape == (n, B, 2)
+        assert np.max(np.abs(dev - host)) < 1e-9, (B, n)
+        if B > 2 and n == 15:
+            assert (dev[:, 1, 1] == 0).all() and (dev[:, 1, 0] == dev[0, 1, 0]).all()
+    with pytest.raises(api.EepaccError):
+        eng = api.Engine("bl", p, U.default_route(), B=1)
+        try:
+            eng.synth_lead(np.zeros((1, S.N_PERT)), y, None, 1)       # a trace needs at least two steps
+        finally:
+            eng.close()
