@@ -8,7 +8,7 @@
  *
  * Parity pins (tests/test_oracle_golden.py):
  *   - plant step, power maps, RK4 map F, QP build + condensing: pinned against the
- *     reference's saved golden .mat data (tests/golden/*.npz).
+ *     reference's saved golden .mat data (tests/golden/ npz files).
  *   - QP solve: the reference solver is qpOASES 3.2 inside CasADi 3.6.3's conic plugin
  *     (binary only, absent from /root/reference).  The oracle's own dense parametric
  *     active-set solver (qp_oracle.c) is pinned through the golden first-stage primal

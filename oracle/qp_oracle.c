@@ -36,6 +36,31 @@
 #define EPS_ROW   1.0e-12    /* |a'dx| below EPS_ROW*|a|_1*|dx|_inf is numerically zero      */
 #define FEAS_TOL  1.0e-10    /* a bound violated by less than this at the full step is not blocking (cf. qpOASES boundTolerance) */
 #define LP_REG    1.0e-6
+#define FLAT_TOL  1.0e-9     /* |g'd| <= FLAT_TOL |g| |d|: the gradient is orthogonal to d within round-off */
+#define TIE_TOL   1.0e-11    /* ratio tests: candidates whose numerator lies within TIE_TOL*(scale) of the
+                              * smallest ratio are TIED; the lowest constraint index among them is taken
+                              * (two-pass Harris ratio test).  Makes the active-set path independent of
+                              * round-off (summation order, FMA contraction) at degenerate vertices. */
+
+/* ---- two-pass ratio test ----------------------------------------------------------------
+ * candidate i blocks at t_i = num_i/den_i (num >= 0, den > 0); del_i = noise level of num_i.
+ * pass 1: tmax = min_i (num_i + del_i)/den_i;  pass 2: among t_i <= tmax the lowest key wins.
+ * With del = 0 this is the textbook "first minimum"; with del > 0 candidates that differ by
+ * round-off only are resolved by index, identically in every arithmetic. */
+typedef struct { double num, den, del; int key, aux; } rt_cand;
+static int rt_select(const rt_cand* c, int nc)
+{
+    double tmax = INFINITY;
+    int best = -1;
+    for (int i = 0; i < nc; ++i) {
+        double t = (c[i].num + c[i].del) / c[i].den;
+        if (t < tmax) tmax = t;
+    }
+    for (int i = 0; i < nc; ++i) {
+        if (c[i].num / c[i].den <= tmax && (best < 0 || c[i].key < c[best].key)) best = i;
+    }
+    return best;
+}
 
 struct orc_qpws {
     int n, m, mt;
@@ -52,7 +77,10 @@ struct orc_qpws {
     const double *H, *A, *g_new;
     double hscale;
     double reg;       /* Tikhonov term for an all-zero Hessian (LP), see orc_qpsolve */
+    double tie;       /* TIE_TOL, or 0 for the eps-regularised LPs (see orc_qpsolve) */
+    double ynoise;    /* scale of the round-off carried by the multipliers: max|y| at set-up + sum of tau*max|dy| */
     int n_exch, n_refac;
+    rt_cand* cand;    /* [2*mt + n] ratio-test candidates */
 };
 
 static double* dalloc(size_t n) { return (double*)calloc(n ? n : 1, sizeof(double)); }
@@ -73,6 +101,7 @@ orc_qpws* orc_qpws_new(int n, int m)
     w->tmp1 = dalloc(w->mt); w->tmp2 = dalloc(w->mt); w->tmp3 = dalloc(w->mt); w->tmp4 = dalloc(w->mt);
     w->dg = dalloc(n); w->dlb = dalloc(w->mt); w->dub = dalloc(w->mt);
     w->anorm = dalloc(w->mt);
+    w->cand = (rt_cand*)calloc((size_t)(2 * w->mt + n + 1), sizeof(rt_cand));
     return w;
 }
 
@@ -82,7 +111,7 @@ void orc_qpws_free(orc_qpws* w)
     free(w->widx); free(w->st); free(w->tabu); free(w->x); free(w->y); free(w->Ax); free(w->g_cur);
     free(w->lb_cur); free(w->ub_cur); free(w->lb_new); free(w->ub_new); free(w->Q); free(w->T);
     free(w->R); free(w->dx); free(w->dyW); free(w->Adx); free(w->tmp1); free(w->tmp2);
-    free(w->tmp3); free(w->tmp4); free(w->dg); free(w->dlb); free(w->dub); free(w->anorm);
+    free(w->tmp3); free(w->tmp4); free(w->dg); free(w->dlb); free(w->dub); free(w->anorm); free(w->cand);
     free(w);
 }
 
@@ -347,7 +376,7 @@ static void reanchor(orc_qpws* w, int recompute_y)
             t[c] = s;
         }
         Tt_solve(w, t, yw);
-        for (int k = 0; k < nA; ++k) w->y[w->widx[k]] = yw[k];
+        for (int k = 0; k < nA; ++k) { w->y[w->widx[k]] = yw[k]; if (fabs(yw[k]) > w->ynoise) w->ynoise = fabs(yw[k]); }
     }
     for (int k = 0; k < nA; ++k) {
         int c = w->widx[k];
@@ -461,26 +490,50 @@ static int resolve_pending(orc_qpws* w, int c_out, int side_out, int dbg, int ze
             for (int i = 0; i < n; ++i) sgn += a_c[i] * d[i];
             if (side_out > 0) sgn = -sgn;
         } else {                                         /* descent direction of the aux QP */
+            double gn = 0, dn2 = 0;
             Hmul(w, w->x, hz);
-            for (int i = 0; i < n; ++i) sgn -= (hz[i] + w->g_cur[i]) * d[i];
+            for (int i = 0; i < n; ++i) { double gi = hz[i] + w->g_cur[i]; sgn -= gi * d[i]; gn += gi * gi; dn2 += d[i] * d[i]; }
+            if (fabs(sgn) <= FLAT_TOL * sqrt(gn) * sqrt(dn2)) {
+                /* the gradient is orthogonal to d within round-off (flat direction): both senses are
+                 * descent directions of equal merit; take a canonical one so that every arithmetic
+                 * makes the same choice: away from the bound that was left, else first significant
+                 * component of d positive */
+                double a_c[ORC_NMAX], an = 0;
+                get_row(w, c_out, a_c);
+                sgn = 0;
+                for (int i = 0; i < n; ++i) { sgn += a_c[i] * d[i]; an += a_c[i] * a_c[i]; }
+                if (side_out > 0) sgn = -sgn;
+                if (fabs(sgn) <= FLAT_TOL * sqrt(an) * sqrt(dn2)) {
+                    double dmx = 0;
+                    for (int i = 0; i < n; ++i) if (fabs(d[i]) > dmx) dmx = fabs(d[i]);
+                    sgn = 1.0;
+                    for (int i = 0; i < n; ++i) if (fabs(d[i]) > 0.25 * dmx) { sgn = d[i]; break; }
+                }
+            }
         }
+        if (dbg) fprintf(stderr, "   exch-dir: first %d sgn %.3e\n", first, sgn);
         if (sgn < 0) for (int i = 0; i < n; ++i) d[i] = -d[i];
         Amul(w, d, w->Adx);
         double tmin = INFINITY; int j = -1, jside = 0;
         double dn = 0; for (int i = 0; i < n; ++i) dn += d[i] * d[i]; dn = sqrt(dn);
+        double xmax = 0; for (int i = 0; i < n; ++i) if (fabs(w->x[i]) > xmax) xmax = fabs(w->x[i]);
+        rt_cand* cd = w->cand; int nc = 0;
         for (int cc = 0; cc < mt; ++cc) {
             if (w->st[cc] != 0 || w->anorm[cc] == 0.0) continue;
             double adx = w->Adx[cc];
             const double rz = EPS_ROW * w->anorm[cc] * dn;
+            const double del = w->tie * w->anorm[cc] * (1.0 + xmax);
             if (adx < -rz && !isinf(w->lb_cur[cc])) {
                 double sl = w->Ax[cc] - w->lb_cur[cc]; if (sl < 0) sl = 0;
-                double t = sl / (-adx);
-                if (t < tmin) { tmin = t; j = cc; jside = -1; }
+                cd[nc].num = sl; cd[nc].den = -adx; cd[nc].del = del; cd[nc].key = 2 * cc; cd[nc].aux = cc; ++nc;
             } else if (adx > rz && !isinf(w->ub_cur[cc])) {
                 double sl = w->ub_cur[cc] - w->Ax[cc]; if (sl < 0) sl = 0;
-                double t = sl / adx;
-                if (t < tmin) { tmin = t; j = cc; jside = 1; }
+                cd[nc].num = sl; cd[nc].den = adx; cd[nc].del = del; cd[nc].key = 2 * cc + 1; cd[nc].aux = cc; ++nc;
             }
+        }
+        {
+            const int sel = rt_select(cd, nc);
+            if (sel >= 0) { tmin = (cd[sel].num <= cd[sel].del) ? 0.0 : cd[sel].num / cd[sel].den; j = cd[sel].aux; jside = (cd[sel].key & 1) ? 1 : -1; }
         }
         if (dbg) fprintf(stderr, "   exch: rho2 %.3e zhz %.3e out %d -> j %d jside %d t %.3e kpd %d\n", rho2, zhz, c_out, j, jside, tmin, kpd);
         if (j < 0) return EEPACC_QP_UNBOUNDED;
@@ -575,6 +628,10 @@ int orc_qpsolve(orc_qpws* w, const double* H, const double* g, const double* A,
         if (hmax == 0.0) w->reg = LP_REG;
     }
     if (w->hscale < LP_REG) w->hscale = LP_REG;
+    /* tie tolerance of the ratio tests.  The eps-regularised LPs keep exact comparisons: with a curvature of
+     * 1e-6 against multipliers of 1e7 a tie tolerance on the duals would have to be below round-off to leave
+     * the least-norm optimum alone, and their optimum is unique anyway (no flat directions). */
+    w->tie = (w->reg != 0.0) ? 0.0 : TIE_TOL;
 
     for (int c = 0; c < m; ++c) w->anorm[c] = 0.0;
     for (int j = 0; j < n; ++j)
@@ -611,6 +668,8 @@ int orc_qpsolve(orc_qpws* w, const double* H, const double* g, const double* A,
     }
     setup_aux(w);
     w->warm = 1;
+    w->ynoise = 1.0;
+    for (int k = 0; k < w->nA; ++k) if (fabs(w->y[w->widx[k]]) > w->ynoise) w->ynoise = fabs(w->y[w->widx[k]]);
 
     /* ---------------- homotopy ---------------- */
     double* db = w->tmp4;
@@ -630,22 +689,24 @@ int orc_qpsolve(orc_qpws* w, const double* H, const double* g, const double* A,
         kkt_step(w, w->dg, dbw, w->dx, w->dyW);
         Amul(w, w->dx, w->Adx);
 
-        /* ratio tests */
+        /* ratio tests (two-pass, see rt_select): primal candidates keyed 2c+side, dual candidates 2mt+c */
         double tau = 1.0; int blk = -1, blk_side = 0, blk_dual = -1;
-        double dxmax = 0;
-        for (int i = 0; i < n; ++i) if (fabs(w->dx[i]) > dxmax) dxmax = fabs(w->dx[i]);
+        double dxmax = 0, xmax = 0, ymax = 0;
+        for (int i = 0; i < n; ++i) { if (fabs(w->dx[i]) > dxmax) dxmax = fabs(w->dx[i]); if (fabs(w->x[i]) > xmax) xmax = fabs(w->x[i]); }
+        for (int k = 0; k < nA; ++k) if (fabs(w->y[w->widx[k]]) > ymax) ymax = fabs(w->y[w->widx[k]]);
+        rt_cand* cd = w->cand; int nc = 0;
         for (int c = 0; c < mt; ++c) {
             if (w->st[c] != 0 || w->anorm[c] == 0.0) continue;     /* all-zero rows can never be added */
             if (w->tabu[c] == 2) continue;                         /* left during this run of zero steps: no re-entry */
             double adx = w->Adx[c];
             const double rz = EPS_ROW * w->anorm[c] * dxmax;
+            const double del = w->tie * w->anorm[c] * (1.0 + xmax);
             if (!isinf(w->lb_cur[c])) {
                 double rate = adx - w->dlb[c];
                 double sl = w->Ax[c] - w->lb_cur[c]; if (sl < 0) sl = 0;
                 if (rate < -(EPS_RATE * (1.0 + fabs(adx) + fabs(w->dlb[c])) + rz) &&
                     -rate - sl > FEAS_TOL * (1.0 + fabs(w->lb_new[c]))) {
-                    double t = sl / (-rate);
-                    if (t < tau) { tau = t; blk = c; blk_side = -1; }
+                    if (sl / (-rate) < 1.0) { cd[nc].num = sl; cd[nc].den = -rate; cd[nc].del = del; cd[nc].key = 2 * c; cd[nc].aux = c; ++nc; }
                 }
             }
             if (!isinf(w->ub_cur[c])) {
@@ -653,8 +714,7 @@ int orc_qpsolve(orc_qpws* w, const double* H, const double* g, const double* A,
                 double sl = w->ub_cur[c] - w->Ax[c]; if (sl < 0) sl = 0;
                 if (rate < -(EPS_RATE * (1.0 + fabs(adx) + fabs(w->dub[c])) + rz) &&
                     -rate - sl > FEAS_TOL * (1.0 + fabs(w->ub_new[c]))) {
-                    double t = sl / (-rate);
-                    if (t < tau) { tau = t; blk = c; blk_side = 1; }
+                    if (sl / (-rate) < 1.0) { cd[nc].num = sl; cd[nc].den = -rate; cd[nc].del = del; cd[nc].key = 2 * c + 1; cd[nc].aux = c; ++nc; }
                 }
             }
         }
@@ -666,15 +726,26 @@ int orc_qpsolve(orc_qpws* w, const double* H, const double* g, const double* A,
             if (w->tabu[c] == 1) continue;                       /* entered during this run of zero steps: stays */
             double yc = w->y[c], dy = w->dyW[k];
             double thr = EPS_RATE * (1.0 + dys);
+            const double ysc = 1.0 + fabs(yc) + fabs(dy);         /* scale of this multiplier along the step */
+            const double del = w->tie * w->ynoise;
+            /* a dual that would end within dtol of zero at the full step is not blocking (dual twin of FEAS_TOL) */
+            const double dtol = fmax(FEAS_TOL * ysc, del);
             if (w->st[c] < 0 && dy < -thr) {
-                double t = (yc > 0 ? yc : 0) / (-dy);
-                if (t < tau) { tau = t; blk = -1; blk_dual = k; }
+                double num = (yc > 0 ? yc : 0);
+                if (num / (-dy) < 1.0 && -dy - num > dtol) { cd[nc].num = num; cd[nc].den = -dy; cd[nc].del = del; cd[nc].key = 2 * mt + c; cd[nc].aux = k; ++nc; }
             } else if (w->st[c] > 0 && dy > thr) {
-                double t = (yc < 0 ? -yc : 0) / dy;
-                if (t < tau) { tau = t; blk = -1; blk_dual = k; }
+                double num = (yc < 0 ? -yc : 0);
+                if (num / dy < 1.0 && dy - num > dtol) { cd[nc].num = num; cd[nc].den = dy; cd[nc].del = del; cd[nc].key = 2 * mt + c; cd[nc].aux = k; ++nc; }
             }
         }
-        if (blk >= 0) blk_dual = -1;
+        {
+            const int sel = rt_select(cd, nc);
+            if (sel >= 0) {
+                tau = (cd[sel].num <= cd[sel].del) ? 0.0 : cd[sel].num / cd[sel].den;   /* within round-off of zero: a zero step */
+                if (cd[sel].key < 2 * mt) { blk = cd[sel].aux; blk_side = (cd[sel].key & 1) ? 1 : -1; }
+                else blk_dual = cd[sel].aux;
+            }
+        }
         /* anti-cycling: constraints that enter while the homotopy makes no progress may not leave
          * again through the dual test until it does (flat edges at degenerate vertices otherwise
          * ping-pong between two equally optimal vertices) */
@@ -682,6 +753,7 @@ int orc_qpsolve(orc_qpws* w, const double* H, const double* g, const double* A,
         if (!zero_step) memset(w->tabu, 0, (size_t)mt);
 
         /* take the step */
+        w->ynoise += tau * dys;
         for (int i = 0; i < n; ++i) { w->x[i] += tau * w->dx[i]; }
         for (int k = 0; k < nA; ++k) w->y[w->widx[k]] += tau * w->dyW[k];
         for (int c = 0; c < mt; ++c) w->Ax[c] += tau * w->Adx[c];
@@ -729,6 +801,9 @@ int orc_qpsolve(orc_qpws* w, const double* H, const double* g, const double* A,
                 double lmax = 0;
                 for (int k = 0; k < w->nA; ++k) if (fabs(lam[k]) > lmax) lmax = fabs(lam[k]);
                 double theta = INFINITY; int kout = -1;
+                double ymx = 0;
+                for (int k = 0; k < w->nA; ++k) if (fabs(w->y[w->widx[k]]) > ymx) ymx = fabs(w->y[w->widx[k]]);
+                rt_cand* cd2 = w->cand; int nc2 = 0;
                 for (int k = 0; k < w->nA; ++k) {
                     int c = w->widx[k];
                     if (w->lb_new[c] == w->ub_new[c]) continue;
@@ -736,14 +811,18 @@ int orc_qpsolve(orc_qpws* w, const double* H, const double* g, const double* A,
                     if (fabs(l) <= 1e-11 * (1.0 + lmax)) continue;
                     double yc = w->y[c];
                     if (w->st[c] < 0 && l > 0) {
-                        double th = (yc > 0 ? yc : 0) / l;
-                        if (th < theta) { theta = th; kout = k; }
+                        cd2[nc2].num = (yc > 0 ? yc : 0); cd2[nc2].den = l;
                     } else if (w->st[c] > 0 && l < 0) {
-                        double th = (yc < 0 ? yc : 0) / l;
-                        if (th < theta) { theta = th; kout = k; }
-                    }
+                        cd2[nc2].num = (yc < 0 ? -yc : 0); cd2[nc2].den = -l;
+                    } else continue;
+                    cd2[nc2].del = w->tie * w->ynoise; cd2[nc2].key = c; cd2[nc2].aux = k; ++nc2;
+                }
+                {
+                    const int sel = rt_select(cd2, nc2);
+                    if (sel >= 0) { theta = (cd2[sel].num <= cd2[sel].del) ? 0.0 : cd2[sel].num / cd2[sel].den; kout = cd2[sel].aux; }
                 }
                 if (kout < 0) { status = EEPACC_QP_INFEASIBLE; break; }
+                w->ynoise += theta * lmax;
                 for (int k = 0; k < w->nA; ++k) {
                     double l = (blk_side < 0) ? lam[k] : -lam[k];
                     w->y[w->widx[k]] -= theta * l;
