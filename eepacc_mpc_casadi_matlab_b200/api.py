@@ -110,6 +110,23 @@ def _ptr(a):
     return a.ctypes.data_as(_dp)
 
 
+def _check_buffer(a, device_index):
+    """The C-ABI takes raw double pointers: refuse anything that is not contiguous float64 (on the engine's GPU)."""
+    if a is None:
+        return
+    if _is_device(a):
+        import torch
+        if a.dtype != torch.float64:
+            raise EepaccError(f"device buffer has dtype {a.dtype}, the ABI computes in float64")
+        if not a.is_contiguous():
+            raise EepaccError("device buffer is not contiguous")
+        if device_index is not None and a.device.index is not None and a.device.index != device_index:
+            raise EepaccError(f"device buffer lives on cuda:{a.device.index}, the engine on cuda:{device_index}")
+    else:
+        if a.dtype != np.float64 or not a.flags["C_CONTIGUOUS"]:
+            raise EepaccError("host buffer must be C-contiguous float64")
+
+
 def _host(a, shape=None):
     if a is None or _is_device(a):
         return a
@@ -158,6 +175,8 @@ class Engine:
             raise EepaccError(f"eepacc_mem_setup failed ({rc}): {msg}")
         self.n = self.L.eepacc_qp_nvar(ctrl)
         self.m = self.L.eepacc_qp_ncon(ctrl, C.byref(params))
+        self.L.eepacc_mem_device.argtypes = [C.c_int]
+        self.device_index = int(self.L.eepacc_mem_device(self.mem))
 
     # ---- plumbing ----
     def _err(self):
@@ -179,6 +198,8 @@ class Engine:
         dev = any(_is_device(a) for a in list(args) + list(ress) if a is not None)
         if dev and any((a is not None and not _is_device(a)) for a in list(args) + list(ress)):
             raise EepaccError("mixing host and device buffers in one call is not supported")
+        for a in list(args) + list(ress):
+            _check_buffer(a, self.device_index)
         argv = (_dp * max(1, len(args)))(*[_ptr(a) for a in args])
         resv = (_dp * max(1, len(ress)))(*[_ptr(a) for a in ress])
         iw = (C.c_longlong * 2)(int(B), S.FLAG_DEVICE_PTR if dev else 0)
@@ -391,8 +412,13 @@ class Engine:
         self.L.eepacc_mem_debug_fetch.restype = C.c_longlong
         got = self.L.eepacc_mem_debug_fetch(self.mem, int(what), out.ctypes.data_as(_dp), C.c_longlong(out.size))
         if got < 0:
-            self._err()
+            raise EepaccError(f"eepacc_mem_debug_fetch({what}) failed ({got}): {self._err()}")
         return out[:got]
+
+    def working_set(self):
+        """int8 [B, m + n]: working set after the last solve (-1 lower, +1 upper, 0 inactive; rows, then the
+        implicit variable bounds) -- what the warm start of the next step begins from."""
+        return self.debug_fetch(10, self.B * (self.m + self.n)).reshape(self.B, self.m + self.n).astype(np.int8)
 
     def kpi_device_ptr(self):
         return self.L.eepacc_mem_kpi_device_ptr(self.mem)

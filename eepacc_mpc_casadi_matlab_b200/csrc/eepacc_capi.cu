@@ -102,6 +102,8 @@ struct Mem {
         }
         if (gfork) cudaEventDestroy(gfork);
         gfork = nullptr;
+        for (int e = 0; e < 2; ++e) { if (cyc_ev[e]) cudaEventDestroy(cyc_ev[e]); cyc_ev[e] = nullptr; }
+        n_lead = 0; kk = 0; t0 = 0.0; launches = 0; deferred_total = 0; cyc_grid = 0; cyc_per_sm = 0;
         ready = false;
     }
 };
@@ -175,14 +177,21 @@ int copy_out(Mem* M, int slot, double* dst, size_t count, bool dev)
     return 0;
 }
 
-struct CallCtx { Mem* M; long long B; bool dev; };
+// The entry points switch to the mem's device and put the caller's current device back when they return
+// (also on the error paths: the guard's destructor does it).
+struct DeviceGuard {
+    int prev = -1;
+    int enter(int dev) { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; return (int)cudaSetDevice(dev); }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+struct CallCtx { Mem* M; long long B; bool dev; DeviceGuard guard; };
 int begin_call(int mem, long long* iw, CallCtx& c)
 {
     Mem* M = get_mem(mem);
     if (!M) return EEPACC_ERR_ARG;
     if (!M->ready) return fail(EEPACC_ERR_ARG, "mem not set up (call eepacc_mem_setup)");
     if (!iw) return fail(EEPACC_ERR_ARG, "iw is NULL (iw[0] = batch, iw[1] = flags)");
-    CK(cudaSetDevice(M->device));
+    CK((cudaError_t)c.guard.enter(M->device));
     c.M = M; c.B = iw[0]; c.dev = (iw[1] & EEPACC_FLAG_DEVICE_PTR) != 0;
     if (c.B < 0) return fail(EEPACC_ERR_ARG, "negative batch");
     return 0;
@@ -426,7 +435,7 @@ static void release_impl(int mem)
 {
     std::lock_guard<std::mutex> lk(g_mu);
     if (mem < 0 || mem >= MAX_MEM || !g_mem[mem].used) return;
-    if (g_mem[mem].ready) cudaSetDevice(g_mem[mem].device);
+    DeviceGuard dg_; if (g_mem[mem].ready) dg_.enter(g_mem[mem].device);
     g_mem[mem].release_all();
     g_mem[mem].used = false;
 }
@@ -442,7 +451,7 @@ int eepacc_mem_setup(int mem, int ctrl, const eepacc_params* p, const eepacc_rou
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return fail(EEPACC_ERR_NO_DEVICE, "no CUDA device (there is no CPU fallback)");
     if (device < 0) { CK(cudaGetDevice(&device)); }
     if (device >= ndev) return fail(EEPACC_ERR_NO_DEVICE, "device index out of range");
-    CK(cudaSetDevice(device));
+    DeviceGuard dg_; CK((cudaError_t)dg_.enter(device));
     M->release_all();
     M->device = device; M->ctrl = ctrl; M->p = *p; M->B = B;
     M->n = nvar(ctrl); M->m = ncon(ctrl, p);
@@ -533,7 +542,7 @@ int eepacc_mem_reset(int mem)
 {
     Mem* M = get_mem(mem);
     if (!M || !M->ready) return fail(EEPACC_ERR_ARG, "mem not set up");
-    CK(cudaSetDevice(M->device));
+    DeviceGuard dg_; CK((cudaError_t)dg_.enter(M->device));
     return reset_state(M);
 }
 
@@ -550,7 +559,7 @@ int eepacc_mem_set_lead(int mem, const double* lead, long long n_steps)
     Mem* M = get_mem(mem);
     if (!M || !M->ready) return fail(EEPACC_ERR_ARG, "mem not set up");
     if (!lead || n_steps <= 0) return fail(EEPACC_ERR_ARG, "bad lead trace");
-    CK(cudaSetDevice(M->device));
+    DeviceGuard dg_; CK((cudaError_t)dg_.enter(M->device));
     size_t bytes = (size_t)n_steps * M->B * 2 * 8;
     if (M->lead.ensure(bytes)) return EEPACC_ERR_MEM;
     CK(cudaMemcpyAsync(M->lead.p, lead, bytes, cudaMemcpyHostToDevice, M->stream));
@@ -566,7 +575,7 @@ int eepacc_mem_synth_lead(int mem, const double* base, long long n_base, const d
     if (!M || !M->ready) return fail(EEPACC_ERR_ARG, "mem not set up");
     if (!base || n_base <= 0 || !pert || n_steps < 2 || (hw && n_hw <= 0))
         return fail(EEPACC_ERR_ARG, "bad lead synthesis arguments");
-    CK(cudaSetDevice(M->device));
+    DeviceGuard dg_; CK((cudaError_t)dg_.enter(M->device));
     const size_t B = (size_t)M->B;
     if (M->lead.ensure((size_t)n_steps * B * 2 * 8)) return EEPACC_ERR_MEM;
     const size_t nb = (size_t)n_base * 8, nh = hw ? (size_t)n_hw * 8 : 0, np_ = B * EEPACC_N_PERT * 8;
@@ -593,6 +602,12 @@ int eepacc_mem_set_stream(int mem, void* stream)
     return EEPACC_OK;
 }
 
+int eepacc_mem_device(int mem)
+{
+    Mem* M = get_mem(mem);
+    return M ? M->device : -1;
+}
+
 long long eepacc_mem_launch_count(int mem)
 {
     Mem* M = get_mem(mem);
@@ -603,7 +618,7 @@ int eepacc_mem_get_counters(int mem, double* out)
 {
     Mem* M = get_mem(mem);
     if (!M || !M->ready || !out) return fail(EEPACC_ERR_ARG, "bad arguments");
-    CK(cudaSetDevice(M->device));
+    DeviceGuard dg_; CK((cudaError_t)dg_.enter(M->device));
     std::vector<unsigned long long> h((size_t)M->B * 4);
     CK(cudaMemcpyAsync(h.data(), M->counters.p, h.size() * 8, cudaMemcpyDeviceToHost, M->stream));
     CK(cudaStreamSynchronize(M->stream));
@@ -627,7 +642,7 @@ int eepacc_mem_debug_phases(int mem, double* out)
 {
     Mem* M = get_mem(mem);
     if (!M || !M->ready || !M->dbg.p || !out) return fail(EEPACC_ERR_ARG, "tracing not enabled");
-    CK(cudaSetDevice(M->device));
+    DeviceGuard dg_; CK((cudaError_t)dg_.enter(M->device));
     CK(cudaMemcpy(out, (double*)M->dbg.p + 4096 * 4, 28 * 8, cudaMemcpyDeviceToHost));
     return EEPACC_OK;
 }
@@ -646,7 +661,7 @@ int eepacc_mem_get_timing(int mem, double* tot, double* step_ms, long long cap)
 {
     Mem* M = get_mem(mem);
     if (!M || !M->ready || !tot) return fail(EEPACC_ERR_ARG, "bad arguments");
-    CK(cudaSetDevice(M->device));
+    DeviceGuard dg_; CK((cudaError_t)dg_.enter(M->device));
     CK(cudaStreamSynchronize(M->stream));
     tot[0] = tot[1] = tot[2] = 0.0; tot[3] = (double)M->ev_steps;
     const long long sets = (long long)M->ev_steps * M->ev_groups;     // one set of events per (step, slice)
@@ -719,7 +734,7 @@ int eepacc_mem_debug_trace(int mem, double* out, int cap)
 {
     Mem* M = get_mem(mem);
     if (!M || !M->ready) return fail(EEPACC_ERR_ARG, "mem not set up");
-    CK(cudaSetDevice(M->device));
+    DeviceGuard dg_; CK((cudaError_t)dg_.enter(M->device));
     if (!M->dbg.p) {
         if (M->dbg.ensure((4096 * 4 + 32) * 8)) return EEPACC_ERR_MEM;
         CK(cudaMemset(M->dbg.p, 0, (4096 * 4 + 32) * 8));
@@ -740,7 +755,7 @@ long long eepacc_mem_debug_fetch(int mem, int what, double* out, long long cap)
 {
     Mem* M = get_mem(mem);
     if (!M || !M->ready || !out) { fail(EEPACC_ERR_ARG, "bad arguments"); return -1; }
-    if (cudaSetDevice(M->device) != cudaSuccess) return -1;
+    DeviceGuard dg_; if (dg_.enter(M->device) != 0) return -1;
     const long long B = M->B;
     const void* src = nullptr; long long cnt = 0;
     switch (what) {
@@ -754,6 +769,23 @@ long long eepacc_mem_debug_fetch(int mem, int what, double* out, long long cap)
     case 7: src = M->cost.p; cnt = B; break;
     case 9: src = M->lead.p; cnt = M->n_lead * B * 2; break;
     case 8: src = M->defer_cnt.p; cnt = 2; break;   // int[4]: vehicles deferred to the full-space kernel in the last step
+    case 10: {
+        // working set after the last solve, [B][m + n] as doubles: -1 held at its lower bound, +1 upper, 0 inactive
+        // (rows 0..m-1, then the implicit variable bounds) -- the layout of the oracle's orc_vehicle_get_ws
+        const long long mt = M->m + M->n, n = M->n;
+        if (cap < B * mt) { fail(EEPACC_ERR_ARG, "working-set fetch needs B*(m+n) doubles"); return -1; }
+        if (cudaStreamSynchronize(M->stream) != cudaSuccess) return -1;
+        std::vector<short> widx((size_t)(B * n)); std::vector<signed char> wside((size_t)(B * n));
+        if (cudaMemcpy(widx.data(), M->widx.p, (size_t)(B * n) * 2, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        if (cudaMemcpy(wside.data(), M->wside.p, (size_t)(B * n), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        for (long long i = 0; i < B * mt; ++i) out[i] = 0.0;
+        for (long long b = 0; b < B; ++b)
+            for (long long i = 0; i < n; ++i) {
+                const int c = widx[(size_t)(b * n + i)];
+                if (c >= 0 && c < mt) out[b * mt + c] = (double)wside[(size_t)(b * n + i)];
+            }
+        return B * mt;
+    }
     default: fail(EEPACC_ERR_ARG, "unknown buffer"); return -1;
     }
     if (cnt > cap) cnt = cap;
@@ -998,7 +1030,8 @@ int eepacc_run(const double** arg, double** res, long long* iw, double*, int mem
     if (!arg || !arg[0] || !res) return fail(EEPACC_ERR_ARG, "n_steps input is required (host scalar)");
     const long long n_steps = (long long)arg[0][0];
     if (n_steps <= 0) return fail(EEPACC_ERR_ARG, "n_steps must be positive");
-    if (M->ctrl != EEPACC_TV && M->n_lead < n_steps) return fail(EEPACC_ERR_ARG, "lead trace shorter than n_steps (eepacc_mem_set_lead)");
+    if (c.B != M->B) return fail(EEPACC_ERR_ARG, "iw[0] (batch) differs from the batch the mem was set up for");
+    if (M->ctrl != EEPACC_TV && (M->n_lead < n_steps || !M->lead.p)) return fail(EEPACC_ERR_ARG, "lead trace shorter than n_steps (eepacc_mem_set_lead)");
     const size_t B = (size_t)M->B;
     if ((rc = reset_state(M))) return rc;
     double* log_dev = nullptr;
@@ -1070,15 +1103,21 @@ int eepacc_run(const double** arg, double** res, long long* iw, double*, int mem
         CK(cudaEventRecord(M->gfork, M->stream));
         for (int g = 0; g < G; ++g) CK(cudaStreamWaitEvent(M->gstream[g], M->gfork, 0));
         double t0 = M->t0;
-        for (long long k = 0; k < n_steps; ++k) {
+        for (long long k = 0; k < n_steps && !rc; ++k) {
             const double* lead = (M->ctrl == EEPACC_TV) ? nullptr : M->lead.as<double>() + (size_t)k * B * 2;
             double* lg = log_dev ? log_dev + (size_t)k * B * EEPACC_LOG_W : nullptr;
-            for (int g = 0; g < G; ++g) {
+            for (int g = 0; g < G && !rc; ++g) {
                 const size_t v0 = B * (size_t)g / G, v1 = B * (size_t)(g + 1) / G;
                 cudaEvent_t* ev = M->timing ? &M->evs[((size_t)k * G + g) * 4] : nullptr;
-                if ((rc = device_step_slice(M, g, v0, (long long)(v1 - v0), M->gstream[g], (int)k, t0, lead, lg, ev))) return rc;
+                rc = device_step_slice(M, g, v0, (long long)(v1 - v0), M->gstream[g], (int)k, t0, lead, lg, ev);
             }
             t0 += M->p.Ts;
+        }
+        if (rc) {
+            // a launch failed with slices in flight on their own (non-blocking) streams: drain them before
+            // handing the failure back, so the caller may free or reuse its buffers
+            for (int g = 0; g < G; ++g) cudaStreamSynchronize(M->gstream[g]);
+            return rc;
         }
         for (int g = 0; g < G; ++g) {
             CK(cudaEventRecord(M->gjoin[g], M->gstream[g]));

@@ -27,12 +27,10 @@ extern "C" size_t eep_build_smem_bytes() { return sizeof(BuildSmem); }
 
 extern "C" int eep_launch_build(const eepacc_params* p, const eep_build_io* io, cudaStream_t st)
 {
-    static bool attr_set = false;
     size_t sm = sizeof(BuildSmem);
-    if (!attr_set) {
+    {   // per-device opt-in: set on every launch (cheap), never cached process-wide
         cudaError_t e = cudaFuncSetAttribute(k2_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         if (e != cudaSuccess) return (int)e;
-        attr_set = true;
     }
     long long g = io->B;
     const long long cap = 148LL * 8;

@@ -213,8 +213,7 @@ __device__ void k2_vehicle(const eepacc_params& p, const eep_build_io& io, const
     }
     __syncthreads();
     // ---------- per-stage bounds (EstimateRouteAndComfortBounds) ----------
-    if (tid < N) {
-        const int k = tid;
+    for (int k = tid; k < N; k += NTB) {        // one stage per thread (a serial loop in the host emulation)
         int mpctype = ctrl == EEPACC_BL ? 1 : ctrl == EEPACC_TV ? 2 : 0;
         double ve = (ctrl == EEPACC_TV) ? 0.0 : S.v_est[k];         // CreateQP_TV.m:44
         eep_bounds_stage(p, r, mpctype, k, S.s_est[k], ve, S.t0, S.bnd[k]);
@@ -263,8 +262,7 @@ __device__ void k2_vehicle(const eepacc_params& p, const eep_build_io& io, const
     }
     __syncthreads();
     // ---------- sensitivities PS/PV (TransformToDenseFormulation.m:46-52) ----------
-    if (tid < N) {
-        const int i = tid;
+    for (int i = tid; i < N; i += NTB) {
         double M0 = (ctrl == EEPACC_FB) ? 0.0 : .5 * T * T;           // B_i (RunOpt_FBMPC.m:89 / RunOpt_ABMPC.m:78-79)
         double M1 = (ctrl == EEPACC_FB) ? T / p.lambda / mass : T;
         for (int k = 0; k <= N; ++k) {
@@ -283,8 +281,7 @@ __device__ void k2_vehicle(const eepacc_params& p, const eep_build_io& io, const
     if (tid == 0) S.cs_vN = (ctrl == EEPACC_BL || ctrl == EEPACC_TV) ? -((ctrl == EEPACC_TV) ? p.W_TV[0] : p.W_BL[0]) : 0.0;
     __syncthreads();
     // ---------- t(v_k) and MV[k][j] = (Hs Psi)(v_k, j) ----------
-    if (tid <= N) {
-        const int k = tid;
+    for (int k = tid; k <= N; k += NTB) {
         double t = 0.0;
         if (k < N) {
             t = S.Dk[k][0] * S.dv[k] + S.cs[k][0];
@@ -362,7 +359,7 @@ __device__ void k2_vehicle(const eepacc_params& p, const eep_build_io& io, const
             const int k = e / (W * W), q = e % (W * W);
             hm = fmax(hm, fmax(fabs(S.Dk[k][q]), fabs(S.Ck[k][q])));
         }
-        __shared__ double red_hd[NTB / 32], red_hm[NTB / 32];
+        __shared__ double red_hd[NTB / 32 > 0 ? NTB / 32 : 1], red_hm[NTB / 32 > 0 ? NTB / 32 : 1];
         for (int o = 16; o > 0; o >>= 1) { hd = fmax(hd, __shfl_xor_sync(0xffffffffu, hd, o)); hm = fmax(hm, __shfl_xor_sync(0xffffffffu, hm, o)); }
         if ((tid & 31) == 0) { red_hd[tid >> 5] = hd; red_hm[tid >> 5] = hm; }
         __syncthreads();

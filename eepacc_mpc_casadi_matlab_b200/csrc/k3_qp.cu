@@ -43,6 +43,7 @@ struct Ctx {
     // global
     const double *H, *g, *A, *lba, *uba, *lbx, *ubx;
     double reg, hscale;
+    double tie, ynoise;     // ratio-test tie tolerance (0 for the LPs), round-off scale of the multipliers (qp_rules.cuh)
     // shared
     double *Q, *M, *sub;
     double *x, *gcur, *dx, *dg, *t1, *t2, *t3, *t4, *yW, *dyW, *dbw, *wv, *csA, *snA;
@@ -115,6 +116,8 @@ __device__ __forceinline__ void block_argmin(Ctx& C, double& t, int& key)
         if (t2 < t || (t2 == t && k2 < key)) { t = t2; key = k2; }
     }
 }
+
+#include "qp_rules.cuh"
 
 struct VestSrc { const double* v_est; };
 
@@ -567,6 +570,9 @@ __device__ void reanchor(Ctx& C, bool recompute_y)
         __syncthreads();
         Qtmul(C, C.t2, C.t3, nZ, n);
         tsolve(C, nZ, n, C.t3, C.yW);
+        double ym = C.ynoise;
+        for (int r = nZ + threadIdx.x; r < n; r += NT) ym = fmax(ym, fabs(C.yW[r]));
+        C.ynoise = block_max(C, ym);
     }
     for (int r = nZ + threadIdx.x; r < n; r += NT) {
         int c = C.widx[r];
@@ -631,33 +637,56 @@ __device__ int resolve_pending(Ctx& C, int c_out, int side_out, unsigned long lo
             if (side_out > 0) sgn = -sgn;
         } else {
             Hmul(C, C.x, hz);
-            for (int i = threadIdx.x; i < n; i += NT) sgn -= (hz[i] + C.gcur[i]) * d[i];
-            sgn = block_sum(C, sgn);
-        }
-        if (sgn < 0) { for (int i = threadIdx.x; i < n; i += NT) d[i] = -d[i]; __syncthreads(); }
-        Amul(C, d, C.Adx);
-        double dn = 0;
-        for (int i = threadIdx.x; i < n; i += NT) dn += d[i] * d[i];
-        dn = sqrt(block_sum(C, dn));
-        double tmin = INFINITY; int key = 0x7fffffff;
-        for (int cc = threadIdx.x; cc < mt; cc += NT) {
-            if (C.st[cc] != 0 || C.anorm[cc] == 0.0f) continue;
-            double adx = C.Adx[cc];
-            const double rz = EPS_ROW * C.anorm[cc] * dn;
-            if (adx < -rz && !isinf(C.lbc[cc])) {
-                double sl = C.Ax[cc] - C.lbc[cc]; if (sl < 0) sl = 0;
-                double t = sl / (-adx);
-                int k = 2 * cc;
-                if (t < tmin || (t == tmin && k < key)) { tmin = t; key = k; }
-            } else if (adx > rz && !isinf(C.ubc[cc])) {
-                double sl = C.ubc[cc] - C.Ax[cc]; if (sl < 0) sl = 0;
-                double t = sl / adx;
-                int k = 2 * cc + 1;
-                if (t < tmin || (t == tmin && k < key)) { tmin = t; key = k; }
+            double gn = 0, dn2 = 0;
+            for (int i = threadIdx.x; i < n; i += NT) { const double gi = hz[i] + C.gcur[i]; sgn -= gi * d[i]; gn += gi * gi; dn2 += d[i] * d[i]; }
+            sgn = block_sum(C, sgn); gn = block_sum(C, gn); dn2 = block_sum(C, dn2);
+            if (fabs(sgn) <= FLAT_TOL * sqrt(gn) * sqrt(dn2)) {
+                // flat direction (gradient orthogonal to d within round-off): canonical sense, see qp_oracle.c
+                get_row(C, c_out, C.t2);
+                double an = 0;
+                sgn = 0;
+                for (int i = threadIdx.x; i < n; i += NT) { sgn += C.t2[i] * d[i]; an += C.t2[i] * C.t2[i]; }
+                sgn = block_sum(C, sgn); an = block_sum(C, an);
+                if (side_out > 0) sgn = -sgn;
+                if (fabs(sgn) <= FLAT_TOL * sqrt(an) * sqrt(dn2)) {
+                    double dmx = 0;
+                    for (int i = threadIdx.x; i < n; i += NT) dmx = fmax(dmx, fabs(d[i]));
+                    dmx = block_max(C, dmx);
+                    int i0 = RT_NONE;
+                    for (int i = threadIdx.x; i < n; i += NT) if (fabs(d[i]) > 0.25 * dmx) i0 = min(i0, i);
+                    i0 = block_imin(C, i0);
+                    sgn = (i0 == RT_NONE) ? 1.0 : d[i0];
+                }
             }
         }
-        block_argmin(C, tmin, key);
-        if (key == 0x7fffffff) return EEPACC_QP_UNBOUNDED;
+        if (sgn < 0) { __syncthreads(); for (int i = threadIdx.x; i < n; i += NT) d[i] = -d[i]; __syncthreads(); }
+        Amul(C, d, C.Adx);
+        double dn = 0, xmax = 0;
+        for (int i = threadIdx.x; i < n; i += NT) { dn += d[i] * d[i]; xmax = fmax(xmax, fabs(C.x[i])); }
+        dn = sqrt(block_sum(C, dn));
+        xmax = block_max(C, xmax);
+        const double pdel = C.tie * (1.0 + xmax);
+        double tmax = INFINITY;
+        for (int cc = threadIdx.x; cc < mt; cc += NT) {
+            if (C.st[cc] != 0 || C.anorm[cc] == 0.0f) continue;
+            int sd; double num, den;
+            if (rt_exch(C, cc, dn, sd, num, den)) tmax = fmin(tmax, (num + pdel * C.anorm[cc]) / den);
+        }
+        tmax = block_min(C, tmax);
+        if (!(tmax < INFINITY)) return EEPACC_QP_UNBOUNDED;
+        int key = RT_NONE;
+        for (int cc = threadIdx.x; cc < mt; cc += NT) {
+            if (C.st[cc] != 0 || C.anorm[cc] == 0.0f) continue;
+            int sd; double num, den;
+            if (rt_exch(C, cc, dn, sd, num, den) && num / den <= tmax) key = min(key, 2 * cc + sd);
+        }
+        key = block_imin(C, key);
+        double tmin;
+        {
+            int sd; double num, den;
+            rt_exch(C, key >> 1, dn, sd, num, den);
+            tmin = (num <= pdel * C.anorm[key >> 1]) ? 0.0 : num / den;
+        }
         const int j = key >> 1, jside = (key & 1) ? 1 : -1;
         for (int i = threadIdx.x; i < n; i += NT) C.x[i] += tmin * d[i];
         for (int cc = threadIdx.x; cc < mt; cc += NT) C.Ax[cc] += tmin * C.Adx[cc];
@@ -965,6 +994,7 @@ __global__ void __launch_bounds__(NT, 1) k3_qp_kernel(const __grid_constant__ ee
             for (int e = threadIdx.x; e < EEP_N; e += NT) C.vest[e] = sb[EEP_SB_VEST + e];
             C.reg = (sb[EEP_SB_HMAX] == 0.0) ? LP_REG : 0.0;
             C.hscale = fmax(sb[EEP_SB_HSCALE], LP_REG);
+            C.tie = (C.reg != 0.0) ? 0.0 : TIE_TOL;
             C.mass = sb[EEP_SB_MASS];
             __syncthreads();
             for (int r = threadIdx.x; r < m; r += NT) {
@@ -985,6 +1015,7 @@ __global__ void __launch_bounds__(NT, 1) k3_qp_kernel(const __grid_constant__ ee
             hm = block_max(C, hm);
             C.reg = (hm == 0.0) ? LP_REG : 0.0;
             C.hscale = fmax(hd, LP_REG);
+            C.tie = (C.reg != 0.0) ? 0.0 : TIE_TOL;
             for (int r = threadIdx.x; r < m; r += NT) {
                 double sa = 0;
                 for (int j = 0; j < n; ++j) sa += fabs(C.A[r + (size_t)j * m]);
@@ -1009,6 +1040,11 @@ __global__ void __launch_bounds__(NT, 1) k3_qp_kernel(const __grid_constant__ ee
         }
         if (need_cold) cold_ws(C);
         setup_aux(C);
+        {
+            double ym = 1.0;
+            for (int r = n - C.nA + threadIdx.x; r < n; r += NT) ym = fmax(ym, fabs(C.yW[r]));
+            C.ynoise = block_max(C, ym);
+        }
         PHASE(3);
 
         // ---------------- homotopy ----------------
@@ -1030,62 +1066,61 @@ __global__ void __launch_bounds__(NT, 1) k3_qp_kernel(const __grid_constant__ ee
             Amul(C, C.dx, C.Adx);
             RPH(0);
 
-            double dxmax = 0;
-            for (int i = threadIdx.x; i < n; i += NT) dxmax = fmax(dxmax, fabs(C.dx[i]));
-            dxmax = block_max(C, dxmax);
-            double tau = 1.0; int key = 0x7fffffff;
-            for (int c = threadIdx.x; c < mt; c += NT) {
-                if (C.st[c] != 0 || C.anorm[c] == 0.0f) continue;      // all-zero rows can never be added
-                if (C.tabu[c] == 2) continue;                          // left during this run of zero steps: no re-entry
-                double adx = C.Adx[c];
-                const double rz = EPS_ROW * C.anorm[c] * dxmax;
-                if (!isinf(C.lbc[c])) {
-                    double ln = lb_new(C, c);
-                    double dlb = isinf(ln) ? 0.0 : ln - C.lbc[c];
-                    double rate = adx - dlb;
-                    double sl = C.Ax[c] - C.lbc[c]; if (sl < 0) sl = 0;
-                    if (rate < -(EPS_RATE * (1.0 + fabs(adx) + fabs(dlb)) + rz) &&
-                        -rate - sl > FEAS_TOL * (1.0 + fabs(ln))) {
-                        double t = sl / (-rate);
-                        int k = 2 * c;
-                        if (t < tau || (t == tau && k < key && t < 1.0)) { tau = t; key = k; }
-                    }
-                }
-                if (!isinf(C.ubc[c])) {
-                    double un = ub_new(C, c);
-                    double dub = isinf(un) ? 0.0 : un - C.ubc[c];
-                    double rate = dub - adx;
-                    double sl = C.ubc[c] - C.Ax[c]; if (sl < 0) sl = 0;
-                    if (rate < -(EPS_RATE * (1.0 + fabs(adx) + fabs(dub)) + rz) &&
-                        -rate - sl > FEAS_TOL * (1.0 + fabs(un))) {
-                        double t = sl / (-rate);
-                        int k = 2 * c + 1;
-                        if (t < tau || (t == tau && k < key && t < 1.0)) { tau = t; key = k; }
-                    }
-                }
-            }
+            // ---- ratio tests, two-pass (qp_rules.cuh; oracle/qp_oracle.c:rt_select) ----
+            double dxmax = 0, xmax = 0;
+            for (int i = threadIdx.x; i < n; i += NT) { dxmax = fmax(dxmax, fabs(C.dx[i])); xmax = fmax(xmax, fabs(C.x[i])); }
+            block_max2(C, dxmax, xmax);
             double dys = 0;
             for (int r = nZ + threadIdx.x; r < n; r += NT) dys = fmax(dys, fabs(C.dyW[r]));
             dys = block_max(C, dys);
             const double thr = EPS_RATE * (1.0 + dys);
+            const double pdel = C.tie * (1.0 + xmax), ddel = C.tie * C.ynoise;
+            double tmax = INFINITY;
+            for (int c = threadIdx.x; c < mt; c += NT) {
+                if (C.st[c] != 0 || C.anorm[c] == 0.0f) continue;      // all-zero rows can never be added
+                if (C.tabu[c] == 2) continue;                          // left during this run of zero steps: no re-entry
+                double num, den;
+                if (rt_primal(C, c, 0, dxmax, num, den)) tmax = fmin(tmax, (num + pdel * C.anorm[c]) / den);
+                if (rt_primal(C, c, 1, dxmax, num, den)) tmax = fmin(tmax, (num + pdel * C.anorm[c]) / den);
+            }
             for (int r = nZ + threadIdx.x; r < n; r += NT) {
-                int c = C.widx[r];
+                const int c = C.widx[r];
                 if (lb_new(C, c) == ub_new(C, c)) continue;
                 if (C.tabu[c] == 1) continue;            // entered during this run of zero steps: stays
-                double yc = C.yW[r], dy = C.dyW[r];
-                int k = 2 * mt + (n - 1 - r);
-                if (C.st[c] < 0 && dy < -thr) {
-                    double t = (yc > 0 ? yc : 0) / (-dy);
-                    if (t < tau || (t == tau && k < key && t < 1.0)) { tau = t; key = k; }
-                } else if (C.st[c] > 0 && dy > thr) {
-                    double t = (yc < 0 ? -yc : 0) / dy;
-                    if (t < tau || (t == tau && k < key && t < 1.0)) { tau = t; key = k; }
-                }
+                double num, den;
+                if (rt_dual(C.st[c], C.yW[r], C.dyW[r], thr, ddel, num, den)) tmax = fmin(tmax, (num + ddel) / den);
             }
-            block_argmin(C, tau, key);
+            tmax = block_min(C, tmax);
+            // pass 2: lowest key among the candidates within tmax; packed = key * 128 + Q column of a dual candidate
+            int pk = RT_NONE;
+            if (tmax < INFINITY) {
+                for (int c = threadIdx.x; c < mt; c += NT) {
+                    if (C.st[c] != 0 || C.anorm[c] == 0.0f) continue;
+                    if (C.tabu[c] == 2) continue;
+                    double num, den;
+                    if (rt_primal(C, c, 0, dxmax, num, den) && num / den <= tmax) pk = min(pk, (2 * c) * 128);
+                    if (rt_primal(C, c, 1, dxmax, num, den) && num / den <= tmax) pk = min(pk, (2 * c + 1) * 128);
+                }
+                for (int r = nZ + threadIdx.x; r < n; r += NT) {
+                    const int c = C.widx[r];
+                    if (lb_new(C, c) == ub_new(C, c)) continue;
+                    if (C.tabu[c] == 1) continue;
+                    double num, den;
+                    if (rt_dual(C.st[c], C.yW[r], C.dyW[r], thr, ddel, num, den) && num / den <= tmax) pk = min(pk, (2 * mt + c) * 128 + r);
+                }
+                pk = block_imin(C, pk);
+            }
             RPH(1);
-            const bool full = !(tau < 1.0) || key == 0x7fffffff;
-            if (full) tau = 1.0;
+            const bool full = (pk == RT_NONE);
+            double tau = 1.0;
+            const int key = full ? RT_NONE : pk >> 7, rsel = pk & 127;
+            if (!full) {
+                double num = 0, den = 1, del;
+                if (key < 2 * mt) { rt_primal(C, key >> 1, key & 1, dxmax, num, den); del = pdel * C.anorm[key >> 1]; }
+                else { rt_dual(C.st[C.widx[rsel]], C.yW[rsel], C.dyW[rsel], thr, ddel, num, den); del = ddel; }
+                tau = (num <= del) ? 0.0 : num / den;       // within round-off of zero: a zero step
+            }
+            C.ynoise += tau * dys;
             // anti-cycling (see oracle/qp_oracle.c): constraints that enter while the homotopy makes no
             // progress may not leave through the dual test until it does
             const bool zero_step = !(tau > 1e-14);
@@ -1141,23 +1176,39 @@ __global__ void __launch_bounds__(NT, 1) k3_qp_kernel(const __grid_constant__ ee
                     double lmax = 0;
                     for (int r = nZc + threadIdx.x; r < n; r += NT) lmax = fmax(lmax, fabs(C.t2[r]));
                     lmax = block_max(C, lmax);
-                    double theta = INFINITY; int kk = 0x7fffffff;
+                    // dual ratio test of the exchange, two-pass; keyed by constraint index, packed with the Q column
+                    const double tdel = C.tie * C.ynoise;
+                    double thmax = INFINITY;
                     for (int r = nZc + threadIdx.x; r < n; r += NT) {
-                        int c = C.widx[r];
+                        const int c = C.widx[r];
                         if (lb_new(C, c) == ub_new(C, c)) continue;
-                        double l = (side < 0) ? C.t2[r] : -C.t2[r];
+                        const double l = (side < 0) ? C.t2[r] : -C.t2[r];
                         if (fabs(l) <= 1e-11 * (1.0 + lmax)) continue;
-                        double yc = C.yW[r];
-                        int pos = n - 1 - r;
-                        if (C.st[c] < 0 && l > 0) {
-                            double th = (yc > 0 ? yc : 0) / l;
-                            if (th < theta || (th == theta && pos < kk)) { theta = th; kk = pos; }
-                        } else if (C.st[c] > 0 && l < 0) {
-                            double th = (yc < 0 ? yc : 0) / l;
-                            if (th < theta || (th == theta && pos < kk)) { theta = th; kk = pos; }
-                        }
+                        const double yc = C.yW[r];
+                        if (C.st[c] < 0 && l > 0) thmax = fmin(thmax, ((yc > 0 ? yc : 0) + tdel) / l);
+                        else if (C.st[c] > 0 && l < 0) thmax = fmin(thmax, ((yc < 0 ? -yc : 0) + tdel) / -l);
                     }
-                    block_argmin(C, theta, kk);
+                    thmax = block_min(C, thmax);
+                    int pk2 = RT_NONE;
+                    for (int r = nZc + threadIdx.x; r < n; r += NT) {
+                        const int c = C.widx[r];
+                        if (lb_new(C, c) == ub_new(C, c)) continue;
+                        const double l = (side < 0) ? C.t2[r] : -C.t2[r];
+                        if (fabs(l) <= 1e-11 * (1.0 + lmax)) continue;
+                        const double yc = C.yW[r];
+                        if (C.st[c] < 0 && l > 0) { if ((yc > 0 ? yc : 0) / l <= thmax) pk2 = min(pk2, c * 128 + r); }
+                        else if (C.st[c] > 0 && l < 0) { if ((yc < 0 ? -yc : 0) / -l <= thmax) pk2 = min(pk2, c * 128 + r); }
+                    }
+                    pk2 = block_imin(C, pk2);
+                    int kk = RT_NONE; double theta = INFINITY;
+                    if (pk2 != RT_NONE) {
+                        const int r = pk2 & 127;
+                        kk = n - 1 - r;
+                        const double yc = C.yW[r], l = (side < 0) ? C.t2[r] : -C.t2[r];
+                        const double num = (l > 0) ? (yc > 0 ? yc : 0) : (yc < 0 ? -yc : 0), den = fabs(l);
+                        theta = (num <= tdel) ? 0.0 : num / den;
+                        C.ynoise += theta * lmax;
+                    }
                     if (kk == 0x7fffffff) { status = EEPACC_QP_INFEASIBLE; break; }
                     for (int r = nZc + threadIdx.x; r < n; r += NT) {
                         double l = (side < 0) ? C.t2[r] : -C.t2[r];
@@ -1180,8 +1231,7 @@ __global__ void __launch_bounds__(NT, 1) k3_qp_kernel(const __grid_constant__ ee
                 }
             } else {
                 // ---------- dual blocking: remove constraint ----------
-                const int pos = key - 2 * mt;
-                const int rp = n - 1 - pos;
+                const int rp = rsel;
                 const int c = C.widx[rp];
                 const int side = C.st[c];
                 __syncthreads();
@@ -1293,11 +1343,10 @@ extern "C" size_t eep_qp_smem_bytes(int n, int m, int smode)
 extern "C" int eep_launch_qp(const eepacc_params* p, const eep_qp_io* io, cudaStream_t st)
 {
     size_t sm = eep_qp_smem_bytes(io->n, io->m, io->sblk != nullptr);
-    static size_t attr_for = 0;
-    if (sm > attr_for) {
+    // the opt-in is per device: set it on every launch (cheap) rather than caching it in a process-wide static
+    {
         cudaError_t e = cudaFuncSetAttribute(k3_qp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         if (e != cudaSuccess) return (int)e;
-        attr_for = sm;
     }
     long long g = io->B;               // one CTA per vehicle: the hardware scheduler balances uneven solves
     if (io->todo_list && g > (io->todo_grid > 0 ? io->todo_grid : 148)) g = (io->todo_grid > 0 ? io->todo_grid : 148);      // fallback mode: a few persistent CTAs walk the (short) hand-over list

@@ -78,6 +78,7 @@ struct CtxT {
     int n, m, mt, fc, ldq;
     int nF, nX, nZ;             // free variables, fixed variables (nF + nX = n), null-space columns
     double reg, hscale;
+    double tie, ynoise;         // ratio-test tie tolerance (0 for the LPs) and round-off scale of the multipliers (qp_rules.cuh)
     const double* g;                           // shared copy of the gradient [n]
     double* gw;                                // the same, writable (filled per vehicle)
     const double *lba, *uba;                   // GLOBAL: this vehicle's new row bounds [m] (far bounds for rows >= m are constants)
@@ -194,6 +195,10 @@ __device__ __forceinline__ double group_sum(double v)
 #endif
 
 struct VestSrc { const double* v_est; };
+
+}  // namespace k3r
+#include "qp_rules.cuh"
+namespace k3r {
 
 // ---- matrix-free operators: H = Psi' Hs Psi and A = Gs Psi are never formed ----
 template <class CT> K3R_FN __device__ void s_prep(CT& C, const double* v)
@@ -840,6 +845,10 @@ template <class CT> K3R_FN __device__ void reanchor(CT& C, bool recompute_y)
             K3R_LOOP for (int k = threadIdx.x; k < nX; k += NT) { const int j = C.xvar[k]; C.yX[k] = (C.t2[j] - C.t3[j]) / C.xcv[k]; }
             __syncthreads();
         }
+        double ym = C.ynoise;
+        K3R_LOOP for (int r = nZ + threadIdx.x; r < nF; r += NT) ym = fmax(ym, fabs(C.yW[r]));
+        K3R_LOOP for (int k = threadIdx.x; k < nX; k += NT) ym = fmax(ym, fabs(C.yX[k]));
+        C.ynoise = block_max(C, ym);
     }
     K3R_LOOP for (int r = nZ + threadIdx.x; r < nF; r += NT) {
         int c = C.widx[r];
@@ -924,33 +933,56 @@ template <class CT> K3R_FN __device__ int resolve_pending(CT& C, int c_out, int 
             if (side_out > 0) sgn = -sgn;
         } else {
             Hmul(C, C.x, hz);
-            K3R_LOOP for (int i = threadIdx.x; i < n; i += NT) sgn -= (hz[i] + C.gcur[i]) * d[i];
-            sgn = block_sum(C, sgn);
+            double gn = 0, dn2 = 0;
+            K3R_LOOP for (int i = threadIdx.x; i < n; i += NT) { const double gi = hz[i] + C.gcur[i]; sgn -= gi * d[i]; gn += gi * gi; dn2 += d[i] * d[i]; }
+            sgn = block_sum(C, sgn); gn = block_sum(C, gn); dn2 = block_sum(C, dn2);
+            if (fabs(sgn) <= FLAT_TOL * sqrt(gn) * sqrt(dn2)) {
+                // flat direction (gradient orthogonal to d within round-off): canonical sense, see qp_oracle.c
+                get_row(C, c_out, C.t2);
+                double an = 0;
+                sgn = 0;
+                K3R_LOOP for (int i = threadIdx.x; i < n; i += NT) { sgn += C.t2[i] * d[i]; an += C.t2[i] * C.t2[i]; }
+                sgn = block_sum(C, sgn); an = block_sum(C, an);
+                if (side_out > 0) sgn = -sgn;
+                if (fabs(sgn) <= FLAT_TOL * sqrt(an) * sqrt(dn2)) {
+                    double dmx = 0;
+                    K3R_LOOP for (int i = threadIdx.x; i < n; i += NT) dmx = fmax(dmx, fabs(d[i]));
+                    dmx = block_max(C, dmx);
+                    int i0 = RT_NONE;
+                    K3R_LOOP for (int i = threadIdx.x; i < n; i += NT) if (fabs(d[i]) > 0.25 * dmx) i0 = min(i0, i);
+                    i0 = block_imin(C, i0);
+                    sgn = (i0 == RT_NONE) ? 1.0 : d[i0];
+                }
+            }
         }
         if (sgn < 0) { __syncthreads(); for (int i = threadIdx.x; i < n; i += NT) d[i] = -d[i]; __syncthreads(); }
         Amul(C, d, C.Adx);
-        double dn = 0;
-        K3R_LOOP for (int i = threadIdx.x; i < n; i += NT) dn += d[i] * d[i];
+        double dn = 0, xmax = 0;
+        K3R_LOOP for (int i = threadIdx.x; i < n; i += NT) { dn += d[i] * d[i]; xmax = fmax(xmax, fabs(C.x[i])); }
         dn = sqrt(block_sum(C, dn));
-        double tmin = INFINITY; int key = 0x7fffffff;
+        xmax = block_max(C, xmax);
+        const double pdel = C.tie * (1.0 + xmax);
+        double tmax = INFINITY;
         K3R_LOOP for (int cc = threadIdx.x; cc < mt; cc += NT) {
             if (C.st[cc] != 0 || C.anorm[cc] == 0.0f) continue;
-            double adx = C.Adx[cc];
-            const double rz = EPS_ROW * C.anorm[cc] * dn;
-            if (adx < -rz && !isinf(C.lbc[cc])) {
-                double sl = C.Ax[cc] - C.lbc[cc]; if (sl < 0) sl = 0;
-                double t = sl / (-adx);
-                int k = 2 * cc;
-                if (t < tmin || (t == tmin && k < key)) { tmin = t; key = k; }
-            } else if (adx > rz && !isinf(C.ubc[cc])) {
-                double sl = C.ubc[cc] - C.Ax[cc]; if (sl < 0) sl = 0;
-                double t = sl / adx;
-                int k = 2 * cc + 1;
-                if (t < tmin || (t == tmin && k < key)) { tmin = t; key = k; }
-            }
+            int sd; double num, den;
+            if (rt_exch(C, cc, dn, sd, num, den)) tmax = fmin(tmax, (num + pdel * C.anorm[cc]) / den);
         }
-        block_argmin(C, tmin, key);
-        if (key == 0x7fffffff) return EEPACC_QP_UNBOUNDED;
+        tmax = block_min(C, tmax);
+        if (!(tmax < INFINITY)) return EEPACC_QP_UNBOUNDED;
+        int key = RT_NONE;
+        K3R_LOOP for (int cc = threadIdx.x; cc < mt; cc += NT) {
+            if (C.st[cc] != 0 || C.anorm[cc] == 0.0f) continue;
+            int sd; double num, den;
+            if (rt_exch(C, cc, dn, sd, num, den) && num / den <= tmax) key = min(key, 2 * cc + sd);
+        }
+        key = block_imin(C, key);
+        double tmin;
+        {
+            int sd; double num, den;
+            rt_exch(C, key >> 1, dn, sd, num, den);
+            tmin = (num <= pdel * C.anorm[key >> 1]) ? 0.0 : num / den;
+        }
         const int j = key >> 1, jside = (key & 1) ? 1 : -1;
         K3R_LOOP for (int i = threadIdx.x; i < n; i += NT) C.x[i] += tmin * d[i];
         K3R_LOOP for (int cc = threadIdx.x; cc < mt; cc += NT) C.Ax[cc] += tmin * C.Adx[cc];
@@ -1365,6 +1397,7 @@ K3R_FN __device__ int k3r_vehicle(CT& C, const eep_qp_io& io, const long long ve
         K3R_LOOP for (int e = threadIdx.x; e < EEP_N; e += NT) C.vest[e] = sb[EEP_SB_VEST + e];
         C.reg = (sb[EEP_SB_HMAX] == 0.0) ? LP_REG : 0.0;
         C.hscale = fmax(sb[EEP_SB_HSCALE], LP_REG);
+        C.tie = (C.reg != 0.0) ? 0.0 : TIE_TOL;
         __syncthreads();
         K3R_LOOP for (int r = threadIdx.x; r < m; r += NT) {
             const RowW rd = row_load(C, r);
@@ -1402,6 +1435,10 @@ K3R_FN __device__ int k3r_vehicle(CT& C, const eep_qp_io& io, const long long ve
     if (status == EEPACC_QP_OK) {
         if (need_cold) cold_ws(C);
         setup_aux(C);
+        double ym = 1.0;
+        K3R_LOOP for (int r = C.nZ + threadIdx.x; r < C.nF; r += NT) ym = fmax(ym, fabs(C.yW[r]));
+        K3R_LOOP for (int k = threadIdx.x; k < C.nX; k += NT) ym = fmax(ym, fabs(C.yX[k]));
+        C.ynoise = block_max(C, ym);
     }
     PH(6);
 
@@ -1427,65 +1464,71 @@ K3R_FN __device__ int k3r_vehicle(CT& C, const eep_qp_io& io, const long long ve
         Amul(C, C.dx, C.Adx);
         PH(13);
 
-        double dxmax = 0;
-        K3R_LOOP for (int i = threadIdx.x; i < n; i += NT) dxmax = fmax(dxmax, fabs(C.dx[i]));
-        dxmax = block_max(C, dxmax);
-        double tau = 1.0; int key = 0x7fffffff;
-        K3R_LOOP for (int c = threadIdx.x; c < mt; c += NT) {
-            if (C.st[c] != 0 || C.anorm[c] == 0.0f) continue;      // all-zero rows can never be added
-            if (C.tabu[c] == 2) continue;                          // left during this run of zero steps: no re-entry
-            double adx = C.Adx[c];
-            const double rz = EPS_ROW * C.anorm[c] * dxmax;
-            if (!isinf(C.lbc[c])) {
-                double ln = lb_new(C, c);
-                double dlb = isinf(ln) ? 0.0 : ln - C.lbc[c];
-                double rate = adx - dlb;
-                double sl = C.Ax[c] - C.lbc[c]; if (sl < 0) sl = 0;
-                if (rate < -(EPS_RATE * (1.0 + fabs(adx) + fabs(dlb)) + rz) &&
-                    -rate - sl > FEAS_TOL * (1.0 + fabs(ln))) {
-                    double t = sl / (-rate);
-                    int k = 2 * c;
-                    if (t < tau || (t == tau && k < key && t < 1.0)) { tau = t; key = k; }
-                }
-            }
-            if (!isinf(C.ubc[c])) {
-                double un = ub_new(C, c);
-                double dub = isinf(un) ? 0.0 : un - C.ubc[c];
-                double rate = dub - adx;
-                double sl = C.ubc[c] - C.Ax[c]; if (sl < 0) sl = 0;
-                if (rate < -(EPS_RATE * (1.0 + fabs(adx) + fabs(dub)) + rz) &&
-                    -rate - sl > FEAS_TOL * (1.0 + fabs(un))) {
-                    double t = sl / (-rate);
-                    int k = 2 * c + 1;
-                    if (t < tau || (t == tau && k < key && t < 1.0)) { tau = t; key = k; }
-                }
-            }
-        }
+        // ---- ratio tests, two-pass (qp_rules.cuh; oracle/qp_oracle.c:rt_select) ----
+        double dxmax = 0, xmax = 0;
+        K3R_LOOP for (int i = threadIdx.x; i < n; i += NT) { dxmax = fmax(dxmax, fabs(C.dx[i])); xmax = fmax(xmax, fabs(C.x[i])); }
+        block_max2(C, dxmax, xmax);
         double dys = 0;
         K3R_LOOP for (int r = nZ + threadIdx.x; r < nF; r += NT) dys = fmax(dys, fabs(C.dyW[r]));
         K3R_LOOP for (int k = threadIdx.x; k < nX; k += NT) dys = fmax(dys, fabs(C.dyX[k]));
         dys = block_max(C, dys);
         const double thr = EPS_RATE * (1.0 + dys);
-        // dual ratio test; key = 2*mt + position (X entries are positions 0..nX-1, the general
-        // row of Qf column r is position nX + nF-1-r)
+        const double pdel = C.tie * (1.0 + xmax), ddel = C.tie * C.ynoise;
+        double tmax = INFINITY;
+        K3R_LOOP for (int c = threadIdx.x; c < mt; c += NT) {
+            if (C.st[c] != 0 || C.anorm[c] == 0.0f) continue;      // all-zero rows can never be added
+            if (C.tabu[c] == 2) continue;                          // left during this run of zero steps: no re-entry
+            double num, den;
+            if (rt_primal(C, c, 0, dxmax, num, den)) tmax = fmin(tmax, (num + pdel * C.anorm[c]) / den);
+            if (rt_primal(C, c, 1, dxmax, num, den)) tmax = fmin(tmax, (num + pdel * C.anorm[c]) / den);
+        }
+        // dual candidates: X entries are positions 0..nX-1, the general row of Qf column r is position nX + nF-1-r
         K3R_LOOP for (int q = threadIdx.x; q < nX + (nF - nZ); q += NT) {
             int c; double yc, dy;
             if (q < nX) { c = C.xcon[q]; yc = C.yX[q]; dy = C.dyX[q]; }
             else { const int r = nF - 1 - (q - nX); c = C.widx[r]; yc = C.yW[r]; dy = C.dyW[r]; }
             if (lb_new(C, c) == ub_new(C, c)) continue;
             if (C.tabu[c] == 1) continue;            // entered during this run of zero steps: stays
-            int k = 2 * mt + q;
-            if (C.st[c] < 0 && dy < -thr) {
-                double t = (yc > 0 ? yc : 0) / (-dy);
-                if (t < tau || (t == tau && k < key && t < 1.0)) { tau = t; key = k; }
-            } else if (C.st[c] > 0 && dy > thr) {
-                double t = (yc < 0 ? -yc : 0) / dy;
-                if (t < tau || (t == tau && k < key && t < 1.0)) { tau = t; key = k; }
-            }
+            double num, den;
+            if (rt_dual(C.st[c], yc, dy, thr, ddel, num, den)) tmax = fmin(tmax, (num + ddel) / den);
         }
-        block_argmin(C, tau, key);
-        const bool full = !(tau < 1.0) || key == 0x7fffffff;
-        if (full) tau = 1.0;
+        tmax = block_min(C, tmax);
+        // pass 2: lowest key among the candidates within tmax; packed = key * 128 + dual position
+        int pk = RT_NONE;
+        if (tmax < INFINITY) {
+            K3R_LOOP for (int c = threadIdx.x; c < mt; c += NT) {
+                if (C.st[c] != 0 || C.anorm[c] == 0.0f) continue;
+                if (C.tabu[c] == 2) continue;
+                double num, den;
+                if (rt_primal(C, c, 0, dxmax, num, den) && num / den <= tmax) pk = min(pk, (2 * c) * 128);
+                if (rt_primal(C, c, 1, dxmax, num, den) && num / den <= tmax) pk = min(pk, (2 * c + 1) * 128);
+            }
+            K3R_LOOP for (int q = threadIdx.x; q < nX + (nF - nZ); q += NT) {
+                int c; double yc, dy;
+                if (q < nX) { c = C.xcon[q]; yc = C.yX[q]; dy = C.dyX[q]; }
+                else { const int r = nF - 1 - (q - nX); c = C.widx[r]; yc = C.yW[r]; dy = C.dyW[r]; }
+                if (lb_new(C, c) == ub_new(C, c)) continue;
+                if (C.tabu[c] == 1) continue;
+                double num, den;
+                if (rt_dual(C.st[c], yc, dy, thr, ddel, num, den) && num / den <= tmax) pk = min(pk, (2 * mt + c) * 128 + q);
+            }
+            pk = block_imin(C, pk);
+        }
+        const bool full = (pk == RT_NONE);
+        double tau = 1.0;
+        const int key = full ? RT_NONE : pk >> 7, qsel = pk & 127;
+        if (!full) {
+            double num = 0, den = 1, del;
+            if (key < 2 * mt) { rt_primal(C, key >> 1, key & 1, dxmax, num, den); del = pdel * C.anorm[key >> 1]; }
+            else {
+                int c; double yc, dy;
+                if (qsel < nX) { c = C.xcon[qsel]; yc = C.yX[qsel]; dy = C.dyX[qsel]; }
+                else { const int r = nF - 1 - (qsel - nX); c = C.widx[r]; yc = C.yW[r]; dy = C.dyW[r]; }
+                rt_dual(C.st[c], yc, dy, thr, ddel, num, den); del = ddel;
+            }
+            tau = (num <= del) ? 0.0 : num / den;       // within round-off of zero: a zero step
+        }
+        C.ynoise += tau * dys;
         // anti-cycling (see oracle/qp_oracle.c): constraints that enter while the homotopy makes no
         // progress may not leave through the dual test until it does
         const bool zero_step = !(tau > 1e-14);
@@ -1553,23 +1596,43 @@ K3R_FN __device__ int k3r_vehicle(CT& C, const eep_qp_io& io, const long long ve
                 K3R_LOOP for (int r = nZc + threadIdx.x; r < nFc; r += NT) lmax = fmax(lmax, fabs(lamG[r]));
                 K3R_LOOP for (int k = threadIdx.x; k < nXc; k += NT) lmax = fmax(lmax, fabs(lamX[k]));
                 lmax = block_max(C, lmax);
-                double theta = INFINITY; int kk = 0x7fffffff;
+                // dual ratio test of the exchange, two-pass; keyed by constraint index, packed with the position
+                const double tdel = C.tie * C.ynoise;
+                double thmax = INFINITY;
                 K3R_LOOP for (int q = threadIdx.x; q < nXc + (nFc - nZc); q += NT) {
                     int c; double yc, lr;
                     if (q < nXc) { c = C.xcon[q]; yc = C.yX[q]; lr = lamX[q]; }
                     else { const int r = nFc - 1 - (q - nXc); c = C.widx[r]; yc = C.yW[r]; lr = lamG[r]; }
                     if (lb_new(C, c) == ub_new(C, c)) continue;
-                    double l = (side < 0) ? lr : -lr;
+                    const double l = (side < 0) ? lr : -lr;
                     if (fabs(l) <= 1e-11 * (1.0 + lmax)) continue;
-                    if (C.st[c] < 0 && l > 0) {
-                        double th = (yc > 0 ? yc : 0) / l;
-                        if (th < theta || (th == theta && q < kk)) { theta = th; kk = q; }
-                    } else if (C.st[c] > 0 && l < 0) {
-                        double th = (yc < 0 ? yc : 0) / l;
-                        if (th < theta || (th == theta && q < kk)) { theta = th; kk = q; }
-                    }
+                    if (C.st[c] < 0 && l > 0) thmax = fmin(thmax, ((yc > 0 ? yc : 0) + tdel) / l);
+                    else if (C.st[c] > 0 && l < 0) thmax = fmin(thmax, ((yc < 0 ? -yc : 0) + tdel) / -l);
                 }
-                block_argmin(C, theta, kk);
+                thmax = block_min(C, thmax);
+                int pk2 = RT_NONE;
+                K3R_LOOP for (int q = threadIdx.x; q < nXc + (nFc - nZc); q += NT) {
+                    int c; double yc, lr;
+                    if (q < nXc) { c = C.xcon[q]; yc = C.yX[q]; lr = lamX[q]; }
+                    else { const int r = nFc - 1 - (q - nXc); c = C.widx[r]; yc = C.yW[r]; lr = lamG[r]; }
+                    if (lb_new(C, c) == ub_new(C, c)) continue;
+                    const double l = (side < 0) ? lr : -lr;
+                    if (fabs(l) <= 1e-11 * (1.0 + lmax)) continue;
+                    if (C.st[c] < 0 && l > 0) { if ((yc > 0 ? yc : 0) / l <= thmax) pk2 = min(pk2, c * 128 + q); }
+                    else if (C.st[c] > 0 && l < 0) { if ((yc < 0 ? -yc : 0) / -l <= thmax) pk2 = min(pk2, c * 128 + q); }
+                }
+                pk2 = block_imin(C, pk2);
+                int kk = RT_NONE; double theta = INFINITY;
+                if (pk2 != RT_NONE) {
+                    kk = pk2 & 127;
+                    double yc, lr;
+                    if (kk < nXc) { yc = C.yX[kk]; lr = lamX[kk]; }
+                    else { const int r = nFc - 1 - (kk - nXc); yc = C.yW[r]; lr = lamG[r]; }
+                    const double l = (side < 0) ? lr : -lr;
+                    const double num = (l > 0) ? (yc > 0 ? yc : 0) : (yc < 0 ? -yc : 0), den = fabs(l);
+                    theta = (num <= tdel) ? 0.0 : num / den;
+                    C.ynoise += theta * lmax;
+                }
                 if (kk == 0x7fffffff) { status = EEPACC_QP_INFEASIBLE; break; }
                 K3R_LOOP for (int r = nZc + threadIdx.x; r < nFc; r += NT) C.yW[r] -= theta * ((side < 0) ? lamG[r] : -lamG[r]);
                 K3R_LOOP for (int k = threadIdx.x; k < nXc; k += NT) C.yX[k] -= theta * ((side < 0) ? lamX[k] : -lamX[k]);
@@ -1600,7 +1663,7 @@ K3R_FN __device__ int k3r_vehicle(CT& C, const eep_qp_io& io, const long long ve
             PH(15);
         } else {
             // ---------- dual blocking: remove constraint ----------
-            const int q = key - 2 * mt;
+            const int q = qsel;
             int c, side;
             __syncthreads();
             if (q < nX) {
@@ -1766,11 +1829,10 @@ template <int NU, int NB>
 static int launch_qpr(const eep_qp_io* io, cudaStream_t st)
 {
     const size_t sm = eep_qpr_smem_bytes(io->n, io->m, io->fc);
-    static size_t attr_for = 0;
-    if (sm > attr_for) {
+    // the opt-in is per device: set it on every launch (cheap) rather than caching it in a process-wide static
+    {
         cudaError_t e = cudaFuncSetAttribute(k3r_qp_kernel<NU, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         if (e != cudaSuccess) return (int)e;
-        attr_for = sm;
     }
     long long g = io->B;               // one CTA per vehicle: the hardware scheduler balances uneven solves
     if (io->todo_list) {                         // hand-over list: a few persistent CTAs walk it

@@ -136,6 +136,8 @@ int eepacc_mem_synth_lead(int mem, const double* base, long long n_base, const d
 /* CUDA stream (cudaStream_t as void*) the mem launches on; default stream if never set. */
 int eepacc_mem_set_stream(int mem, void* stream);
 /* Number of kernel launches issued through this mem so far (bench.py's gpu_launches). */
+int eepacc_mem_device(int mem);                 /* CUDA device the mem is bound to (-1: invalid handle).  Every entry point
+                                                  * switches to it and restores the caller's current device on return. */
 long long eepacc_mem_launch_count(int mem);
 /* Per-vehicle counters accumulated so far: double[B][4] = working-set changes, failed QPs,
  * refactorisations with dropped rows, flips.  Host pointer. */
@@ -176,7 +178,8 @@ int eepacc_mem_get_fused(int mem);
 int eepacc_mem_get_cycle_timing(int mem, double* out);
 int eepacc_mem_get_groups(int mem);
 /* Developer aid: copy a per-step device buffer of the closed loop to the host (0 sblk, 1 g, 2 lba, 3 uba,
- * 4 x, 5 status, 6 iter, 7 cost, 8 deferred-vehicle count, 9 the lead trace [n_lead][B][2]); returns the number of doubles written or < 0. */
+ * 4 x, 5 status, 6 iter, 7 cost, 8 deferred-vehicle count, 9 the lead trace [n_lead][B][2], 10 the working set after the
+ * last solve [B][m + n]: -1 lower / +1 upper / 0 inactive, rows then variable bounds); returns the number of doubles written or < 0. */
 long long eepacc_mem_debug_fetch(int mem, int what, double* out, long long cap);
 /* FP64-FMA peak microbenchmark (register-resident DFMA chains); returns GFLOP/s or <0. */
 double eepacc_measure_dfma_peak(int device);

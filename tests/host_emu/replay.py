@@ -122,3 +122,25 @@ if __name__ == "__main__":
     w = replay(sys.argv[1], fc=int(sys.argv[2]) if len(sys.argv) > 2 else None,
                steps=int(sys.argv[3]) if len(sys.argv) > 3 else None)
     print("worst |x - x_ref| =", w)
+
+
+def emu_run(ctrl, params, route, lead, fc=56, want_ws=False, stats=None):
+    """Closed loop of ONE vehicle through the host emulation of the product's device code (K2 -> K3r -> K4).
+    lead: float64[n_steps, 2] (None for TVMPC with n_steps given as an int).  -> log[n_steps, 12] (, ws[n_steps, m+n])."""
+    from eepacc_mpc_casadi_matlab_b200.settings import Params, Route
+    L = build()
+    L.k3r_emu_run.argtypes = [C.c_int, C.POINTER(Params), C.POINTER(Route), _dp, C.c_int, C.c_int, _dp, C.c_void_p, _ip]
+    if isinstance(lead, int):
+        ns, lp = lead, None
+    else:
+        lead = np.ascontiguousarray(lead, dtype=np.float64)
+        ns, lp = lead.shape[0], lead.ctypes.data_as(_dp)
+    log = np.zeros((ns, 12))
+    n = {S.FB: 120, S.AB: 100}.get(ctrl, 40)
+    m = {S.FB: 522, S.AB: 362 if params.ab_route_rows else 282, S.BL: 262, S.TV: 220}[ctrl]
+    ws = np.zeros((ns, n + m), np.int8) if want_ws else None
+    rc = L.k3r_emu_run(ctrl, C.byref(params), C.byref(route), lp, ns, fc, log.ctypes.data_as(_dp),
+                       ws.ctypes.data_as(C.c_void_p) if want_ws else None,
+                       stats.ctypes.data_as(_ip) if stats is not None else None)
+    assert rc == 0, rc
+    return (log, ws) if want_ws else log

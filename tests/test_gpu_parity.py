@@ -86,9 +86,17 @@ def test_qpbuild_matches_oracle(oracle, lead_urban, tree, cn):
     n, m = eng.n, eng.m
     prev = np.zeros(12)
     v_tv_prev = 0.0
+    checked = 0
     for k in range(60):
         s_tv, v_tv = lead_urban[k]
         out = V.step(s_tv, v_tv)
+        if cn == "fb" and k == 0:
+            # FB: the A(k)/D(k) rows (RunOpt_FBMPC.m:78-90, 247-259, the indexing quirk) live in mem.  The closed-loop
+            # step 0 initialises them; from then on every qpbuild call at simulation step k rewrites row k from the
+            # state it is given, exactly as the reference does, so the dense build is comparable at every k >= 1.
+            eng.step(np.array([[s_tv, v_tv]]))
+            prev = out
+            continue
         Ho, go, Ao, lbo, ubo = oracle.qp_arrays(V.qp())
         # reconstruct the step's inputs (RunOpt_FBMPC.m:166-201)
         x0 = np.array([[out[0], out[1]]])
@@ -100,25 +108,20 @@ def test_qpbuild_matches_oracle(oracle, lead_urban, tree, cn):
             at = (v_tv - v_tv_prev) / p.Ts
         eng.set_step(k, k * p.Ts)
         h, g, a, lba, uba = eng.qpbuild(x0, np.array([am1]), np.array([[s_tv, vt, at]]), np.array([k * p.Ts]))
-        if cn == "fb" and k < 25:
-            # the FB A(k) quirk rows live in mem and are only advanced by the closed-loop path;
-            # compare FB builds through the step test below instead
-            pass
-        else:
-            assert _rel(h[0], Ho) < 1e-12, (k, "H")
-            assert _rel(g[0], go) < 1e-11, (k, "g")
-            assert _rel(a[0], Ao) < 1e-12, (k, "A")
-            fin = np.isfinite(lbo)
-            assert np.array_equal(np.isfinite(lba[0]), fin)
-            assert _rel(lba[0][fin], lbo[fin]) < 1e-12
-            fin = np.isfinite(ubo)
-            assert np.array_equal(np.isfinite(uba[0]), fin)
-            assert _rel(uba[0][fin], ubo[fin]) < 1e-12
+        assert _rel(h[0], Ho) < 1e-12, (k, "H")
+        assert _rel(g[0], go) < 1e-11, (k, "g")
+        assert _rel(a[0], Ao) < 1e-12, (k, "A")
+        fin = np.isfinite(lbo)
+        assert np.array_equal(np.isfinite(lba[0]), fin)
+        assert _rel(lba[0][fin], lbo[fin]) < 1e-12
+        fin = np.isfinite(ubo)
+        assert np.array_equal(np.isfinite(uba[0]), fin)
+        assert _rel(uba[0][fin], ubo[fin]) < 1e-12
+        checked += 1
         prev = out
         v_tv_prev = vt if k > 0 else 0.0
-        if cn == "fb":
-            break
     eng.close()
+    assert checked >= 59
 
 
 @pytest.mark.parametrize("tree,cn,tol", [("mc", "ab", 1e-6), ("mc", "fb", 1e-6), ("abo", "fb", 1e-6),
@@ -145,15 +148,12 @@ def test_batched_steps_match_oracle(oracle, lead_urban, cn):
     """Perturbed scenarios, step by step against the oracle: solver status, objective (1e-9 relative,
     1e-5 for the eps-regularised LPs), states (1e-6; LPs 2e-6), Fm+Fb (1e-4 N) and slacks.
 
-    Non-unique optima.  Two problem classes do not determine their solution:
-    * FB while the whole horizon stands still behind a stopped lead (indefinite Hessian, flat Fm/Fb
-      split direction),
-    * the BL/TV LPs at degenerate vertices.
-    There round-off decides which of several (near-)equally good KKT points is reached, and from
-    that step on the two closed loops are different experiments.  For these classes the comparison
-    of a scenario therefore STOPS at its first divergent step, after asserting that the step before
-    was solved to the same objective within 1e-3 (an alternative optimum, not an error).  ABMPC and
-    non-degenerate FBMPC scenarios must never diverge."""
+    ABMPC and FBMPC (degenerate standstill included: the ratio tests are round-off independent, csrc/qp_rules.cuh)
+    must never diverge and must take the same number of working-set changes as the oracle.
+    The BL/TV LPs (H = 0, solved as eps-regularised QPs: multipliers of 1e7 against a curvature of 1e-6) do not
+    determine their vertex to double precision at degenerate steps; there the comparison of a scenario STOPS at
+    its first divergent step, after asserting that the step before was solved to the same objective within
+    1e-3 (an alternative optimum, not an error)."""
     api = _api()
     p = S.default_params("mc")
     B, n_steps = 6, 90
@@ -171,8 +171,6 @@ def test_batched_steps_match_oracle(oracle, lead_urban, cn):
         prev_rel = 0.0
         for k in range(n_steps):
             o, g = ref[k], log[k, b]
-            if cn == "fb" and o[1] < 1e-3 and lead[k, b, 1] == 0.0 and b > 0:
-                may_diverge = True                                  # degenerate standstill seen
             tol = 2e-6 if lp else 1e-6
             state_ok = np.max(np.abs(g[:2] - o[:2])) < tol
             if not state_ok and may_diverge:
@@ -182,13 +180,14 @@ def test_batched_steps_match_oracle(oracle, lead_urban, cn):
             assert g[9] == o[9], (k, b, "status")
             prev_rel = abs(g[11] - o[11]) / (1 + abs(o[11]))
             if not may_diverge:
+                assert g[10] == o[10], (k, b, "working-set changes", g[10], o[10])
                 assert prev_rel <= 1e-9, (k, b, "objective", g[11], o[11])
                 assert abs((g[2] + g[3]) - (o[2] + o[3])) < 1e-4, (k, b, "Fm+Fb")     # the plant only sees Fm+Fb
                 assert np.max(np.abs(g[4:8] - o[4:8])) < 1e-5, (k, b, "slacks")
                 if o[1] > 2.0:
                     assert np.max(np.abs(g[2:4] - o[2:4])) < 1e-4, (k, b, "forces")
             compared += 1
-    assert compared >= 0.6 * B * n_steps, compared
+    assert compared >= (0.6 if lp else 1.0) * B * n_steps, compared
 
 
 def test_qpsolve_conic_scheme_matches_oracle(oracle):
@@ -275,13 +274,8 @@ def test_fused_closed_loop_kernel_matches_per_step_launches(lead_urban, cn):
     lp = cn in ("bl", "tv")
     same = np.all(a == b, axis=(0, 2))
     assert same.mean() > 0.25                                 # vehicles without a hand-over: bit-identical
-    # FB: a hand-over solved by a different factorisation may pick another point on the flat Fm/Fb direction of
-    # the indefinite objective while the vehicle stands still ("degenerate standstill")
     d = np.max(np.abs(a[:, :, :2] - b[:, :, :2]), axis=(0, 2))       # per vehicle, over the cycle
-    if cn == "fb":
-        assert (d < 1e-6).mean() > 0.8 and d.max() < 5e-2, (float((d < 1e-6).mean()), float(d.max()))
-    else:
-        assert d.max() < (2e-6 if lp else 1e-6)
+    assert d.max() < (2e-6 if lp else 1e-6)
     if cn == "ab":
         assert _rel(a[:, :, 11], b[:, :, 11]) < 1e-9
-    assert np.max(np.abs(kpis[0][:, 1] - kpis[1][:, 1])) < (5e-2 if cn == "fb" else 1e-5)
+    assert np.max(np.abs(kpis[0][:, 1] - kpis[1][:, 1])) < 1e-5

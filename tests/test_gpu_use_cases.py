@@ -2,8 +2,10 @@
 
 Covers what use case 0 never reaches: non-zero initial speed, stops, traffic lights, curves, a hill, a cut-in,
 recorded lead traces and runs without a target vehicle (s_tv = inf).  Criteria as in test_gpu_parity.py:
-ABMPC must follow the oracle over the whole run; for the BL/TV LPs and FBMPC (indefinite Hessian) a scenario is
-compared up to its first divergent step, which must follow a step solved to the same objective."""
+ABMPC and FBMPC must follow the oracle over the whole run with the same solver status and the same number of
+working-set changes at every step (FBMPC also from a non-zero initial speed, where RunOpt_FBMPC.m:84 makes the first
+QPs infeasible: the kernel must return what the oracle returns); for the BL/TV LPs a scenario is compared up to its
+first divergent step, which must follow a step solved to the same objective."""
 import numpy as np
 import pytest
 
@@ -12,7 +14,13 @@ from eepacc_mpc_casadi_matlab_b200 import report as R, settings as S, usecase as
 pytestmark = pytest.mark.gpu
 CTRL = {"ab": S.AB, "fb": S.FB, "bl": S.BL, "tv": S.TV}
 MAX_STEPS = 300
-FB_CASES = [1, 4, 6, 8, 11, 12]        # v_init = 0: RunOpt_FBMPC.m:84 puts v_0^2 into A, other starts are infeasible at k = 0
+FB_CASES = list(range(1, 13))
+# Use case 11 (stop lines at 80/450/600 m, 300 steps): the closed loop itself amplifies a state difference by ~1e7
+# between step 40 and step 300 (the stop funnel v_stop_max = |stop - s| slope + v_stop feeds the position error
+# straight back; measured on the CPU between two builds of the ORACLE that differ only in FMA contraction: 1e-13 m
+# at step 40, 1e-10 at 60, 1e-6 at 212, 4e-6 at 218).  No two arithmetics can stay within 1e-6 there; the test keeps
+# the per-step decisions exact (status, working-set changes) and bounds the states by that measured growth.
+FB_STATE_TOL = {11: 1e-4}
 
 
 def _api():
@@ -30,12 +38,13 @@ def _lead_for(oracle, num, p, uc):
     return U.generate_lead_tvmpc(run_tv, p, uc["route"], uc["n_steps"])
 
 
-def _compare(cn, log, ref, strict, w_max=0.0):
+def _compare(cn, log, ref, strict, w_max=0.0, tol_state=None):
     """w_max: largest penalty weight of the controller.  The objective is dominated by weight * slack terms, so a
     1e-11 difference in a slack (states agree to 1e-6, the bar) moves it by 1e-11 * w_max: the 1e-9 relative bar
     on the objective is applied up to that absolute floor."""
     lp = cn in ("bl", "tv")
-    tol = 2e-6 if lp else 1e-6
+    tol = tol_state or (2e-6 if lp else 1e-6)
+    loose = tol_state is not None
     prev_rel, compared = 0.0, 0
     for k in range(len(ref)):
         o, g = ref[k], log[k]
@@ -46,9 +55,11 @@ def _compare(cn, log, ref, strict, w_max=0.0):
         assert ok, (k, g[:2], o[:2], g[9], o[9])
         prev_rel = abs(g[11] - o[11]) / (1 + abs(o[11]))
         if strict:
-            assert prev_rel <= 1e-9 or abs(g[11] - o[11]) <= 1e-10 * w_max, (k, "objective", g[11], o[11])
-            assert abs((g[2] + g[3]) - (o[2] + o[3])) < 1e-4, (k, "Fm+Fb")
-            assert np.max(np.abs(g[4:8] - o[4:8])) < 1e-5, (k, "slacks")
+            assert g[10] == o[10], (k, "working-set changes", g[10], o[10])
+            if not loose:
+                assert prev_rel <= 1e-9 or abs(g[11] - o[11]) <= 1e-10 * w_max, (k, "objective", g[11], o[11])
+                assert abs((g[2] + g[3]) - (o[2] + o[3])) < 1e-4, (k, "Fm+Fb")
+                assert np.max(np.abs(g[4:8] - o[4:8])) < 1e-5, (k, "slacks")
         compared += 1
     return compared
 
@@ -89,13 +100,17 @@ def test_bl_and_fb_on_use_cases(oracle, cn):
         log, _ = eng.run(n)
         eng.close()
         ref, _ = oracle.run(CTRL[cn], p, uc["route"], lead)
-        c = _compare(cn, log[:, 0, :], ref, strict=False)
+        if cn == "fb":
+            c = _compare(cn, log[:, 0, :], ref, strict=True, w_max=max(p.W_FB), tol_state=FB_STATE_TOL.get(num))
+            assert c == n, (num, c, n)
+        else:
+            c = _compare(cn, log[:, 0, :], ref, strict=False)
         assert c >= 20, (num, c)
         per_case[num] = (c, n)
         total += n
         compared += c
     print(cn, "steps compared before the first alternative optimum, per use case:", per_case)
-    assert compared >= 0.5 * total, (compared, total, per_case)
+    assert compared >= (1.0 if cn == "fb" else 0.5) * total, (compared, total, per_case)
 
 
 @pytest.mark.parametrize("num", [3, 4, 5, 6, 7, 11, 12])
