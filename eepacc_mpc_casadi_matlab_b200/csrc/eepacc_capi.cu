@@ -283,6 +283,7 @@ static void slice_io(eep_post_io& io, size_t v0, long long nb)
     io.prev_sol = shift(io.prev_sol, v0 * 2 * (NH + 1));
     io.log = shift(io.log, v0 * EEPACC_LOG_W);
     io.kpi_acc = shift(io.kpi_acc, v0 * ACC_W);
+    io.lead = shift(io.lead, v0 * 2);
 }
 
 static eep_post_io make_post_io(Mem* M, int kk, double* log_dev)
@@ -356,6 +357,7 @@ int device_step_slice(Mem* M, int g, size_t v0, long long nb, cudaStream_t st, i
     }
     if (ev) CK(cudaEventRecord(ev[2], st));
     eep_post_io pio = make_post_io(M, kk, log_dev);
+    pio.lead = (M->ctrl == EEPACC_TV) ? nullptr : lead_dev;      // headway KPIs (TVMPC has no target vehicle)
     slice_io(pio, v0, nb);
     rc = eep_launch_post(&M->p, &pio, st);
     if (rc) return fail(EEPACC_ERR_CUDA, "k4_post launch", (cudaError_t)rc);
@@ -771,7 +773,7 @@ long long eepacc_mem_debug_fetch(int mem, int what, double* out, long long cap)
     case 8: src = M->defer_cnt.p; cnt = 2; break;   // int[4]: vehicles deferred to the full-space kernel in the last step
     case 10: {
         // working set after the last solve, [B][m + n] as doubles: -1 held at its lower bound, +1 upper, 0 inactive
-        // (rows 0..m-1, then the implicit variable bounds) -- the layout of the oracle's orc_vehicle_get_ws
+        // (rows 0..m-1, then the implicit variable bounds) -- the layout tests/ compare against (orc_vehicle_get_ws)
         const long long mt = M->m + M->n, n = M->n;
         if (cap < B * mt) { fail(EEPACC_ERR_ARG, "working-set fetch needs B*(m+n) doubles"); return -1; }
         if (cudaStreamSynchronize(M->stream) != cudaSuccess) return -1;

@@ -81,7 +81,8 @@ struct eep_post_io {
     double *s_prev, *v_prev, *Fm_prev, *Fb_prev;
     double *prev_sol;           // [B][2][N+1]
     double *log;                // [B][EEPACC_LOG_W] for this step (may be null)
-    double *kpi_acc;            // [B][12] running KPI accumulators
+    double *kpi_acc;            // [B][ACC_W] running KPI accumulators
+    const double* lead;         // [B][2] this step's (s_tv, v_tv) for the headway KPIs (may be null: no lead)
 };
 
 // fused closed loop (k3r_qp.cu: k5_cycle_kernel): one CTA takes a vehicle through the MPC steps

@@ -670,7 +670,7 @@ __device__ int resolve_pending(Ctx& C, int c_out, int side_out, unsigned long lo
         for (int cc = threadIdx.x; cc < mt; cc += NT) {
             if (C.st[cc] != 0 || C.anorm[cc] == 0.0f) continue;
             int sd; double num, den;
-            if (rt_exch(C, cc, dn, sd, num, den)) tmax = fmin(tmax, (num + pdel * C.anorm[cc]) / den);
+            if (rt_exch(C, cc, dn, sd, num, den)) tmax = fmin(tmax, (num + pdel * C.anorm[cc]) * (1.0 / den));
         }
         tmax = block_min(C, tmax);
         if (!(tmax < INFINITY)) return EEPACC_QP_UNBOUNDED;
@@ -678,7 +678,7 @@ __device__ int resolve_pending(Ctx& C, int c_out, int side_out, unsigned long lo
         for (int cc = threadIdx.x; cc < mt; cc += NT) {
             if (C.st[cc] != 0 || C.anorm[cc] == 0.0f) continue;
             int sd; double num, den;
-            if (rt_exch(C, cc, dn, sd, num, den) && num / den <= tmax) key = min(key, 2 * cc + sd);
+            if (rt_exch(C, cc, dn, sd, num, den) && num * (1.0 / den) <= tmax) key = min(key, 2 * cc + sd);
         }
         key = block_imin(C, key);
         double tmin;
@@ -1080,15 +1080,15 @@ __global__ void __launch_bounds__(NT, 1) k3_qp_kernel(const __grid_constant__ ee
                 if (C.st[c] != 0 || C.anorm[c] == 0.0f) continue;      // all-zero rows can never be added
                 if (C.tabu[c] == 2) continue;                          // left during this run of zero steps: no re-entry
                 double num, den;
-                if (rt_primal(C, c, 0, dxmax, num, den)) tmax = fmin(tmax, (num + pdel * C.anorm[c]) / den);
-                if (rt_primal(C, c, 1, dxmax, num, den)) tmax = fmin(tmax, (num + pdel * C.anorm[c]) / den);
+                if (rt_primal(C, c, 0, dxmax, num, den)) tmax = fmin(tmax, (num + pdel * C.anorm[c]) * (1.0 / den));
+                if (rt_primal(C, c, 1, dxmax, num, den)) tmax = fmin(tmax, (num + pdel * C.anorm[c]) * (1.0 / den));
             }
             for (int r = nZ + threadIdx.x; r < n; r += NT) {
                 const int c = C.widx[r];
                 if (lb_new(C, c) == ub_new(C, c)) continue;
                 if (C.tabu[c] == 1) continue;            // entered during this run of zero steps: stays
                 double num, den;
-                if (rt_dual(C.st[c], C.yW[r], C.dyW[r], thr, ddel, num, den)) tmax = fmin(tmax, (num + ddel) / den);
+                if (rt_dual(C.st[c], C.yW[r], C.dyW[r], thr, ddel, num, den)) tmax = fmin(tmax, (num + ddel) * (1.0 / den));
             }
             tmax = block_min(C, tmax);
             // pass 2: lowest key among the candidates within tmax; packed = key * 128 + Q column of a dual candidate
@@ -1098,15 +1098,15 @@ __global__ void __launch_bounds__(NT, 1) k3_qp_kernel(const __grid_constant__ ee
                     if (C.st[c] != 0 || C.anorm[c] == 0.0f) continue;
                     if (C.tabu[c] == 2) continue;
                     double num, den;
-                    if (rt_primal(C, c, 0, dxmax, num, den) && num / den <= tmax) pk = min(pk, (2 * c) * 128);
-                    if (rt_primal(C, c, 1, dxmax, num, den) && num / den <= tmax) pk = min(pk, (2 * c + 1) * 128);
+                    if (rt_primal(C, c, 0, dxmax, num, den) && num * (1.0 / den) <= tmax) pk = min(pk, (2 * c) * 128);
+                    if (rt_primal(C, c, 1, dxmax, num, den) && num * (1.0 / den) <= tmax) pk = min(pk, (2 * c + 1) * 128);
                 }
                 for (int r = nZ + threadIdx.x; r < n; r += NT) {
                     const int c = C.widx[r];
                     if (lb_new(C, c) == ub_new(C, c)) continue;
                     if (C.tabu[c] == 1) continue;
                     double num, den;
-                    if (rt_dual(C.st[c], C.yW[r], C.dyW[r], thr, ddel, num, den) && num / den <= tmax) pk = min(pk, (2 * mt + c) * 128 + r);
+                    if (rt_dual(C.st[c], C.yW[r], C.dyW[r], thr, ddel, num, den) && num * (1.0 / den) <= tmax) pk = min(pk, (2 * mt + c) * 128 + r);
                 }
                 pk = block_imin(C, pk);
             }
@@ -1185,8 +1185,8 @@ __global__ void __launch_bounds__(NT, 1) k3_qp_kernel(const __grid_constant__ ee
                         const double l = (side < 0) ? C.t2[r] : -C.t2[r];
                         if (fabs(l) <= 1e-11 * (1.0 + lmax)) continue;
                         const double yc = C.yW[r];
-                        if (C.st[c] < 0 && l > 0) thmax = fmin(thmax, ((yc > 0 ? yc : 0) + tdel) / l);
-                        else if (C.st[c] > 0 && l < 0) thmax = fmin(thmax, ((yc < 0 ? -yc : 0) + tdel) / -l);
+                        if (C.st[c] < 0 && l > 0) thmax = fmin(thmax, ((yc > 0 ? yc : 0) + tdel) * (1.0 / l));
+                        else if (C.st[c] > 0 && l < 0) thmax = fmin(thmax, ((yc < 0 ? -yc : 0) + tdel) * (1.0 / -l));
                     }
                     thmax = block_min(C, thmax);
                     int pk2 = RT_NONE;
@@ -1196,8 +1196,8 @@ __global__ void __launch_bounds__(NT, 1) k3_qp_kernel(const __grid_constant__ ee
                         const double l = (side < 0) ? C.t2[r] : -C.t2[r];
                         if (fabs(l) <= 1e-11 * (1.0 + lmax)) continue;
                         const double yc = C.yW[r];
-                        if (C.st[c] < 0 && l > 0) { if ((yc > 0 ? yc : 0) / l <= thmax) pk2 = min(pk2, c * 128 + r); }
-                        else if (C.st[c] > 0 && l < 0) { if ((yc < 0 ? -yc : 0) / -l <= thmax) pk2 = min(pk2, c * 128 + r); }
+                        if (C.st[c] < 0 && l > 0) { if ((yc > 0 ? yc : 0) * (1.0 / l) <= thmax) pk2 = min(pk2, c * 128 + r); }
+                        else if (C.st[c] > 0 && l < 0) { if ((yc < 0 ? -yc : 0) * (1.0 / -l) <= thmax) pk2 = min(pk2, c * 128 + r); }
                     }
                     pk2 = block_imin(C, pk2);
                     int kk = RT_NONE; double theta = INFINITY;

@@ -107,6 +107,7 @@ struct CtxT {
     signed char *st, *tabu;
     double* red;
     int* ired;
+    double* tt;                 // [(2 ceil(mt/NT) + ceil(n/NT)) NT] ratios of the ratio-test candidates (pass 1 -> pass 2)
 #ifdef EEP_K3_TIMERS
     long long* ph;              // [32] clock64() cycles by phase + [32] = last stamp (thread 0 only)
 #endif
@@ -140,6 +141,7 @@ template <class CT> __device__ __forceinline__ double ub_new(const CT& C, int c)
 template <class CT> __device__ __forceinline__ double block_sum(CT&, double v) { return v; }
 template <class CT> __device__ __forceinline__ double block_max(CT&, double v) { return v; }
 template <class CT> __device__ __forceinline__ void block_argmin(CT&, double&, int&) {}
+template <class CT> __device__ __forceinline__ void block_max3(CT&, double&, double&, double&) {}
 #else
 template <class CT> __device__ __forceinline__ double block_sum(CT& C, double v)
 {
@@ -160,6 +162,18 @@ template <class CT> __device__ __forceinline__ double block_max(CT& C, double v)
     double s = C.red[0];
     for (int w = 1; w < NT / 32; ++w) s = fmax(s, C.red[w]);
     return s;
+}
+// three maxima in one pass (C.red holds 16 doubles)
+template <class CT> __device__ __forceinline__ void block_max3(CT& C, double& a, double& b, double& c)
+{
+    for (int o = 16; o > 0; o >>= 1) {
+        a = fmax(a, __shfl_xor_sync(0xffffffffu, a, o)); b = fmax(b, __shfl_xor_sync(0xffffffffu, b, o)); c = fmax(c, __shfl_xor_sync(0xffffffffu, c, o));
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { C.red[threadIdx.x >> 5] = a; C.red[NT / 32 + (threadIdx.x >> 5)] = b; C.red[2 * (NT / 32) + (threadIdx.x >> 5)] = c; }
+    __syncthreads();
+    a = C.red[0]; b = C.red[NT / 32]; c = C.red[2 * (NT / 32)];
+    for (int w = 1; w < NT / 32; ++w) { a = fmax(a, C.red[w]); b = fmax(b, C.red[NT / 32 + w]); c = fmax(c, C.red[2 * (NT / 32) + w]); }
 }
 // lexicographic (t, key) minimum
 template <class CT> __device__ __forceinline__ void block_argmin(CT& C, double& t, int& key)
@@ -546,7 +560,31 @@ template <class CT> K3R_FN __device__ int givens_add(CT& C, int cidx, int side, 
             }
             MM(i, nR - 1) = u;
         }
-        // R phase B: re-triangularise (row rotations), wavefront over k
+        // R phase B: re-triangularise (row rotations k = 0..nR-2 on rows k, k+1).  Column j only sees rotations
+        // 0..j, one after the other, and rotation k is defined by column k once rotations 0..k-1 have passed over it:
+        // ONE WARP walks the chain with lane j owning column j (shuffles, no block barrier per rotation).
+#ifndef EEP_HOST_EMU
+        if (nR <= 32) {
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                const int j = threadIdx.x;
+                for (int k = 0; k < nR - 1; ++k) {
+                    double c2 = 1.0, s2 = 0.0, rr = 0.0;
+                    if (j == k) {
+                        const double pa = MM(k, k), pb = C.sub[k + 1];
+                        rr = hypot(pa, pb);
+                        if (rr != 0.0) { c2 = pa / rr; s2 = pb / rr; MM(k, k) = rr; }
+                    }
+                    c2 = __shfl_sync(0xffffffffu, c2, k); s2 = __shfl_sync(0xffffffffu, s2, k); rr = __shfl_sync(0xffffffffu, rr, k);
+                    if (rr != 0.0 && j > k && j < nR) {
+                        const double u = MM(k, j), v = MM(k + 1, j);
+                        MM(k, j) = c2 * u + s2 * v;
+                        MM(k + 1, j) = -s2 * u + c2 * v;
+                    }
+                }
+            }
+        } else
+#endif
         for (int k = 0; k < nR - 1; ++k) {
             __syncthreads();
             double pa = MM(k, k), pb = C.sub[k + 1];
@@ -589,7 +627,34 @@ template <class CT> K3R_FN __device__ void remove_general(CT& C, int rp)
     if (threadIdx.x == 0) {
         for (int r = rp; r > nZ; --r) { C.widx[r] = C.widx[r - 1]; C.yW[r] = C.yW[r - 1]; }
     }
-    // Givens wavefront: rotation at r (columns r-1, r) for r = rp .. nZ+1
+    // Givens wavefront: rotation at r (columns r-1, r) for r = rp .. nZ+1.  Row rr only sees rotations rp..rr, one
+    // after the other, and rotation r is defined by row r once rotations rp..r+1 have passed over it: ONE WARP
+    // walks the chain with a lane per row (shuffles instead of two block barriers per rotation).
+#ifndef EEP_HOST_EMU
+    if (rp - nZ <= 32) {
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const int rr = rp - (int)threadIdx.x;           // lane l owns row rp - l
+            for (int r = rp; r > nZ; --r) {
+                const int src = rp - r;
+                double cs = 1.0, sn = 0.0;
+                if (rr == r) {
+                    const double a = C.sub[r], b = MM(r, r);
+                    const double rho = hypot(a, b);
+                    if (rho != 0.0) { cs = b / rho; sn = a / rho; }
+                    C.csA[r] = cs; C.snA[r] = sn;
+                    MM(r, r) = sn * a + cs * b;
+                }
+                cs = __shfl_sync(0xffffffffu, cs, src); sn = __shfl_sync(0xffffffffu, sn, src);
+                if (rr < r && rr > nZ) {
+                    const double u = MM(rr, r - 1), v = MM(rr, r);
+                    MM(rr, r - 1) = cs * u - sn * v;
+                    MM(rr, r) = sn * u + cs * v;
+                }
+            }
+        }
+    } else
+#endif
     for (int r = rp; r > nZ; --r) {
         __syncthreads();
         double a = C.sub[r], b = MM(r, r);
@@ -751,6 +816,32 @@ template <class CT> K3R_FN __device__ int refactor_R(CT& C)
         __syncthreads();
     }
     const double thr = EPS_PD * C.hscale;
+#ifndef EEP_HOST_EMU
+    if (nZ <= 32) {
+        // one warp, lane j owns column j: left-looking upper Cholesky, row by row; R(i,i) is handed on by shuffle
+        __syncthreads();
+        int bad = 0;
+        if (threadIdx.x < 32) {
+            const int j = threadIdx.x;
+            for (int i = 0; i < nZ; ++i) {
+                double v = 0.0;
+                if (j >= i && j < nZ) {
+                    v = MM(i, j);
+                    for (int k = 0; k < i; ++k) v -= MM(k, i) * MM(k, j);
+                }
+                const double d = __shfl_sync(0xffffffffu, v, i);
+                if (!(d > thr)) { bad = 1; break; }
+                const double rk = sqrt(d), inv = 1.0 / rk;
+                if (j == i) MM(i, i) = rk;
+                else if (j > i && j < nZ) MM(i, j) = v * inv;
+                __syncwarp();
+            }
+            if (j == 0) C.ired[7] = bad;
+        }
+        __syncthreads();
+        return C.ired[7];
+    }
+#endif
     for (int k = 0; k < nZ; ++k) {
         __syncthreads();
         double d = MM(k, k);
@@ -966,7 +1057,7 @@ template <class CT> K3R_FN __device__ int resolve_pending(CT& C, int c_out, int 
         K3R_LOOP for (int cc = threadIdx.x; cc < mt; cc += NT) {
             if (C.st[cc] != 0 || C.anorm[cc] == 0.0f) continue;
             int sd; double num, den;
-            if (rt_exch(C, cc, dn, sd, num, den)) tmax = fmin(tmax, (num + pdel * C.anorm[cc]) / den);
+            if (rt_exch(C, cc, dn, sd, num, den)) tmax = fmin(tmax, (num + pdel * C.anorm[cc]) * (1.0 / den));
         }
         tmax = block_min(C, tmax);
         if (!(tmax < INFINITY)) return EEPACC_QP_UNBOUNDED;
@@ -974,7 +1065,7 @@ template <class CT> K3R_FN __device__ int resolve_pending(CT& C, int c_out, int 
         K3R_LOOP for (int cc = threadIdx.x; cc < mt; cc += NT) {
             if (C.st[cc] != 0 || C.anorm[cc] == 0.0f) continue;
             int sd; double num, den;
-            if (rt_exch(C, cc, dn, sd, num, den) && num / den <= tmax) key = min(key, 2 * cc + sd);
+            if (rt_exch(C, cc, dn, sd, num, den) && num * (1.0 / den) <= tmax) key = min(key, 2 * cc + sd);
         }
         key = block_imin(C, key);
         double tmin;
@@ -1034,6 +1125,53 @@ template <class CT> K3R_FN __device__ int warm_setup(CT& C, int old_nA, const sh
     }
     K3R_LOOP for (int j = threadIdx.x; j < n; j += NT) C.fpos[j] = 0;
     __syncthreads();
+#ifndef EEP_HOST_EMU
+    // X list, general candidates and free list by ordered stream compaction in ONE WARP (ballots + popcounts; the
+    // order of the stored working set is kept, exactly what the serial statement below does).  A second unit row
+    // on a variable that is already pinned is dropped: the first occurrence is found with a shared atomicMin.
+    int* first = reinterpret_cast<int*>(C.t1) + n;       // [n] (cand uses the first n shorts of t1)
+    K3R_LOOP for (int j = threadIdx.x; j < n; j += NT) first[j] = 0x7fffffff;
+    __syncthreads();
+    K3R_LOOP for (int k = threadIdx.x; k < old_nA; k += NT)
+        if (tmpc[3 * k] >= 0 && tmpc[3 * k + 1] >= 0) atomicMin(&first[tmpc[3 * k + 1]], k);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const unsigned lane = threadIdx.x, lt = (1u << lane) - 1u;
+        int nx = 0, ng = 0;
+        for (int k0 = 0; k0 < old_nA; k0 += 32) {
+            const int k = k0 + (int)lane;
+            int c = -1, jv = -1;
+            if (k < old_nA) { c = tmpc[3 * k]; jv = tmpc[3 * k + 1]; }
+            const bool isX = c >= 0 && jv >= 0 && first[jv] == k;
+            const bool isG = c >= 0 && jv < 0;
+            const unsigned mx = __ballot_sync(0xffffffffu, isX), mg = __ballot_sync(0xffffffffu, isG);
+            if (isX) {
+                const int q = nx + __popc(mx & lt);
+                C.xvar[q] = (short)jv; C.xcon[q] = (short)c; C.xcv[q] = tmpv[k]; C.yX[q] = tmpy[k];
+                C.fpos[jv] = (short)(-1 - q);
+                C.st[c] = (signed char)tmpc[3 * k + 2];
+            } else if (isG) {
+                const int q = ng + __popc(mg & lt);
+                cand[q] = (short)c; ycand[q] = tmpy[k]; C.st[c] = (signed char)tmpc[3 * k + 2];
+            }
+            nx += __popc(mx); ng += __popc(mg);
+        }
+        __syncwarp();
+        int nf = 0;
+        for (int j0 = 0; j0 < n; j0 += 32) {
+            const int j = j0 + (int)lane;
+            const bool fr = j < n && C.fpos[j] >= 0;
+            const unsigned mf = __ballot_sync(0xffffffffu, fr);
+            if (fr) {
+                const int q = nf + __popc(mf & lt);
+                if (q < C.fc) C.flist[q] = (short)j;
+                C.fpos[j] = (short)q;
+            }
+            nf += __popc(mf);
+        }
+        if (lane == 0) { C.ired[4] = ng; C.ired[5] = nx; C.ired[6] = nf; }
+    }
+#else
     // thread 0: X list, general candidates, free list
     if (threadIdx.x == 0) {
         int nx = 0, ng = 0;
@@ -1056,6 +1194,7 @@ template <class CT> K3R_FN __device__ int warm_setup(CT& C, int old_nA, const sh
             if (C.fpos[j] >= 0) { if (nf < C.fc) C.flist[nf] = (short)j; C.fpos[j] = (short)nf; ++nf; }
         C.ired[4] = ng; C.ired[5] = nx; C.ired[6] = nf;
     }
+#endif
     __syncthreads();
     int cnt = C.ired[4];
     const int nX = C.ired[5], nF = C.ired[6];
@@ -1340,8 +1479,9 @@ __device__ __forceinline__ void k3r_setup(k3r::CtxT<NU, NB>& C, const eep_qp_io&
         C.sv = p; p += NH + 1; C.vv = p; p += NH + 1; C.drv = p; p += NH; C.yc = p; p += NH * 3;
         C.aS = p; p += NH + 1; C.aV = p; p += NH + 1; C.aD = p; p += NH;
         C.rS = p; p += fc + 1; C.rV = p; p += fc + 1; C.rv0 = p; p += fc + 1; C.rv1 = p; p += fc + 1; C.rv2 = p; p += fc + 1;
-        C.red = p; p += 8;
+        C.red = p; p += 16;
         C.ired = reinterpret_cast<int*>(p); p += 4;      // 8 ints
+        C.tt = p; p += (size_t)(2 * ((mt + NT - 1) / NT) + (n + NT - 1) / NT) * NT;
         double* cst = p; p += 96;
         C.g = gS; C.gw = gS; C.rtab = io.rowtab; C.cvals = cst; C.cva = cst + 32; C.cvb = cst + 64;
         short* sp = reinterpret_cast<short*>(p);
@@ -1464,53 +1604,57 @@ K3R_FN __device__ int k3r_vehicle(CT& C, const eep_qp_io& io, const long long ve
         Amul(C, C.dx, C.Adx);
         PH(13);
 
-        // ---- ratio tests, two-pass (qp_rules.cuh; oracle/qp_oracle.c:rt_select) ----
-        double dxmax = 0, xmax = 0;
+        // ---- ratio tests, two-pass (qp_rules.cuh; oracle/qp_oracle.c:rt_select).  Pass 1 leaves every candidate's
+        // ratio in the shared scratch C.tt (slot-major, one column per thread: no bank conflicts), pass 2 only
+        // compares: no second evaluation, one division per candidate. ----
+        double dxmax = 0, xmax = 0, dys = 0;
         K3R_LOOP for (int i = threadIdx.x; i < n; i += NT) { dxmax = fmax(dxmax, fabs(C.dx[i])); xmax = fmax(xmax, fabs(C.x[i])); }
-        block_max2(C, dxmax, xmax);
-        double dys = 0;
         K3R_LOOP for (int r = nZ + threadIdx.x; r < nF; r += NT) dys = fmax(dys, fabs(C.dyW[r]));
         K3R_LOOP for (int k = threadIdx.x; k < nX; k += NT) dys = fmax(dys, fabs(C.dyX[k]));
-        dys = block_max(C, dys);
+        block_max3(C, dxmax, xmax, dys);
         const double thr = EPS_RATE * (1.0 + dys);
         const double pdel = C.tie * (1.0 + xmax), ddel = C.tie * C.ynoise;
         double tmax = INFINITY;
-        K3R_LOOP for (int c = threadIdx.x; c < mt; c += NT) {
-            if (C.st[c] != 0 || C.anorm[c] == 0.0f) continue;      // all-zero rows can never be added
-            if (C.tabu[c] == 2) continue;                          // left during this run of zero steps: no re-entry
-            double num, den;
-            if (rt_primal(C, c, 0, dxmax, num, den)) tmax = fmin(tmax, (num + pdel * C.anorm[c]) / den);
-            if (rt_primal(C, c, 1, dxmax, num, den)) tmax = fmin(tmax, (num + pdel * C.anorm[c]) / den);
+        double* tt = C.tt + threadIdx.x;
+        int slot = 0;
+        K3R_LOOP for (int c = threadIdx.x; c < mt; c += NT, slot += 2) {
+            double t0 = INFINITY, t1 = INFINITY;
+            if (C.st[c] == 0 && C.anorm[c] != 0.0f && C.tabu[c] != 2) {   // all-zero rows can never be added; tabu 2: left during this run of zero steps
+                double num, den;
+                if (rt_primal(C, c, 0, dxmax, num, den)) { const double inv = 1.0 / den; t0 = num * inv; tmax = fmin(tmax, (num + pdel * C.anorm[c]) * inv); }
+                if (rt_primal(C, c, 1, dxmax, num, den)) { const double inv = 1.0 / den; t1 = num * inv; tmax = fmin(tmax, (num + pdel * C.anorm[c]) * inv); }
+            }
+            tt[slot * NT] = t0; tt[(slot + 1) * NT] = t1;
         }
         // dual candidates: X entries are positions 0..nX-1, the general row of Qf column r is position nX + nF-1-r
-        K3R_LOOP for (int q = threadIdx.x; q < nX + (nF - nZ); q += NT) {
+        const int dslot0 = 2 * ((mt + NT - 1) / NT);
+        slot = dslot0;
+        K3R_LOOP for (int q = threadIdx.x; q < nX + (nF - nZ); q += NT, ++slot) {
             int c; double yc, dy;
             if (q < nX) { c = C.xcon[q]; yc = C.yX[q]; dy = C.dyX[q]; }
             else { const int r = nF - 1 - (q - nX); c = C.widx[r]; yc = C.yW[r]; dy = C.dyW[r]; }
-            if (lb_new(C, c) == ub_new(C, c)) continue;
-            if (C.tabu[c] == 1) continue;            // entered during this run of zero steps: stays
-            double num, den;
-            if (rt_dual(C.st[c], yc, dy, thr, ddel, num, den)) tmax = fmin(tmax, (num + ddel) / den);
+            double t0 = INFINITY, num, den;
+            // equalities never leave; tabu 1: entered during this run of zero steps, stays
+            if (lb_new(C, c) != ub_new(C, c) && C.tabu[c] != 1 && rt_dual(C.st[c], yc, dy, thr, ddel, num, den)) {
+                const double inv = 1.0 / den; t0 = num * inv; tmax = fmin(tmax, (num + ddel) * inv);
+            }
+            tt[slot * NT] = t0;
         }
         tmax = block_min(C, tmax);
         // pass 2: lowest key among the candidates within tmax; packed = key * 128 + dual position
         int pk = RT_NONE;
         if (tmax < INFINITY) {
-            K3R_LOOP for (int c = threadIdx.x; c < mt; c += NT) {
-                if (C.st[c] != 0 || C.anorm[c] == 0.0f) continue;
-                if (C.tabu[c] == 2) continue;
-                double num, den;
-                if (rt_primal(C, c, 0, dxmax, num, den) && num / den <= tmax) pk = min(pk, (2 * c) * 128);
-                if (rt_primal(C, c, 1, dxmax, num, den) && num / den <= tmax) pk = min(pk, (2 * c + 1) * 128);
+            slot = 0;
+            K3R_LOOP for (int c = threadIdx.x; c < mt; c += NT, slot += 2) {
+                if (tt[slot * NT] <= tmax) pk = min(pk, (2 * c) * 128);
+                if (tt[(slot + 1) * NT] <= tmax) pk = min(pk, (2 * c + 1) * 128);
             }
-            K3R_LOOP for (int q = threadIdx.x; q < nX + (nF - nZ); q += NT) {
-                int c; double yc, dy;
-                if (q < nX) { c = C.xcon[q]; yc = C.yX[q]; dy = C.dyX[q]; }
-                else { const int r = nF - 1 - (q - nX); c = C.widx[r]; yc = C.yW[r]; dy = C.dyW[r]; }
-                if (lb_new(C, c) == ub_new(C, c)) continue;
-                if (C.tabu[c] == 1) continue;
-                double num, den;
-                if (rt_dual(C.st[c], yc, dy, thr, ddel, num, den) && num / den <= tmax) pk = min(pk, (2 * mt + c) * 128 + q);
+            slot = dslot0;
+            K3R_LOOP for (int q = threadIdx.x; q < nX + (nF - nZ); q += NT, ++slot) {
+                if (tt[slot * NT] <= tmax) {
+                    const int c = (q < nX) ? C.xcon[q] : C.widx[nF - 1 - (q - nX)];
+                    pk = min(pk, (2 * mt + c) * 128 + q);
+                }
             }
             pk = block_imin(C, pk);
         }
@@ -1606,8 +1750,8 @@ K3R_FN __device__ int k3r_vehicle(CT& C, const eep_qp_io& io, const long long ve
                     if (lb_new(C, c) == ub_new(C, c)) continue;
                     const double l = (side < 0) ? lr : -lr;
                     if (fabs(l) <= 1e-11 * (1.0 + lmax)) continue;
-                    if (C.st[c] < 0 && l > 0) thmax = fmin(thmax, ((yc > 0 ? yc : 0) + tdel) / l);
-                    else if (C.st[c] > 0 && l < 0) thmax = fmin(thmax, ((yc < 0 ? -yc : 0) + tdel) / -l);
+                    if (C.st[c] < 0 && l > 0) thmax = fmin(thmax, ((yc > 0 ? yc : 0) + tdel) * (1.0 / l));
+                    else if (C.st[c] > 0 && l < 0) thmax = fmin(thmax, ((yc < 0 ? -yc : 0) + tdel) * (1.0 / -l));
                 }
                 thmax = block_min(C, thmax);
                 int pk2 = RT_NONE;
@@ -1618,8 +1762,8 @@ K3R_FN __device__ int k3r_vehicle(CT& C, const eep_qp_io& io, const long long ve
                     if (lb_new(C, c) == ub_new(C, c)) continue;
                     const double l = (side < 0) ? lr : -lr;
                     if (fabs(l) <= 1e-11 * (1.0 + lmax)) continue;
-                    if (C.st[c] < 0 && l > 0) { if ((yc > 0 ? yc : 0) / l <= thmax) pk2 = min(pk2, c * 128 + q); }
-                    else if (C.st[c] > 0 && l < 0) { if ((yc < 0 ? -yc : 0) / -l <= thmax) pk2 = min(pk2, c * 128 + q); }
+                    if (C.st[c] < 0 && l > 0) { if ((yc > 0 ? yc : 0) * (1.0 / l) <= thmax) pk2 = min(pk2, c * 128 + q); }
+                    else if (C.st[c] > 0 && l < 0) { if ((yc < 0 ? -yc : 0) * (1.0 / -l) <= thmax) pk2 = min(pk2, c * 128 + q); }
                 }
                 pk2 = block_imin(C, pk2);
                 int kk = RT_NONE; double theta = INFINITY;
@@ -1800,7 +1944,8 @@ extern "C" __host__ __device__ size_t eep_qpr_smem_bytes(int n, int m, int fc)
     size_t d = (size_t)(fc + 1) * ldq + (size_t)fc * (fc + 1) / 2 + fc + 2 + (fc + 2) + 13 * (size_t)n + 10 * (size_t)(fc + 1)
              + (mt + 1) / 2
              + 2 * (size_t)(NH + 1) * NH + NH + 1 + 2 * NH * 9 + NH * 4 + 2 * (NH + 1) + NH + NH * 3
-             + 2 * (NH + 1) + NH + 5 * (size_t)(fc + 1) + 8 + 4 + 96;
+             + 2 * (NH + 1) + NH + 5 * (size_t)(fc + 1) + 16 + 4 + 96
+             + (size_t)(2 * ((mt + NT - 1) / NT) + (n + NT - 1) / NT) * NT;
     size_t shorts = 7 * (size_t)(fc + 1) + 3 * (size_t)n;
     size_t b = d * 8 + shorts * 2 + 2 * (size_t)mt + 16;
 #ifdef EEP_K3_TIMERS
@@ -1895,6 +2040,7 @@ __global__ void __launch_bounds__(NT, K3R_MINB) k5_cycle_kernel(const eepacc_par
             if (threadIdx.x == 0) {
                 po.kk = k;
                 po.log = cy.log_all ? cy.log_all + (size_t)k * cy.log_stride : nullptr;
+                po.lead = b.lead;
                 k4_vehicle(p, po, veh);
                 c_build += tk1 - tk0; c_qp += tk2 - tk1; c_big += tk3 - tk2; c_post += clock64() - tk3;
             }

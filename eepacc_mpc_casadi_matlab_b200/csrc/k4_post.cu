@@ -18,13 +18,17 @@ __global__ void __launch_bounds__(128) k4_kpi_final_kernel(eepacc_params p, long
          veh += (long long)gridDim.x * blockDim.x) {
         const double* A = acc + veh * ACC_W;
         double* K = kpi + veh * EEPACC_N_KPI;
-        double distInd, Ecut, amax, amin, a2;
-        if (A[4] != 0.0) { distInd = A[5]; Ecut = A[13]; amax = A[14]; amin = A[15]; a2 = A[16]; }
-        else { distInd = (double)(n_steps - 1); Ecut = A[2]; amax = A[9]; amin = A[10]; a2 = A[11]; }
+        double distInd, Ecut, amax, amin, a2, jmax, jmin, j2;
+        if (A[4] != 0.0) { distInd = A[5]; Ecut = A[13]; amax = A[14]; amin = A[15]; a2 = A[16]; jmax = A[24]; jmin = A[25]; j2 = A[26]; }
+        else { distInd = (double)(n_steps - 1); Ecut = A[2]; amax = A[9]; amin = A[10]; a2 = A[11]; jmax = A[21]; jmin = A[22]; j2 = A[23]; }
         if (distInd < 1) distInd = 1;
         K[0] = A[0]; K[1] = A[3];
         K[2] = 0.1 * floor(distInd * p.Ts * 10 + 0.5);
         K[3] = Ecut; K[4] = amax; K[5] = amin; K[6] = sqrt(a2 / distInd); K[7] = A[12];
+        const double nj = fmin(distInd, (double)(n_steps - 1));          // j has n-1 entries
+        K[8] = n_steps > 1 ? jmax : 0.0; K[9] = n_steps > 1 ? jmin : 0.0; K[10] = n_steps > 1 ? sqrt(j2 / fmax(nj, 1.0)) : 0.0;
+        K[11] = A[27]; K[12] = A[28]; K[13] = A[29]; K[14] = A[30];
+        K[15] = A[31]; K[16] = A[32]; K[17] = A[33];
     }
 }
 

@@ -7,7 +7,7 @@
 #ifndef N
 #define N EEP_N
 #endif
-#define ACC_W 20
+#define ACC_W 36
 
 __device__ __forceinline__ void k4_vehicle(const eepacc_params& p, const eep_post_io& io, const long long veh)
 {
@@ -70,4 +70,28 @@ __device__ __forceinline__ void k4_vehicle(const eepacc_params& p, const eep_pos
     else { A[6] = fmax(A[6], a_out); A[7] = fmin(A[7], a_out); }
     A[8] += a_out * a_out;
     if (st != 0.0) A[12] += 1.0;
+    // jerk j(i) = (a(i+1) - a(i)) / Ts (RunOpt_FBMPC.m:339), statistics over j(1..distInd) (Main.m:247-250):
+    // [20] a of the previous step, [21..23] running max / min / sum of squares, [24..26] their values at the cut-off
+    if (i1 >= 2) {
+        const double j = (a_out - A[20]) / T;
+        if (i1 == 2) { A[21] = j; A[22] = j; }
+        else { A[21] = fmax(A[21], j); A[22] = fmin(A[22], j); }
+        A[23] += j * j;
+    }
+    A[20] = a_out;
+    if (A[4] == 1.0) { A[4] = 2.0; A[24] = A[21]; A[25] = A[22]; A[26] = A[23]; }   // cut-off found at THIS step: j(distInd) is the newest entry
+    // constraint violations: steps with an active soft constraint ([27..30]) and headway against the lead ([31..33])
+    if (xi0 > 1e-6) A[27] += 1.0;
+    if (xi1 > 1e-6) A[28] += 1.0;
+    if (xi2 > 1e-6) A[29] += 1.0;
+    if (xi3 > 1e-6) A[30] += 1.0;
+    if (io.kk == 0) A[33] = INFINITY;
+    if (io.lead) {
+        const double gap = io.lead[2 * veh] - s0;
+        if (isfinite(gap)) {
+            if (gap < p.h_min) A[31] += 1.0;
+            if (gap < p.tau_min * v0) A[32] += 1.0;
+            A[33] = fmin(A[33], gap);
+        }
+    }
 }

@@ -47,7 +47,7 @@ template <class CT> __device__ __forceinline__ bool rt_primal(const CT& C, int c
     const double rate = s ? db - adx : adx - db;
     double sl = s ? cur - C.Ax[c] : C.Ax[c] - cur;
     if (sl < 0) sl = 0;
-    if (rate < -(EPS_RATE * (1.0 + fabs(adx) + fabs(db)) + rz) && -rate - sl > FEAS_TOL * (1.0 + fabs(nw)) && sl / (-rate) < 1.0) {
+    if (rate < -(EPS_RATE * (1.0 + fabs(adx) + fabs(db)) + rz) && -rate - sl > FEAS_TOL * (1.0 + fabs(nw)) && sl < -rate) {
         num = sl; den = -rate;
         return true;
     }
@@ -60,7 +60,7 @@ __device__ __forceinline__ bool rt_dual(int st, double yc, double dy, double thr
     if (st < 0 && dy < -thr) { num = yc > 0 ? yc : 0; den = -dy; }
     else if (st > 0 && dy > thr) { num = yc < 0 ? -yc : 0; den = dy; }
     else return false;
-    return num / den < 1.0 && den - num > dtol;
+    return num < den && den - num > dtol;
 }
 // primal candidate of the exchange ratio test along d (A d in C.Adx)
 template <class CT> __device__ __forceinline__ bool rt_exch(const CT& C, int c, double dn, int& s, double& num, double& den)

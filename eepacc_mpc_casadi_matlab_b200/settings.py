@@ -13,7 +13,7 @@ import math
 
 N_HOR = 20
 MAX_SL, MAX_CURV, MAX_SLOPE, MAX_STOP, MAX_TL = 16, 48, 24, 8, 4
-N_KPI = 8
+N_KPI = 18
 AB, FB, BL, TV = 0, 1, 2, 3
 CTRL_NAMES = {"ab": AB, "fb": FB, "bl": BL, "tv": TV}
 

@@ -252,10 +252,16 @@ EEPACC_DECLARE(eepacc_step_tv)
  * batched); out: log[n_steps][B][12] = z1[8], a, status, iter, cost (may be NULL);  kpi[B][8]. */
 EEPACC_DECLARE(eepacc_run)
 
-/* KPI block per scenario (Main.m:136-148,218-258; RunOpt_FBMPC.m:334-339):
+/* KPI block per scenario (Main.m:136-148,188-262; RunOpt_FBMPC.m:334-339), what the ranks gather over NCCL:
  * [0] E_opt(end) J   [1] s_opt(end) m   [2] travel time at cutOffDist s   [3] E_opt at cut-off J
- * [4] max a   [5] min a   [6] rms a (over 1..distInd)   [7] failed QPs (sum exitMessage)       */
-#define EEPACC_N_KPI 8
+ * [4] max a   [5] min a   [6] rms a (over 1..distInd)   [7] failed QPs (sum exitMessage)
+ * comfort, Main.m:247-250 (j = diff(a)/Ts over 1..distInd):   [8] max j   [9] min j   [10] rms j
+ * constraint violations, counted over the whole run (steps with a slack above 1e-6, the soft constraints of
+ * CreateQP_FB.m:211-215):   [11] xi_v (speed incentive)   [12] xi_h (desired headway)   [13] xi_s (safe headway /
+ * speed rows)   [14] xi_f (feasibility)
+ * headway against the lead trace (finite s_tv only):   [15] steps with gap < h_min   [16] steps with
+ * gap < tau_min * v   [17] smallest gap m (+inf without a lead)                                                  */
+#define EEPACC_N_KPI 18
 #define EEPACC_N_PERT 16
 
 #ifdef __cplusplus

@@ -976,6 +976,25 @@ void orc_kpi(const eepacc_params* p, double mass_scale, const double* log, int n
     kpi[0] = E; kpi[1] = log[(size_t)(n - 1) * 12];
     kpi[2] = 0.1 * floor(distInd * p->Ts * 10 + 0.5);
     kpi[3] = Ecut; kpi[4] = amax; kpi[5] = amin; kpi[6] = sqrt(a2 / distInd); kpi[7] = fail;
+    /* comfort: j = diff(a)/Ts (RunOpt_FBMPC.m:339), max / min / rms over j(1:distInd) (Main.m:247-250) */
+    {
+        double jmax = 0, jmin = 0, j2 = 0;
+        int nj = distInd < n - 1 ? distInd : n - 1;
+        for (int i = 1; i <= nj; ++i) {
+            double j = (log[(size_t)i * 12 + 8] - log[(size_t)(i - 1) * 12 + 8]) / p->Ts;
+            if (i == 1 || j > jmax) jmax = j;
+            if (i == 1 || j < jmin) jmin = j;
+            j2 += j * j;
+        }
+        kpi[8] = jmax; kpi[9] = jmin; kpi[10] = nj > 0 ? sqrt(j2 / nj) : 0.0;
+    }
+    /* constraint violations: steps with an active soft constraint (xi_v, xi_h, xi_s, xi_f; CreateQP_FB.m:211-215) */
+    for (int q = 0; q < 4; ++q) {
+        double cnt = 0;
+        for (int i = 0; i < n; ++i) if (log[(size_t)i * 12 + 4 + q] > 1e-6) cnt += 1;
+        kpi[11 + q] = cnt;
+    }
+    kpi[15] = 0; kpi[16] = 0; kpi[17] = INFINITY;      /* headway figures need the lead trace: orc_run */
 }
 
 int orc_run(int ctrl, const eepacc_params* p, const eepacc_route* r, const double* lead,
@@ -986,7 +1005,31 @@ int orc_run(int ctrl, const eepacc_params* p, const eepacc_route* r, const doubl
     for (int k = 0; k < n_steps; ++k)
         orc_vehicle_step(v, lead[(size_t)k * lead_stride], lead[(size_t)k * lead_stride + 1],
                          log + (size_t)k * 12);
-    if (kpi) orc_kpi(p, r->mass_scale, log, n_steps, kpi);
+    if (kpi) {
+        orc_kpi(p, r->mass_scale, log, n_steps, kpi);
+        if (ctrl != EEPACC_TV) {               /* headway against the lead trace (the TVMPC has no target vehicle) */
+            for (int k = 0; k < n_steps; ++k) {
+                double gap = lead[(size_t)k * lead_stride] - log[(size_t)k * 12];
+                if (!isfinite(gap)) continue;
+                if (gap < p->h_min) kpi[15] += 1;
+                if (gap < p->tau_min * log[(size_t)k * 12 + 1]) kpi[16] += 1;
+                if (gap < kpi[17]) kpi[17] = gap;
+            }
+        }
+    }
     orc_vehicle_free(v);
+    return 0;
+}
+
+/* B scenarios one after the other (the C-side loop of the CPU baseline: no per-scenario interpreter overhead).
+ * routes[B]; lead [n_steps][B][2] (the engine's layout); kpi [B][EEPACC_N_KPI]; log_scratch [n_steps][12]. */
+int orc_run_batch(int ctrl, const eepacc_params* p, const eepacc_route* routes, const double* lead, long long B,
+                  int n_steps, double* kpi, double* log_scratch)
+{
+    for (long long b = 0; b < B; ++b) {
+        int rc = orc_run(ctrl, p, routes + b, lead + 2 * b, (int)(2 * B), n_steps, log_scratch,
+                         kpi ? kpi + b * EEPACC_N_KPI : 0);
+        if (rc) return rc;
+    }
     return 0;
 }

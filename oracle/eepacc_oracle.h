@@ -105,6 +105,9 @@ void orc_vehicle_get_sol(const orc_vehicle* v, double* x, double* lam_a);
 int orc_run(int ctrl, const eepacc_params* p, const eepacc_route* r, const double* lead,
             int lead_stride, int n_steps, double* log, double* kpi);
 void orc_kpi(const eepacc_params* p, double mass_scale, const double* log, int n_steps, double* kpi);
+/* B scenarios in a C loop (CPU baseline): routes[B], lead [n_steps][B][2], kpi [B][EEPACC_N_KPI], log_scratch [n_steps][12] */
+int orc_run_batch(int ctrl, const eepacc_params* p, const eepacc_route* routes, const double* lead, long long B,
+                  int n_steps, double* kpi, double* log_scratch);
 
 int orc_qp_nvar(int ctrl);
 int orc_qp_ncon(int ctrl, const eepacc_params* p);

@@ -33,6 +33,28 @@ def build(force=False):
     return _LIB
 
 
+def build_fast():
+    """-O3 -march=native build of the same sources, for bench.py's CPU timing arm only (never for parity)."""
+    fast = os.path.join(_HERE, "_build", "liboracle_fast.so")
+    if not os.path.exists(fast) or any(
+            os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(fast)
+            for f in ("eepacc_oracle.c", "qp_oracle.c", "eepacc_oracle.h")):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "fast"])
+    return fast
+
+
+def run_batch_fast(ctrl, params, routes, lead):
+    """Timing arm: B scenarios in one C call of the -O3 -march=native build.  lead [n_steps, B, 2] -> kpi [B, N_KPI]."""
+    L = C.CDLL(build_fast())
+    lead = np.ascontiguousarray(lead, dtype=np.float64)
+    n, B = lead.shape[0], lead.shape[1]
+    kpi = np.zeros((B, N_KPI)); scratch = np.zeros((n, 12))
+    L.orc_run_batch.argtypes = [C.c_int, C.POINTER(Params), C.POINTER(Route), _dp, C.c_longlong, C.c_int, _dp, _dp]
+    rc = L.orc_run_batch(ctrl, C.byref(params), routes, _p(lead), B, n, _p(kpi), _p(scratch))
+    assert rc == 0, rc
+    return kpi
+
+
 _lib = None
 
 

@@ -53,11 +53,13 @@ static int rt_select(const rt_cand* c, int nc)
     double tmax = INFINITY;
     int best = -1;
     for (int i = 0; i < nc; ++i) {
-        double t = (c[i].num + c[i].del) / c[i].den;
+        const double inv = 1.0 / c[i].den;              /* one division per candidate, as in the kernels */
+        double t = (c[i].num + c[i].del) * inv;
         if (t < tmax) tmax = t;
     }
     for (int i = 0; i < nc; ++i) {
-        if (c[i].num / c[i].den <= tmax && (best < 0 || c[i].key < c[best].key)) best = i;
+        const double inv = 1.0 / c[i].den;
+        if (c[i].num * inv <= tmax && (best < 0 || c[i].key < c[best].key)) best = i;
     }
     return best;
 }
@@ -706,7 +708,7 @@ int orc_qpsolve(orc_qpws* w, const double* H, const double* g, const double* A,
                 double sl = w->Ax[c] - w->lb_cur[c]; if (sl < 0) sl = 0;
                 if (rate < -(EPS_RATE * (1.0 + fabs(adx) + fabs(w->dlb[c])) + rz) &&
                     -rate - sl > FEAS_TOL * (1.0 + fabs(w->lb_new[c]))) {
-                    if (sl / (-rate) < 1.0) { cd[nc].num = sl; cd[nc].den = -rate; cd[nc].del = del; cd[nc].key = 2 * c; cd[nc].aux = c; ++nc; }
+                    if (sl < -rate) { cd[nc].num = sl; cd[nc].den = -rate; cd[nc].del = del; cd[nc].key = 2 * c; cd[nc].aux = c; ++nc; }
                 }
             }
             if (!isinf(w->ub_cur[c])) {
@@ -714,7 +716,7 @@ int orc_qpsolve(orc_qpws* w, const double* H, const double* g, const double* A,
                 double sl = w->ub_cur[c] - w->Ax[c]; if (sl < 0) sl = 0;
                 if (rate < -(EPS_RATE * (1.0 + fabs(adx) + fabs(w->dub[c])) + rz) &&
                     -rate - sl > FEAS_TOL * (1.0 + fabs(w->ub_new[c]))) {
-                    if (sl / (-rate) < 1.0) { cd[nc].num = sl; cd[nc].den = -rate; cd[nc].del = del; cd[nc].key = 2 * c + 1; cd[nc].aux = c; ++nc; }
+                    if (sl < -rate) { cd[nc].num = sl; cd[nc].den = -rate; cd[nc].del = del; cd[nc].key = 2 * c + 1; cd[nc].aux = c; ++nc; }
                 }
             }
         }
@@ -732,10 +734,10 @@ int orc_qpsolve(orc_qpws* w, const double* H, const double* g, const double* A,
             const double dtol = fmax(FEAS_TOL * ysc, del);
             if (w->st[c] < 0 && dy < -thr) {
                 double num = (yc > 0 ? yc : 0);
-                if (num / (-dy) < 1.0 && -dy - num > dtol) { cd[nc].num = num; cd[nc].den = -dy; cd[nc].del = del; cd[nc].key = 2 * mt + c; cd[nc].aux = k; ++nc; }
+                if (num < -dy && -dy - num > dtol) { cd[nc].num = num; cd[nc].den = -dy; cd[nc].del = del; cd[nc].key = 2 * mt + c; cd[nc].aux = k; ++nc; }
             } else if (w->st[c] > 0 && dy > thr) {
                 double num = (yc < 0 ? -yc : 0);
-                if (num / dy < 1.0 && dy - num > dtol) { cd[nc].num = num; cd[nc].den = dy; cd[nc].del = del; cd[nc].key = 2 * mt + c; cd[nc].aux = k; ++nc; }
+                if (num < dy && dy - num > dtol) { cd[nc].num = num; cd[nc].den = dy; cd[nc].del = del; cd[nc].key = 2 * mt + c; cd[nc].aux = k; ++nc; }
             }
         }
         {
