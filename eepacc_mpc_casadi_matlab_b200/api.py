@@ -66,6 +66,9 @@ def load_library():
     L.eepacc_mem_set_lead.argtypes = [C.c_int, _dp, C.c_longlong]
     L.eepacc_mem_synth_lead.argtypes = [C.c_int, _dp, C.c_longlong, _dp, C.c_longlong, _dp, C.c_longlong, C.c_double]
     L.eepacc_mem_set_step.argtypes = [C.c_int, C.c_int, C.c_double]
+    L.eepacc_mem_gen_routes.argtypes = [C.c_int, C.c_void_p, C.c_longlong]
+    L.eepacc_mem_fetch_routes.argtypes = [C.c_int, C.c_void_p, C.c_longlong]
+    L.eepacc_sizeof_route_spec.restype = C.c_longlong
     L.eepacc_mem_set_stream.argtypes = [C.c_int, C.c_void_p]
     L.eepacc_mem_launch_count.restype = C.c_longlong
     L.eepacc_mem_get_counters.argtypes = [C.c_int, _dp]
@@ -92,7 +95,8 @@ def load_library():
         getattr(L, f + "_n_in").restype = C.c_longlong
         getattr(L, f + "_n_out").restype = C.c_longlong
         getattr(L, f + "_release").argtypes = [C.c_int]
-    if L.eepacc_sizeof_params() != C.sizeof(S.Params) or L.eepacc_sizeof_route() != C.sizeof(S.Route):
+    if (L.eepacc_sizeof_params() != C.sizeof(S.Params) or L.eepacc_sizeof_route() != C.sizeof(S.Route)
+            or L.eepacc_sizeof_route_spec() != C.sizeof(S.RouteSpec)):
         raise EepaccError("ABI mismatch between settings.py and include/eepacc.h")
     _lib = L
     return L
@@ -163,12 +167,13 @@ class Engine:
         if B is None:
             B = 1 if isinstance(routes, S.Route) else len(routes)
         self.B = int(B)
-        self.routes = routes_array(routes, self.B)
+        # routes=None: the route blocks are built on the device afterwards (gen_routes) -- nothing is uploaded
+        self.routes = routes_array(routes, self.B) if routes is not None else None
         self._fam = ["eepacc_step_ab", "eepacc_step_fb", "eepacc_step_bl", "eepacc_step_tv"][ctrl]
         self.mem = getattr(self.L, self._fam + "_checkout")()
         if self.mem < 0:
             raise EepaccError(self._err())
-        rc = self.L.eepacc_mem_setup(self.mem, ctrl, C.byref(params), self.routes, self.B, device)
+        rc = self.L.eepacc_mem_setup(self.mem, ctrl, C.byref(params), self.routes, self.B, device)     # routes None -> NULL
         if rc:
             msg = self._err()
             self.close()
@@ -254,6 +259,36 @@ class Engine:
         xn = self._out(x, (B, 2))
         self._call("eepacc_plant", [x, u], [xn], B)
         return xn
+
+    # ---- K5r: route previews built on the device ----
+    def gen_routes(self, specs):
+        """specs: usecase.SPEC_DTYPE[B] (spec_table_fast), a RouteSpec ctypes array, or a list of RouteSpec:
+        k5_route_gen_kernel builds the B route blocks in HBM (GenerateUseCase.m + SimplifyPWA.m per scenario) and
+        the closed-loop state is reset."""
+        if isinstance(specs, np.ndarray):
+            specs = np.ascontiguousarray(specs)
+            if specs.shape != (self.B,) or specs.dtype.itemsize != C.sizeof(S.RouteSpec):
+                raise EepaccError("specs must be B eepacc_route_spec records")
+            ptr, keep = specs.ctypes.data, specs
+        else:
+            if isinstance(specs, (list, tuple)):
+                arr = (S.RouteSpec * self.B)()
+                for b in range(self.B):
+                    C.memmove(C.byref(arr[b]), C.byref(specs[b]), C.sizeof(S.RouteSpec))
+                specs = arr
+            ptr, keep = C.addressof(specs), specs
+        rc = self.L.eepacc_mem_gen_routes(self.mem, ptr, self.B)
+        del keep
+        if rc:
+            raise EepaccError(f"eepacc_mem_gen_routes failed ({rc}): {self._err()}")
+
+    def fetch_routes(self):
+        """The mem's B route blocks as a ctypes Route array (tests: bit-compare with usecase.generate_use_case)."""
+        out = (S.Route * self.B)()
+        rc = self.L.eepacc_mem_fetch_routes(self.mem, C.addressof(out), self.B)
+        if rc:
+            raise EepaccError(f"eepacc_mem_fetch_routes failed ({rc}): {self._err()}")
+        return out
 
     # ---- K2 / K3 ----
     def set_step(self, kk, t0):

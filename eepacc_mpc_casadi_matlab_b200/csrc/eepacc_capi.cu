@@ -14,7 +14,7 @@
 #include "eepacc_kernels.h"
 
 #define NH EEPACC_N_HOR
-#define ACC_W 20
+#define ACC_W EEP_ACC_W
 #define MAX_MEM 64
 
 namespace {
@@ -181,7 +181,12 @@ int copy_out(Mem* M, int slot, double* dst, size_t count, bool dev)
 // (also on the error paths: the guard's destructor does it).
 struct DeviceGuard {
     int prev = -1;
-    int enter(int dev) { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; return (int)cudaSetDevice(dev); }
+    int enter(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev == dev) { prev = -1; return 0; }          // already there: nothing to switch, nothing to restore
+        return (int)cudaSetDevice(dev);
+    }
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 struct CallCtx { Mem* M; long long B; bool dev; DeviceGuard guard; };
@@ -446,7 +451,7 @@ int eepacc_mem_setup(int mem, int ctrl, const eepacc_params* p, const eepacc_rou
 {
     Mem* M = get_mem(mem);
     if (!M) return EEPACC_ERR_ARG;
-    if (!p || !routes || B <= 0) return fail(EEPACC_ERR_ARG, "eepacc_mem_setup: bad arguments");
+    if (!p || B <= 0) return fail(EEPACC_ERR_ARG, "eepacc_mem_setup: bad arguments");      // routes == NULL: built later by eepacc_mem_gen_routes
     if (ctrl < EEPACC_AB || ctrl > EEPACC_TV) return fail(EEPACC_ERR_ARG, "unknown controller");
     if (p->N != NH) return fail(EEPACC_ERR_ARG, "params.N must equal EEPACC_N_HOR (20)");
     int ndev = 0;
@@ -478,12 +483,13 @@ int eepacc_mem_setup(int mem, int ctrl, const eepacc_params* p, const eepacc_rou
         { &M->hscr, (size_t)B * 4 * (size_t)(n + m) * 8 }, { &M->defer_list2, (size_t)(B + 1) * 4 },
     };
     for (auto& e : plan) if (e.b->ensure(e.bytes)) return EEPACC_ERR_MEM;
-    CK(cudaMemcpyAsync(M->routes.p, routes, (size_t)B * sizeof(eepacc_route), cudaMemcpyHostToDevice, M->stream));
+    if (routes) CK(cudaMemcpyAsync(M->routes.p, routes, (size_t)B * sizeof(eepacc_route), cudaMemcpyHostToDevice, M->stream));
+    else CK(cudaMemsetAsync(M->routes.p, 0, (size_t)B * sizeof(eepacc_route), M->stream));      // to be built by eepacc_mem_gen_routes
     // FB dynamics rows before the first step (RunOpt_FBMPC.m:78-90)
     {
         std::vector<double> fa((size_t)B * NH), fd((size_t)B * NH);
         for (long long b = 0; b < B; ++b) {
-            double mass = p->m * routes[b].mass_scale;
+            double mass = p->m * (routes ? routes[b].mass_scale : 1.0);      // (K2 rewrites these rows at closed-loop step 0 from the device routes)
             for (int k = 0; k < NH; ++k) {
                 fa[b * NH + k] = 1 - 2 * p->Ts * p->zeta_a * p->v_init * p->v_init / p->lambda / mass;
                 fd[b * NH + k] = p->Ts / p->lambda / mass * (p->zeta_a * p->v_init * p->v_init);
@@ -595,6 +601,46 @@ int eepacc_mem_synth_lead(int mem, const double* base, long long n_base, const d
     M->n_lead = n_steps;
     return EEPACC_OK;
 }
+
+int eepacc_mem_gen_routes(int mem, const eepacc_route_spec* specs, long long B)
+{
+    Mem* M = get_mem(mem);
+    if (!M || !M->ready) return fail(EEPACC_ERR_ARG, "mem not set up");
+    if (!specs || B != M->B) return fail(EEPACC_ERR_ARG, "eepacc_mem_gen_routes: B must equal the batch the mem was set up for");
+    DeviceGuard dg_; CK((cudaError_t)dg_.enter(M->device));
+    const size_t bytes = (size_t)B * sizeof(eepacc_route_spec);
+    if (M->synth_in.ensure(bytes + 16)) return EEPACC_ERR_MEM;
+    char* d = (char*)M->synth_in.p;
+    int* err = (int*)(d + bytes);
+    const int big = 0x7fffffff;
+    CK(cudaMemcpyAsync(d, specs, bytes, cudaMemcpyHostToDevice, M->stream));
+    CK(cudaMemcpyAsync(err, &big, sizeof(int), cudaMemcpyHostToDevice, M->stream));
+    if (eep_launch_route_gen(B, (const eepacc_route_spec*)d, M->routes.as<eepacc_route>(), err, M->stream))
+        return fail(EEPACC_ERR_CUDA, "k5_route_gen_kernel launch");
+    M->launches += 1;
+    int e = 0;
+    CK(cudaMemcpyAsync(&e, err, sizeof(int), cudaMemcpyDeviceToHost, M->stream));
+    CK(cudaStreamSynchronize(M->stream));
+    if (e != big) {
+        static char msg[160];
+        const char* what[] = { "", "speed-limit", "curvature", "slope", "stop / traffic-light" };
+        snprintf(msg, sizeof msg, "eepacc_mem_gen_routes: scenario %d needs more %s points than the route block holds", e / 8, what[e % 8 <= 4 ? e % 8 : 0]);
+        return fail(EEPACC_ERR_ARG, msg);
+    }
+    return reset_state(M);
+}
+
+int eepacc_mem_fetch_routes(int mem, eepacc_route* out, long long B)
+{
+    Mem* M = get_mem(mem);
+    if (!M || !M->ready || !out || B != M->B) return fail(EEPACC_ERR_ARG, "eepacc_mem_fetch_routes: bad arguments");
+    DeviceGuard dg_; CK((cudaError_t)dg_.enter(M->device));
+    CK(cudaStreamSynchronize(M->stream));
+    CK(cudaMemcpy(out, M->routes.p, (size_t)B * sizeof(eepacc_route), cudaMemcpyDeviceToHost));
+    return EEPACC_OK;
+}
+
+long long eepacc_sizeof_route_spec(void) { return (long long)sizeof(eepacc_route_spec); }
 
 int eepacc_mem_set_stream(int mem, void* stream)
 {

@@ -6,6 +6,7 @@
 #define EEPACC_MAX_NVAR 120     // FB: 6*20
 #define EEPACC_MAX_NCON 522     // FB: 26*20+2
 #define EEPACC_LOG_W    12      // z1[8], a, status, iter, cost
+#define EEP_ACC_W       36      // running KPI accumulators per vehicle (k4_post.cuh); ONE definition for the kernels and the host side
 
 // Structured per-vehicle QP block written by K2 for K3's matrix-free path (doubles):
 //   PS/PV [(N+1) x N]  d s_k, v_k / d (driven control of stage i);  VEST [N] v_est(k);
@@ -106,6 +107,23 @@ struct eep_cycle_io {
 };
 
 #ifdef __cplusplus
+// Dynamic shared-memory opt-in of a kernel, cached PER DEVICE (the attribute is per device; calling
+// cudaFuncSetAttribute before each of the ~55 000 launches of a cycle costs several per cent of the cycle).
+// `slot` is a per-kernel static array of EEP_MAX_DEV entries, zero-initialised.
+#define EEP_MAX_DEV 64
+template <class K> static inline int eep_optin_smem(K kernel, size_t bytes, size_t* slot)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= EEP_MAX_DEV) dev = -1;
+    if (dev >= 0 && bytes <= slot[dev]) return 0;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return (int)e;
+    if (dev >= 0) slot[dev] = bytes;
+    return 0;
+}
+#endif
+
+#ifdef __cplusplus
 extern "C" {
 #endif
 int eep_launch_cycle(const eepacc_params* p, const eep_cycle_io* cy, int grid, cudaStream_t st);
@@ -126,6 +144,7 @@ size_t eep_qp_smem_bytes(int n, int m, int smode);
 int eep_launch_post(const eepacc_params* p, const eep_post_io* io, cudaStream_t st);
 int eep_launch_lead_synth(long long B, int n_steps, double ts, double tv_length, const double* base, int n_base,
                           const double* hw, int n_hw, const double* pert, double* lead, cudaStream_t st);
+int eep_launch_route_gen(long long B, const eepacc_route_spec* specs, eepacc_route* routes, int* err, cudaStream_t st);
 int eep_launch_kpi_final(const eepacc_params* p, long long B, int n_steps, const double* kpi_acc, double* kpi, cudaStream_t st);
 double eep_dfma_peak(int device);
 #ifdef __cplusplus

@@ -28,10 +28,8 @@ extern "C" size_t eep_build_smem_bytes() { return sizeof(BuildSmem); }
 extern "C" int eep_launch_build(const eepacc_params* p, const eep_build_io* io, cudaStream_t st)
 {
     size_t sm = sizeof(BuildSmem);
-    {   // per-device opt-in: set on every launch (cheap), never cached process-wide
-        cudaError_t e = cudaFuncSetAttribute(k2_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        if (e != cudaSuccess) return (int)e;
-    }
+    static size_t optin[EEP_MAX_DEV];                    // per device (eep_optin_smem)
+    if (int e = eep_optin_smem(k2_build_kernel, sm, optin)) return e;
     long long g = io->B;
     const long long cap = 148LL * 8;
     if (g > cap) g = cap;

@@ -23,6 +23,7 @@ struct BuildSmem {
     double tv[N + 1];                       // t(v_k) = (Hs d + cs)(v_k)
     double MV[N][EEPACC_MAX_NVAR];          // (Hs Psi)(v_k, j)
     double s_meas, v_meas, a_minus1, s_tv, v_tv, a_tv, t0;
+    alignas(16) eepacc_route route;         // this vehicle's route preview, staged once per step (K5)
 };
 
 __device__ __forceinline__ void add3(double* D, int W, const int* ii, const double* M, int n, double sc)
@@ -171,10 +172,20 @@ __device__ void k2_vehicle(const eepacc_params& p, const eep_build_io& io, const
     const int W = 1 + nu;
     const int n = N * nu, m = io.m;
 
-    const eepacc_route* r = io.routes + veh * io.route_stride;
-    const double mass = p.m * r->mass_scale;
     const double T = p.Ts;
     __syncthreads();
+    // K5: the route preview (1 KB, contiguous) is pulled into shared memory ONCE per vehicle and step with
+    // coalesced 16-byte loads; the plant step (InterpPWA inside every RK4 stage) and the 20 per-stage bound
+    // look-ups then walk shared memory instead of chasing the block through global memory.
+    {
+        static_assert(sizeof(eepacc_route) % 16 == 0, "route block must be a whole number of 16-byte words");
+        const double2* src = reinterpret_cast<const double2*>(io.routes + veh * io.route_stride);
+        double2* dst = reinterpret_cast<double2*>(&S.route);
+        for (int e = tid; e < (int)(sizeof(eepacc_route) / 16); e += NTB) dst[e] = __ldg(src + e);
+    }
+    __syncthreads();
+    const eepacc_route* r = &S.route;
+    const double mass = p.m * r->mass_scale;
     // ---------- measurement + estimators (one thread; RunOpt_FBMPC.m:166-208) ----------
     if (tid == 0) {
         double s_meas, v_meas, a_m1, s_tv = 0, v_tv = 0, a_tv = 0, t0;

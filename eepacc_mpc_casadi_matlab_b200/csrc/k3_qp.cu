@@ -409,7 +409,9 @@ __device__ int givens_add(Ctx& C, int cidx, int side, const double* a, int nZt, 
             }
             MM(i, nR - 1) = u;
         }
-        // R phase B: re-triangularise (row rotations), wavefront over k
+        // R phase B: re-triangularise (row rotations), wavefront over k.  (Measured: with up to 120 columns the whole
+        // CTA per rotation beats the one-warp chain of qp_rules.cuh that the reduced-space kernel uses: 29.8 M vs
+        // 32.1 M cycles of working-set changes per cold start.)
         for (int k = 0; k < nR - 1; ++k) {
             __syncthreads();
             double pa = MM(k, k), pb = C.sub[k + 1];
@@ -1343,11 +1345,8 @@ extern "C" size_t eep_qp_smem_bytes(int n, int m, int smode)
 extern "C" int eep_launch_qp(const eepacc_params* p, const eep_qp_io* io, cudaStream_t st)
 {
     size_t sm = eep_qp_smem_bytes(io->n, io->m, io->sblk != nullptr);
-    // the opt-in is per device: set it on every launch (cheap) rather than caching it in a process-wide static
-    {
-        cudaError_t e = cudaFuncSetAttribute(k3_qp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        if (e != cudaSuccess) return (int)e;
-    }
+    static size_t optin[EEP_MAX_DEV];                    // per device (eep_optin_smem)
+    if (int e = eep_optin_smem(k3_qp_kernel, sm, optin)) return e;
     long long g = io->B;               // one CTA per vehicle: the hardware scheduler balances uneven solves
     if (io->todo_list && g > (io->todo_grid > 0 ? io->todo_grid : 148)) g = (io->todo_grid > 0 ? io->todo_grid : 148);      // fallback mode: a few persistent CTAs walk the (short) hand-over list
     if (g < 1) g = 1;

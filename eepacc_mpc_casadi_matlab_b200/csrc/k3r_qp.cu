@@ -564,27 +564,9 @@ template <class CT> K3R_FN __device__ int givens_add(CT& C, int cidx, int side, 
         // 0..j, one after the other, and rotation k is defined by column k once rotations 0..k-1 have passed over it:
         // ONE WARP walks the chain with lane j owning column j (shuffles, no block barrier per rotation).
 #ifndef EEP_HOST_EMU
-        if (nR <= 32) {
-            __syncthreads();
-            if (threadIdx.x < 32) {
-                const int j = threadIdx.x;
-                for (int k = 0; k < nR - 1; ++k) {
-                    double c2 = 1.0, s2 = 0.0, rr = 0.0;
-                    if (j == k) {
-                        const double pa = MM(k, k), pb = C.sub[k + 1];
-                        rr = hypot(pa, pb);
-                        if (rr != 0.0) { c2 = pa / rr; s2 = pb / rr; MM(k, k) = rr; }
-                    }
-                    c2 = __shfl_sync(0xffffffffu, c2, k); s2 = __shfl_sync(0xffffffffu, s2, k); rr = __shfl_sync(0xffffffffu, rr, k);
-                    if (rr != 0.0 && j > k && j < nR) {
-                        const double u = MM(k, j), v = MM(k + 1, j);
-                        MM(k, j) = c2 * u + s2 * v;
-                        MM(k + 1, j) = -s2 * u + c2 * v;
-                    }
-                }
-            }
-        } else
-#endif
+        __syncthreads();
+        if (threadIdx.x < 32) warp_chain_rows(C, nR);
+#else
         for (int k = 0; k < nR - 1; ++k) {
             __syncthreads();
             double pa = MM(k, k), pb = C.sub[k + 1];
@@ -600,6 +582,7 @@ template <class CT> K3R_FN __device__ int givens_add(CT& C, int cidx, int side, 
                 }
             }
         }
+#endif
     }
     __syncthreads();
     // new T row = M row nZt-1 (columns >= nZt-1)
@@ -631,30 +614,9 @@ template <class CT> K3R_FN __device__ void remove_general(CT& C, int rp)
     // after the other, and rotation r is defined by row r once rotations rp..r+1 have passed over it: ONE WARP
     // walks the chain with a lane per row (shuffles instead of two block barriers per rotation).
 #ifndef EEP_HOST_EMU
-    if (rp - nZ <= 32) {
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            const int rr = rp - (int)threadIdx.x;           // lane l owns row rp - l
-            for (int r = rp; r > nZ; --r) {
-                const int src = rp - r;
-                double cs = 1.0, sn = 0.0;
-                if (rr == r) {
-                    const double a = C.sub[r], b = MM(r, r);
-                    const double rho = hypot(a, b);
-                    if (rho != 0.0) { cs = b / rho; sn = a / rho; }
-                    C.csA[r] = cs; C.snA[r] = sn;
-                    MM(r, r) = sn * a + cs * b;
-                }
-                cs = __shfl_sync(0xffffffffu, cs, src); sn = __shfl_sync(0xffffffffu, sn, src);
-                if (rr < r && rr > nZ) {
-                    const double u = MM(rr, r - 1), v = MM(rr, r);
-                    MM(rr, r - 1) = cs * u - sn * v;
-                    MM(rr, r) = sn * u + cs * v;
-                }
-            }
-        }
-    } else
-#endif
+    __syncthreads();
+    if (threadIdx.x < 32) warp_chain_cols(C, rp, nZ);
+#else
     for (int r = rp; r > nZ; --r) {
         __syncthreads();
         double a = C.sub[r], b = MM(r, r);
@@ -671,6 +633,7 @@ template <class CT> K3R_FN __device__ void remove_general(CT& C, int rp)
             MM(rr, r) = sn * u + cs * v;
         }
     }
+#endif
     __syncthreads();
     K3R_LOOP for (int i = threadIdx.x; i < nF; i += NT) {
         if (rp > nZ) {
@@ -1974,11 +1937,8 @@ template <int NU, int NB>
 static int launch_qpr(const eep_qp_io* io, cudaStream_t st)
 {
     const size_t sm = eep_qpr_smem_bytes(io->n, io->m, io->fc);
-    // the opt-in is per device: set it on every launch (cheap) rather than caching it in a process-wide static
-    {
-        cudaError_t e = cudaFuncSetAttribute(k3r_qp_kernel<NU, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        if (e != cudaSuccess) return (int)e;
-    }
+    static size_t optin[EEP_MAX_DEV];                    // per device and per instantiation (eep_optin_smem)
+    if (int e = eep_optin_smem(k3r_qp_kernel<NU, NB>, sm, optin)) return e;
     long long g = io->B;               // one CTA per vehicle: the hardware scheduler balances uneven solves
     if (io->todo_list) {                         // hand-over list: a few persistent CTAs walk it
         const long long cap = io->todo_grid > 0 ? io->todo_grid : 148;

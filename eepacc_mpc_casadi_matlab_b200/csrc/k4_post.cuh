@@ -7,7 +7,7 @@
 #ifndef N
 #define N EEP_N
 #endif
-#define ACC_W 36
+#define ACC_W EEP_ACC_W
 
 __device__ __forceinline__ void k4_vehicle(const eepacc_params& p, const eep_post_io& io, const long long veh)
 {

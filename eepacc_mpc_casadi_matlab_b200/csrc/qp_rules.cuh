@@ -71,3 +71,56 @@ template <class CT> __device__ __forceinline__ bool rt_exch(const CT& C, int c, 
     if (adx > rz && !isinf(C.ubc[c])) { double sl = C.ubc[c] - C.Ax[c]; if (sl < 0) sl = 0; s = 1; num = sl; den = adx; return true; }
     return false;
 }
+
+// ---- sequential Givens chains walked by ONE WARP (both kernels; MM(r, c) = packed triangle of the including file) ----
+// The two wavefronts of a working-set change are chains: rotation k is only defined once rotation k-1 has passed over
+// one column (row) of the triangle.  Walking them with the whole CTA costs two block barriers per rotation; here warp 0
+// walks the chain alone, lane l owning the columns (rows) l, l+32, l+64, ..., and hands the rotation on by shuffle.
+#ifndef EEP_HOST_EMU
+// re-triangularise after the column rotations of an addition: row rotations k = 0..nR-2 on rows (k, k+1); the
+// sub-diagonal entry (k+1, k) is in C.sub[k+1].  Call with every thread of warp 0.
+template <class CT> __device__ __forceinline__ void warp_chain_rows(CT& C, int nR)
+{
+    const int lane = threadIdx.x & 31;
+    for (int k = 0; k < nR - 1; ++k) {
+        double c2 = 1.0, s2 = 0.0, rr = 0.0;
+        if (lane == (k & 31)) {
+            const double pa = MM(k, k), pb = C.sub[k + 1];
+            rr = hypot(pa, pb);
+            if (rr != 0.0) { c2 = pa / rr; s2 = pb / rr; MM(k, k) = rr; }
+        }
+        c2 = __shfl_sync(0xffffffffu, c2, k & 31); s2 = __shfl_sync(0xffffffffu, s2, k & 31); rr = __shfl_sync(0xffffffffu, rr, k & 31);
+        if (rr != 0.0)
+            for (int j = lane; j < nR; j += 32)
+                if (j > k) {
+                    const double u = MM(k, j), v = MM(k + 1, j);
+                    MM(k, j) = c2 * u + s2 * v;
+                    MM(k + 1, j) = -s2 * u + c2 * v;
+                }
+    }
+}
+// restore the triangle after a removal: column rotations r = rp .. nZ+1 on columns (r-1, r) over the rows nZ+1..r; the
+// entry (r, r-1) is in C.sub[r].  Leaves the rotations in C.csA / C.snA for the Q update.  Call with every thread of warp 0.
+template <class CT> __device__ __forceinline__ void warp_chain_cols(CT& C, int rp, int nZ)
+{
+    const int lane = threadIdx.x & 31;
+    for (int r = rp; r > nZ; --r) {
+        const int src = (rp - r) & 31;
+        double cs = 1.0, sn = 0.0;
+        if (lane == src) {
+            const double a = C.sub[r], b = MM(r, r);
+            const double rho = hypot(a, b);
+            if (rho != 0.0) { cs = b / rho; sn = a / rho; }
+            C.csA[r] = cs; C.snA[r] = sn;
+            MM(r, r) = sn * a + cs * b;
+        }
+        cs = __shfl_sync(0xffffffffu, cs, src); sn = __shfl_sync(0xffffffffu, sn, src);
+        for (int rr = rp - lane; rr > nZ; rr -= 32)
+            if (rr < r) {
+                const double u = MM(rr, r - 1), v = MM(rr, r);
+                MM(rr, r - 1) = cs * u - sn * v;
+                MM(rr, r) = sn * u + cs * v;
+            }
+    }
+}
+#endif

@@ -62,6 +62,20 @@ class Route(C.Structure):
     ]
 
 
+SPEC_MAX_ZONE, SPEC_MAX_CURVE, SPEC_MAX_SLOPE = 6, 12, 10      # eepacc.h EEPACC_SPEC_MAX_*
+
+
+class RouteSpec(C.Structure):
+    """eepacc_route_spec: what GetUseCase.m / a scenario draw specifies; the device builds the Route from it."""
+    _fields_ = [
+        ("zones", (C.c_double * 2) * SPEC_MAX_ZONE), ("curves", (C.c_double * 3) * SPEC_MAX_CURVE),
+        ("slopes", (C.c_double * 3) * SPEC_MAX_SLOPE), ("stops", C.c_double * MAX_STOP),
+        ("tls", (C.c_double * 4) * MAX_TL), ("mass_scale", C.c_double),
+        ("n_zone", C.c_int), ("n_curve", C.c_int), ("n_slope", C.c_int), ("n_stop", C.c_int),
+        ("n_tl", C.c_int), ("pad_", C.c_int),
+    ]
+
+
 B_QUADR = [185, 1.296e-20, 2.301, 0, 0.003728, -0.000181]                 # Settings.m:227
 B_FIFTH = [185, 0.427461350854152, 1.33881428409239, 0,                  # Settings.m:228-236
            0.00357911242725773, -0.000183195720362408, 0,

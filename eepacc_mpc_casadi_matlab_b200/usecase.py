@@ -10,7 +10,8 @@ import os
 
 import numpy as np
 
-from .settings import (MAX_CURV, MAX_SL, MAX_SLOPE, MAX_STOP, MAX_TL, Route)
+from .settings import (MAX_CURV, MAX_SL, MAX_SLOPE, MAX_STOP, MAX_TL, Route, RouteSpec, SPEC_MAX_CURVE, SPEC_MAX_SLOPE,
+                       SPEC_MAX_ZONE)
 
 
 def simplify_pwa(doms, vals):
@@ -45,7 +46,7 @@ def simplify_pwa(doms, vals):
 
 
 def generate_use_case(speed_lim_zones=None, curves=None, slopes=None, stops=(), tls=(),
-                      mass_scale=1.0):
+                      mass_scale=1.0, slopes_are_angles=False):
     """GenerateUseCase.m -> Route.  speed_lim_zones [[km/h, start m]], curves [[1/m, s0, s1]],
     slopes [[%, s0, s1]], stops [m], tls [[pos, phase, red, green]]."""
     if speed_lim_zones is None or len(speed_lim_zones) == 0:
@@ -81,7 +82,8 @@ def generate_use_case(speed_lim_zones=None, curves=None, slopes=None, stops=(), 
     for s in slopes:
         for i in range(int(s[1]), int(s[2]) + 1):
             sl[i - 1] = s[0]
-    sl = [math.atan(v / 100) for v in sl]
+    if not slopes_are_angles:                  # a route spec (route_spec / spec_table_fast) carries atan(% / 100) already
+        sl = [math.atan(v / 100) for v in sl]
     s_s, sl = simplify_pwa(range(1, n + 1), sl)
     return make_route(s_sl, v_sl, s_c, curv, s_s, sl, stops, tls, mass_scale)
 
@@ -103,6 +105,129 @@ def make_route(s_sl, v_sl, s_c, curv, s_s, sl, stops=(), tls=(), mass_scale=1.0)
     r.n_stop, r.n_tl = len(stops), len(tls)
     r.mass_scale = float(mass_scale)
     return r
+
+
+def route_spec(speed_lim_zones=None, curves=None, slopes=None, stops=(), tls=(), mass_scale=1.0):
+    """The arguments of generate_use_case as an eepacc_route_spec block for the DEVICE route generator
+    (k5_route_gen_kernel, Engine.gen_routes).  Slopes go in as angles: atan(percent / 100), GenerateUseCase.m:104."""
+    sp = RouteSpec()
+    for name, rows, cap in (("zones", speed_lim_zones or [], SPEC_MAX_ZONE), ("curves", curves or [], SPEC_MAX_CURVE),
+                            ("slopes", slopes or [], SPEC_MAX_SLOPE), ("tls", list(tls), MAX_TL)):
+        if len(rows) > cap:
+            raise ValueError(f"{name}: {len(rows)} entries exceed the spec block capacity {cap}")
+        for i, row in enumerate(rows):
+            row = [float(a) for a in row]
+            if name == "slopes":
+                row[0] = math.atan(row[0] / 100)
+            getattr(sp, name)[i][:] = row
+    if len(stops) > MAX_STOP:
+        raise ValueError("too many stops")
+    sp.stops[:len(stops)] = [float(a) for a in stops]
+    sp.n_zone, sp.n_curve, sp.n_slope = len(speed_lim_zones or []), len(curves or []), len(slopes or [])
+    sp.n_stop, sp.n_tl = len(stops), len(tls)
+    sp.mass_scale = float(mass_scale)
+    return sp
+
+
+SPEC_DTYPE = np.dtype([("zones", "f8", (SPEC_MAX_ZONE, 2)), ("curves", "f8", (SPEC_MAX_CURVE, 3)),
+                       ("slopes", "f8", (SPEC_MAX_SLOPE, 3)), ("stops", "f8", (MAX_STOP,)), ("tls", "f8", (MAX_TL, 4)),
+                       ("mass_scale", "f8"), ("n_zone", "i4"), ("n_curve", "i4"), ("n_slope", "i4"), ("n_stop", "i4"),
+                       ("n_tl", "i4"), ("pad_", "i4")], align=True)
+SPEC_K = 96      # uniforms consumed per scenario by spec_table_fast
+
+
+def spec_table_fast(B, first=0, seed=0xEE9ACC, full_route=True, mass=False):
+    """Vectorised scenario draw for the large sweeps of BASELINE config 4 (10^6 scenarios in about a second instead
+    of minutes of per-scenario Python): the Philox stream with key = seed is advanced to position first * SPEC_K, so
+    scenario b always consumes uniforms [b * SPEC_K, (b + 1) * SPEC_K) -- the table is independent of how the batch
+    is partitioned over ranks.  Returns (pert float64[B, N_PERT], specs: SPEC_DTYPE[B] = eepacc_route_spec blocks).
+    Same distributions as perturbation_table, a different stream: the two tables are
+    different scenario sets.  Curves, slopes, stops and lights only with full_route."""
+    bg = np.random.Philox(key=seed)
+    bg.advance(int(first) * (SPEC_K // 4))         # Philox4x64: one counter step = four 64-bit outputs
+    U = np.ascontiguousarray(np.random.Generator(bg).random((B, SPEC_K)).T)       # [SPEC_K, B]: one row per draw
+    u = iter(range(SPEC_K))
+
+    def col():
+        return U[next(u)]
+    pert_t = np.zeros((N_PERT, B))
+    pert_t[0] = 0.85 + 0.30 * col()
+    pert_t[1] = np.floor(21 * col())
+    pert_t[2] = 6.0 + 24.0 * col()
+    for r in range(3):
+        pert_t[3 + 3 * r] = 0.3 * col()
+        pert_t[4 + 3 * r] = 0.01 + 0.09 * col()
+        pert_t[5 + 3 * r] = 2 * math.pi * col()
+    pert = np.ascontiguousarray(pert_t.T)
+    sp = np.zeros(B, dtype=SPEC_DTYPE)
+    # speed zones [60, 0; 50, 1000], each limit +{-10, 0, +10} km/h, the change point +U[-200, 200] m
+    zones = np.zeros((SPEC_MAX_ZONE, 2, B))
+    zones[0, 0] = 60 + 10 * (np.floor(3 * col()) - 1)
+    zones[1, 0] = 50 + 10 * (np.floor(3 * col()) - 1)
+    zones[1, 1] = np.maximum(50.0, np.round(1000 + (-200 + 400 * col())))
+    sp["zones"] = zones.transpose(2, 0, 1)
+    sp["n_zone"] = 2
+    cm = col()
+    sp["mass_scale"] = (0.9 + 0.2 * cm) if mass else 1.0
+    if full_route:
+        sp["n_curve"] = np.floor(11 * col()).astype(np.int32)           # 0..10 curves
+        curves = np.zeros((SPEC_MAX_CURVE, 3, B))
+        pos = np.full(B, 150.0)
+        for k in range(10):
+            pos = pos + 100 + 500 * col()
+            ln = 5 + 345 * col()
+            sign = np.where(col() < 0.5, -1.0, 1.0)
+            curves[k, 0] = sign / (9 + 66 * col())
+            curves[k, 1] = np.floor(pos)
+            curves[k, 2] = np.floor(pos + ln)
+            pos = pos + ln
+        sp["curves"] = curves.transpose(2, 0, 1)
+        sp["n_stop"] = np.floor(6 * col()).astype(np.int32)             # 0..5 stops, sorted
+        stops = np.zeros((MAX_STOP, B))
+        stops[:5] = np.sort(200 + 3800 * np.stack([col() for _ in range(5)]), axis=0)
+        sp["stops"] = stops.T
+        sp["n_tl"] = np.floor(4 * col()).astype(np.int32)               # 0..3 traffic lights
+        tls = np.zeros((MAX_TL, 4, B))
+        for k in range(3):
+            tls[k, 0] = 200 + 3800 * col()
+            tls[k, 1] = 20 * col()
+            tls[k, 2] = 10 + 7 * col()
+            tls[k, 3] = 10 + 5 * col()
+        sp["tls"] = tls.transpose(2, 0, 1)
+        sp["n_slope"] = np.floor(4 * col()).astype(np.int32)            # 0..3 slope segments of 0-8 %
+        slopes = np.zeros((SPEC_MAX_SLOPE, 3, B))
+        pos = np.full(B, 100.0)
+        for k in range(3):
+            pos = pos + 100 + 700 * col()
+            ln = 50 + 350 * col()
+            slopes[k, 0] = np.arctan(8 * col() / 100)
+            slopes[k, 1] = np.floor(pos)
+            slopes[k, 2] = np.floor(pos + ln)
+            pos = pos + ln
+        sp["slopes"] = slopes.transpose(2, 0, 1)
+    if first == 0 and B > 0:                       # global scenario 0 is the unperturbed golden case
+        pert[0] = 0.0
+        pert[0, 0], pert[0, 2] = 1.0, 10.0
+        sp[0] = np.zeros((), dtype=SPEC_DTYPE)
+        sp["n_zone"][0] = 2
+        sp["zones"][0, 0], sp["zones"][0, 1] = (60.0, 0.0), (50.0, 1000.0)
+        sp["mass_scale"][0] = 1.0
+    return pert, sp
+
+
+def spec_to_route(sp):
+    """Host statement of k5_route_gen_kernel for ONE spec (a RouteSpec or a SPEC_DTYPE record): generate_use_case on
+    the same lists (slopes converted back to percent only formally: the angle is passed through unchanged)."""
+    def lst(name, n, w):
+        a = np.asarray(sp[name] if isinstance(sp, np.void) else np.ctypeslib.as_array(getattr(sp, name)))
+        return [[float(x) for x in a[i][:w]] for i in range(int(n))]
+    g = (lambda k: sp[k]) if isinstance(sp, np.void) else (lambda k: getattr(sp, k))
+    zones = lst("zones", g("n_zone"), 2)
+    curves = lst("curves", g("n_curve"), 3)
+    slopes = lst("slopes", g("n_slope"), 3)
+    stops = [float(x) for x in np.asarray(g("stops") if isinstance(sp, np.void) else np.ctypeslib.as_array(sp.stops))[:int(g("n_stop"))]]
+    tls = lst("tls", g("n_tl"), 4)
+    return generate_use_case(zones, curves, slopes, stops, tls, float(g("mass_scale")), slopes_are_angles=True)
 
 
 def default_route(mass_scale=1.0):

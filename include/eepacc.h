@@ -133,6 +133,28 @@ int eepacc_mem_set_lead(int mem, const double* lead, long long n_steps);
  * phase rad), use-highway flag, 3 spare.  Result: the same device buffer eepacc_mem_set_lead fills. */
 int eepacc_mem_synth_lead(int mem, const double* base, long long n_base, const double* hw, long long n_hw,
                           const double* pert, long long n_steps, double tv_length);
+/* Route previews built on the device (replaces the host loop GenerateUseCase.m:50-107 + SimplifyPWA.m:14-49 per
+ * scenario): what GetUseCase.m / the scenario draw specifies, one block per scenario.  Slopes are given as angles
+ * (atan(percent / 100), GenerateUseCase.m:104, evaluated by the caller so that host and device agree bit for bit). */
+#define EEPACC_SPEC_MAX_ZONE  6
+#define EEPACC_SPEC_MAX_CURVE 12
+#define EEPACC_SPEC_MAX_SLOPE 10
+typedef struct eepacc_route_spec {
+    double zones[EEPACC_SPEC_MAX_ZONE][2];      /* [speed limit km/h, start m]; an empty list = no limit (1e5)      */
+    double curves[EEPACC_SPEC_MAX_CURVE][3];    /* [curvature 1/m, s0 m, s1 m]                                      */
+    double slopes[EEPACC_SPEC_MAX_SLOPE][3];    /* [angle rad, s0 m, s1 m]                                          */
+    double stops[EEPACC_MAX_STOP];
+    double tls[EEPACC_MAX_TL][4];               /* [pos, phase, red, green]                                         */
+    double mass_scale;
+    int    n_zone, n_curve, n_slope, n_stop, n_tl, pad_;
+} eepacc_route_spec;
+/* Build the B route blocks of a set-up mem from B specs (host pointer) with k5_route_gen_kernel and make them the mem's
+ * routes; the closed-loop state is reset.  Fails (EEPACC_ERR_ARG) if a scenario's PWA needs more points than the route
+ * block holds; eepacc_last_error() names the first such scenario. */
+int eepacc_mem_gen_routes(int mem, const eepacc_route_spec* specs, long long B);
+/* Copy the mem's B route blocks back to the host (tests: bit-compare with the host statement). */
+int eepacc_mem_fetch_routes(int mem, eepacc_route* out, long long B);
+long long eepacc_sizeof_route_spec(void);
 /* CUDA stream (cudaStream_t as void*) the mem launches on; default stream if never set. */
 int eepacc_mem_set_stream(int mem, void* stream);
 /* Number of kernel launches issued through this mem so far (bench.py's gpu_launches). */

@@ -20,14 +20,24 @@ KEYS = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "dra
         "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
         "smsp__issue_active.avg.pct", "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
         "smsp__average_warp_latency_issue_stalled_barrier.pct", "sm__cycles_active.avg", "sm__cycles_elapsed.max"]
+KEYS += ["sm__inst_executed.avg.per_cycle_active", "smsp__warps_eligible.avg.per_cycle_active",
+         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+         "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "l1tex__throughput.avg.pct_of_peak_sustained_active",
+         "sm__sass_inst_executed_op_shared_ld.sum", "sm__sass_inst_executed_op_shared_st.sum", "smsp__inst_executed.sum",
+         "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct"]
+KEYS += sorted(k for k in hdr if k.startswith("smsp__average_warps_issue_stalled_") and k.endswith("_per_issue_active.ratio")
+               and k not in KEYS)
 out = []
 tot = []
+fp64 = []
 for d in data:
     rec = dict(zip(hdr, d))
     out.append("--- launch ---")
     for k in KEYS:
         if k in rec:
             out.append(f"{k:75s} {rec[k]:>18s} {units[hdr.index(k)]}")
+    if "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active" in rec:
+        fp64.append(float(rec["sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"].replace(",", "")) / 100.0)
 
     def num(k):
         v = float(rec[k].replace(",", ""))
@@ -40,6 +50,9 @@ print(f"DRAM bytes per launch (mean of {len(tot)}): {sum(tot) / len(tot):.0f}  -
 tj_path = os.path.join(ROOT, "profiles", "k3r_traffic.json")
 tj = json.load(open(tj_path))
 tj[ctrl] = {"dram_bytes_per_vehicle": per, "vehicles_per_launch": veh,
+            "fp64_pipe_active_frac": (sum(fp64) / len(fp64)) if fp64 else None,
+            "capture": f"profiles/{os.path.basename(rep).replace('.ncu-rep', '')}_summary.txt: ncu --set full, sm__pipe_fp64_cycles_active "
+                       f"(share of active cycles) of {len(tot)} k3r_qp_kernel launches of {veh} vehicles",
             "source": f"profiles/{os.path.basename(rep).replace('.ncu-rep', '')}_summary.txt (dram__bytes_read.sum + "
                       f"dram__bytes_write.sum, mean of {len(tot)} k3r_qp_kernel launches)"}
 json.dump(tj, open(tj_path, "w"), indent=1)

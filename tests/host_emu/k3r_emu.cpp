@@ -24,6 +24,7 @@ struct EmuIdx { int x; };
 static const EmuIdx threadIdx = { 0 }, blockIdx = { 0 }, gridDim = { 1 };
 static inline void __syncthreads() {}
 static inline double __shfl_xor_sync(unsigned, double v, int) { return v; }
+template <class T> static inline T __ldg(const T* p) { return *p; }
 #include "../../eepacc_mpc_casadi_matlab_b200/csrc/k3r_qp.cu"
 #include "../../eepacc_mpc_casadi_matlab_b200/csrc/k2_build.cuh"
 #include "../../eepacc_mpc_casadi_matlab_b200/csrc/k4_post.cuh"

@@ -112,3 +112,27 @@ def test_device_pointer_mode_matches_host_mode(lead_urban):
         d = b.step(torch.from_numpy(lead_urban[k:k + 1].copy()).cuda())
         assert np.array_equal(h["z1"], d["z1"].cpu().numpy())
     a.close(); b.close()
+
+
+def test_two_devices_in_one_process(lead_urban):
+    """The dynamic shared-memory opt-in of the kernels is per device: an Engine on device 1 created after one on
+    device 0 has run must work (it used to be cached process-wide), give the same bits, and leave the caller's
+    current device alone."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    api = _api()
+    p = S.default_params("mc")
+    y = np.r_[0.0, np.diff(lead_urban[:, 0]) / p.Ts][:871]
+    routes, lead = U.perturbed_scenarios(40, y, n_steps=30)
+    logs = []
+    torch.cuda.set_device(0)
+    for dev in (0, 1, 0):
+        eng = api.Engine("fb", p, routes, B=40, device=dev)
+        assert eng.device_index == dev
+        eng.set_lead(lead)
+        log, _ = eng.run(30)
+        logs.append(log.copy())
+        eng.close()
+        assert torch.cuda.current_device() == 0
+    assert np.array_equal(logs[0], logs[1]) and np.array_equal(logs[0], logs[2])
