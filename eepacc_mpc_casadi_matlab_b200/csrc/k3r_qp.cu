@@ -49,7 +49,10 @@
 #ifdef K3R_NOINLINE
 #define K3R_FN __noinline__
 #else
-#define K3R_FN
+// Every primitive is inlined into the kernel: the solver context (some 60 pointers and sizes) then lives in registers.
+// Left to the inliner's budget, one instantiation (ABMPC) kept a call and with it a 912-byte stack frame holding the
+// context: every C.member access became a local-memory load and the kernel ran 30 % slower.
+#define K3R_FN __forceinline__
 #endif
 #define EMU_ONLY(...)
 #define LDG(p) __ldg(p)
@@ -108,6 +111,7 @@ struct CtxT {
     double* red;
     int* ired;
     double* tt;                 // [(2 ceil(mt/NT) + ceil(n/NT)) NT] ratios of the ratio-test candidates (pass 1 -> pass 2)
+    double* hs_sm;              // shared-memory home of the homotopy state (4 mt doubles) at the first-level capacity, else null
 #ifdef EEP_K3_TIMERS
     long long* ph;              // [32] clock64() cycles by phase + [32] = last stamp (thread 0 only)
 #endif
@@ -1355,6 +1359,12 @@ template <class CT> K3R_FN __device__ void setup_aux(CT& C)
 }  // namespace k3r
 
 extern "C" __host__ __device__ size_t eep_qpr_smem_bytes(int n, int m, int fc);
+__host__ __device__ size_t eep_qpr_smem_base(int n, int m, int fc);
+// the homotopy state (4 (m + n) doubles) lives in shared memory whenever two CTAs per SM still fit with it
+__host__ __device__ inline bool eep_qpr_hs_in_smem(int n, int m, int fc)
+{
+    return eep_qpr_smem_base(n, m, fc) + 32 * (size_t)(n + m) <= (size_t)113 * 1024;
+}
 #ifndef EEP_HOST_EMU
 extern __shared__ __align__(16) unsigned char k3r_smem[];
 #endif
@@ -1445,6 +1455,8 @@ __device__ __forceinline__ void k3r_setup(k3r::CtxT<NU, NB>& C, const eep_qp_io&
         C.red = p; p += 16;
         C.ired = reinterpret_cast<int*>(p); p += 4;      // 8 ints
         C.tt = p; p += (size_t)(2 * ((mt + NT - 1) / NT) + (n + NT - 1) / NT) * NT;
+        C.hs_sm = nullptr;
+        if (eep_qpr_hs_in_smem(n, m, fc)) { C.hs_sm = p; p += 4 * (size_t)mt; }
         double* cst = p; p += 96;
         C.g = gS; C.gw = gS; C.rtab = io.rowtab; C.cvals = cst; C.cva = cst + 32; C.cvb = cst + 64;
         short* sp = reinterpret_cast<short*>(p);
@@ -1490,7 +1502,10 @@ K3R_FN __device__ int k3r_vehicle(CT& C, const eep_qp_io& io, const long long ve
         K3R_LOOP for (int i = threadIdx.x; i < n; i += NT) C.gw[i] = gg[i];
         C.lba = la; C.uba = ua;
         {
-            double* hs = io.hscr + veh * (size_t)(4 * mt);
+            // homotopy state over all m + n rows: in shared memory at the first-level capacity (registers, not shared
+            // memory, hold the kernel to two CTAs per SM, so the 20 KB are free; ncu had 23 % of these accesses miss
+            // L1), in the per-vehicle global scratch for the large-capacity hand-over launches
+            double* hs = C.hs_sm ? C.hs_sm : io.hscr + veh * (size_t)(4 * mt);
             C.Ax = hs; C.lbc = hs + mt; C.ubc = hs + 2 * mt; C.Adx = hs + 3 * mt;
         }
         const double* sb = io.sblk + veh * (size_t)EEP_SBLK;
@@ -1901,7 +1916,7 @@ __global__ void k3r_rowtab_kernel(int ctrl, eepacc_params p, int m, unsigned lon
     if (threadIdx.x == 0 && blockIdx.x == 0) *rc = k3r_build_rowtab(ctrl, p, m, tab, consts);
 }
 
-extern "C" __host__ __device__ size_t eep_qpr_smem_bytes(int n, int m, int fc)
+__host__ __device__ size_t eep_qpr_smem_base(int n, int m, int fc)
 {
     const int mt = n + m, ldq = (fc + 1) | 1, NH = EEP_N;
     size_t d = (size_t)(fc + 1) * ldq + (size_t)fc * (fc + 1) / 2 + fc + 2 + (fc + 2) + 13 * (size_t)n + 10 * (size_t)(fc + 1)
@@ -1910,7 +1925,12 @@ extern "C" __host__ __device__ size_t eep_qpr_smem_bytes(int n, int m, int fc)
              + 2 * (NH + 1) + NH + 5 * (size_t)(fc + 1) + 16 + 4 + 96
              + (size_t)(2 * ((mt + NT - 1) / NT) + (n + NT - 1) / NT) * NT;
     size_t shorts = 7 * (size_t)(fc + 1) + 3 * (size_t)n;
-    size_t b = d * 8 + shorts * 2 + 2 * (size_t)mt + 16;
+    return d * 8 + shorts * 2 + 2 * (size_t)mt + 16;
+}
+extern "C" __host__ __device__ size_t eep_qpr_smem_bytes(int n, int m, int fc)
+{
+    size_t b = eep_qpr_smem_base(n, m, fc);
+    if (eep_qpr_hs_in_smem(n, m, fc)) b += 32 * (size_t)(n + m);
 #ifdef EEP_K3_TIMERS
     b = ((b + 7) & ~(size_t)7) + 34 * 8;
 #endif
@@ -1985,15 +2005,15 @@ __global__ void __launch_bounds__(NT, K3R_MINB) k5_cycle_kernel(const eepacc_par
             k2_vehicle<NT>(p, b, veh, S);
             __syncthreads();                                       // K2's outputs (global) are visible to the CTA
             const long long tk1 = clock64();
-            k3r_tables(C, cy.q);
-            int st = k3r_vehicle(C, cy.q, veh);
-            const long long tk2 = clock64();
-            if (st == K3R_DEFER) {
-                k3r_setup<NU, NB>(C, cy.q, cy.big + (size_t)blockIdx.x * cy.big_bytes, cy.fc_big);
-                __syncthreads();
+            // ONE call site of the (force-inlined) solver: first in shared memory at capacity fc; a solve that outgrows it
+            // is repeated in place at capacity n from this CTA's global work area (it cannot hand over again)
+            long long tk2 = 0;
+            for (int attempt = 0; attempt < 2; ++attempt) {
+                if (attempt == 1) { k3r_setup<NU, NB>(C, cy.q, cy.big + (size_t)blockIdx.x * cy.big_bytes, cy.fc_big); __syncthreads(); }
                 k3r_tables(C, cy.q);
-                st = k3r_vehicle(C, cy.q, veh);                    // capacity n: cannot hand over again
-                k3r_setup<NU, NB>(C, cy.q, k3r_smem, cy.q.fc);
+                const int st = k3r_vehicle(C, cy.q, veh);
+                if (attempt == 0) tk2 = clock64();
+                if (st != K3R_DEFER) { if (attempt == 1) k3r_setup<NU, NB>(C, cy.q, k3r_smem, cy.q.fc); break; }
             }
             __syncthreads();
             const long long tk3 = clock64();
