@@ -26,7 +26,10 @@
 #include "eepacc_kernels.h"
 #include "eepacc_rows.cuh"
 
-#define NT 256
+#ifndef K3_NT
+#define K3_NT 256
+#endif
+#define NT K3_NT
 #define FARB      1.0e6
 #define RELAX     1.0e4
 #define BIGB      1.0e19
