@@ -757,6 +757,16 @@ template <class CT> K3R_FN __device__ int refactor_R(CT& C)
     int GMAX = (9 * n) / (n + HG_SCR);
     if (GMAX > 4) GMAX = 4;
     double* V = C.gcur;
+#ifndef EEP_HOST_EMU
+    if (C.hs_sm) {
+        // first-level capacity: the ratio-test slots and the homotopy state behind them are dead until setup_aux and hold
+        // up to 16 null-space columns at a time (fewer barrier-separated passes of the stage operators)
+        const int navail = (2 * ((C.mt + NT - 1) / NT) + (n + NT - 1) / NT) * NT + 4 * C.mt;
+        GMAX = navail / (n + HG_SCR);
+        if (GMAX > 16) GMAX = 16;
+        V = C.tt;
+    }
+#endif
     double* scr = V + GMAX * n;
     for (int j0 = 0; j0 < nZ; j0 += GMAX) {
         const int G = (nZ - j0 < GMAX) ? nZ - j0 : GMAX;
@@ -1265,7 +1275,49 @@ template <class CT> K3R_FN __device__ int warm_setup(CT& C, int old_nA, const sh
         }
     }
     __syncthreads();
-    // 5. form Qh: backward accumulation of the reflectors
+    // 5. form Qh = H_0 H_1 ... H_(nAC-1).
+#ifndef EEP_HOST_EMU
+    // Column j of Qh is H_0 .. H_min(j, nAC-1) e_j: the columns are INDEPENDENT once the reflectors are read-only.  They
+    // are copied (with their leading entry made explicit) into the scratch that is dead during the set-up -- the
+    // ratio-test slots and, at the first-level capacity, the homotopy state behind them -- and every column is then
+    // built by a pair of lanes with no block barrier at all (the in-place backward accumulation below pays one barrier
+    // and a full pass over the trailing block per reflector: 59-70 k cycles of a ~450-700 k cycle solve).  The column
+    // lands straight in its final, reversed position (step 6 disappears).
+    {
+        const int navail = (2 * ((mt + NT - 1) / NT) + (n + NT - 1) / NT) * NT + (C.hs_sm ? 4 * mt : 0);
+        if (nAC > 0 && nF * nAC <= navail) {
+            double* Vs = C.tt;                                   // [nAC][nF]: reflector k = Vs[k * nF + (k .. nF-1)]
+            K3R_LOOP for (int e = threadIdx.x; e < nAC * nF; e += NT) {
+                const int k = e / nF, i = e - k * nF;
+                Vs[e] = (i > k) ? QF(i, k) : (i == k ? v0a[k] : 0.0);
+            }
+            __syncthreads();
+            for (int j0 = 0; j0 < nF; j0 += NT / 2) {            // warp-uniform trip count (full-mask shuffles inside)
+                const int j = j0 + (int)(threadIdx.x >> 1), lane = threadIdx.x & 1;
+                const bool act = j < nF;
+                const int dc = act ? nF - 1 - j : 0;             // Qf = Qh with reversed columns
+                if (act) for (int i = lane; i < nF; i += 2) QF(i, dc) = (i == j) ? 1.0 : 0.0;
+                __syncwarp();
+                for (int kk = nAC - 1; kk >= 0; --kk) {
+                    const bool on = act && kk <= j;              // H_kk e_j = e_j for kk > j
+                    const double* v = Vs + kk * nF;
+                    const int i0 = kk + ((lane - kk) & 1);       // first row >= kk of this lane's parity
+                    double d = 0;
+                    if (on) for (int i = i0; i < nF; i += 2) d += v[i] * QF(i, dc);
+                    d += __shfl_xor_sync(0xffffffffu, d, 1);
+                    d *= beta[kk];
+                    if (on) for (int i = i0; i < nF; i += 2) QF(i, dc) -= d * v[i];
+                    __syncwarp();
+                }
+            }
+            K3R_LOOP for (int kq = threadIdx.x; kq < nAC; kq += NT) { C.yW[nF - 1 - kq] = ycand[kq]; C.widx[nF - 1 - kq] = cand[kq]; }
+            C.nZ = nZ;
+            __syncthreads();
+            PH(4);
+            return 0;
+        }
+    }
+#endif
     K3R_LOOP for (int j = nAC + threadIdx.x; j < nF; j += NT)
         for (int i = 0; i < nF; ++i) QF(i, j) = (i == j) ? 1.0 : 0.0;
     __syncthreads();
