@@ -1233,6 +1233,43 @@ template <class CT> K3R_FN __device__ int warm_setup(CT& C, int old_nA, const sh
         const double alpha = (x0 >= 0.0) ? -sigma : sigma;
         const double v0 = x0 - alpha;
         const double bt = 1.0 / (s2 - x0 * alpha);
+#ifndef EEP_HOST_EMU
+        // lanes per column: as many as the remaining columns leave room for (4, 8 or 16): the per-lane chain of the
+        // dot product and of the update is what a column step costs
+        const int ncol = cnt - k - 1;
+        const int lpc = (ncol * 16 <= NT) ? 16 : (ncol * 8 <= NT) ? 8 : 4;
+        for (int j0 = k + 1; j0 < cnt; j0 += NT / lpc) {
+            const int j = j0 + (int)threadIdx.x / lpc, lane = threadIdx.x % lpc;
+            const bool act = j < cnt;
+            double d = 0, d1 = 0;
+            if (act) {
+                int i = k + 1 + lane;
+                for (; i + lpc < nF; i += 2 * lpc) { d += QF(i, k) * QF(i, j); d1 += QF(i + lpc, k) * QF(i + lpc, j); }
+                if (i < nF) d += QF(i, k) * QF(i, j);
+            }
+            if (act && lane == 0) d += v0 * QF(k, j);     // consumed before the shuffle: lane 0 rewrites it below
+            d += d1;
+            d += __shfl_xor_sync(0xffffffffu, d, 1); d += __shfl_xor_sync(0xffffffffu, d, 2);
+            if (lpc >= 8) d += __shfl_xor_sync(0xffffffffu, d, 4);
+            if (lpc >= 16) d += __shfl_xor_sync(0xffffffffu, d, 8);
+            double nn = 0;
+            if (act) {
+                d *= bt;
+                for (int i = k + 1 + lane; i < nF; i += lpc) {
+                    const double v = QF(i, j) - d * QF(i, k);
+                    QF(i, j) = v;
+                    nn += v * v;
+                }
+            }
+            if (j0 == k + 1) {                            // warp-uniform: first pass only
+                nn += __shfl_xor_sync(0xffffffffu, nn, 1); nn += __shfl_xor_sync(0xffffffffu, nn, 2);
+                if (lpc >= 8) nn += __shfl_xor_sync(0xffffffffu, nn, 4);
+                if (lpc >= 16) nn += __shfl_xor_sync(0xffffffffu, nn, 8);
+                if (act && j == k + 1 && lane == 0) C.red[6 + slot] = nn;
+            }
+            if (act && lane == 0) QF(k, j) -= d * v0;
+        }
+#else
         for (int j0 = k + 1; j0 < cnt; j0 += NT / LPC) {
             const int j = j0 + threadIdx.x / LPC, lane = threadIdx.x % LPC;
             const bool act = j < cnt;
@@ -1259,6 +1296,7 @@ template <class CT> K3R_FN __device__ int warm_setup(CT& C, int old_nA, const sh
             }
             if (act && lane == 0) QF(k, j) -= d * v0;
         }
+#endif
         if (threadIdx.x == 0) { v0a[k] = v0; beta[k] = bt; rdiag[k] = alpha; }
         __syncthreads();
         ++k;

@@ -117,3 +117,22 @@ extern "C" int k3r_emu_run(int ctrl, const eepacc_params* p, const eepacc_route*
     delete S;
     return 0;
 }
+
+// ---- unit entry points of the product's device functions (compiled for the host): the estimator in all its modes
+// and the per-stage route / comfort bounds, for CPU tests against the oracle ----
+extern "C" void k3r_emu_est_traj(const eepacc_params* p, int est_setting, double s, double v, double a, const double* sp,
+                                 const double* vp, double* s_est, double* v_est)
+{
+    eep_est_traj(*p, est_setting, s, v, a, sp, vp, s_est, v_est);
+}
+// out[N][9] = slope, v_lim, v_stop, v_tl, v_curv, a_min, a_max, j_min, j_max per stage
+extern "C" void k3r_emu_bounds(const eepacc_params* p, const eepacc_route* r, int mpctype, const double* s_est, const double* v_est,
+                               double t0, double* out)
+{
+    for (int i = 0; i < EEP_N; ++i) {
+        eep_stage_bounds B;
+        eep_bounds_stage(*p, r, mpctype, i, s_est[i], v_est[i], t0, B);
+        double* o = out + 9 * i;
+        o[0] = B.slope; o[1] = B.v_lim; o[2] = B.v_stop; o[3] = B.v_tl; o[4] = B.v_curv; o[5] = B.a_min; o[6] = B.a_max; o[7] = B.j_min; o[8] = B.j_max;
+    }
+}
