@@ -82,6 +82,9 @@ def load_library():
     L.eepacc_mem_enable_timing.argtypes = [C.c_int, C.c_int]
     L.eepacc_mem_debug_phases.argtypes = [C.c_int, _dp]
     L.eepacc_mem_get_timing.argtypes = [C.c_int, _dp, _dp, C.c_longlong]
+    L.eepacc_mem_set_solver.argtypes = [C.c_int, C.c_int]
+    L.eepacc_mem_get_solver.argtypes = [C.c_int]
+    L.eepacc_mem_set_ocp_options.argtypes = [C.c_int, _dp]
     for f in FAMILIES:
         getattr(L, f).argtypes = [_dpp, _dpp, C.POINTER(C.c_longlong), _dp, C.c_int]
         getattr(L, f + "_name_in").restype = C.c_char_p
@@ -402,6 +405,26 @@ class Engine:
 
     def groups(self):
         return int(self.L.eepacc_mem_get_groups(self.mem))
+
+    def set_solver(self, solver="qpoases", **options):
+        """Closed-loop QP solver (the reference's OPTsettings.solverToUse, MC/Settings.m:112): "qpoases" (default) =
+        condensing + dense online active set (K3 / K3r); "ocp" = the same QP kept stage-structured and solved by a
+        Riccati-based interior-point method, one vehicle per thread (K6; FBMPC / ABMPC).  options for "ocp":
+        mu0, eps_mu, eps_p, eps_d, eps_accept, maxit (include/eepacc.h)."""
+        code = {"qpoases": 0, "dense": 0, "ocp": 1, "hpipm": 1}[solver] if isinstance(solver, str) else int(solver)
+        if self.L.eepacc_mem_set_solver(self.mem, code):
+            raise EepaccError(self._err())
+        if options:
+            keys = ["mu0", "eps_mu", "eps_p", "eps_d", "eps_accept", "maxit"]
+            bad = set(options) - set(keys)
+            if bad:
+                raise EepaccError(f"unknown solver options {sorted(bad)}")
+            o = np.array([float(options.get(k, np.nan)) for k in keys])
+            if self.L.eepacc_mem_set_ocp_options(self.mem, o.ctypes.data_as(_dp)):
+                raise EepaccError(self._err())
+
+    def solver(self):
+        return {0: "qpoases", 1: "ocp"}.get(int(self.L.eepacc_mem_get_solver(self.mem)), "?")
 
     def set_fused(self, on=True):
         """run(): False (default) = per-step launches over pipelined slices; True = one fused closed-loop launch

@@ -6,8 +6,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libeepacc.so")
-SOURCES = ["k1_eval.cu", "k2_build.cu", "k3_qp.cu", "k3r_qp.cu", "k4_post.cu", "k5_scenario.cu", "eepacc_capi.cu"]
-HEADERS = ["eepacc_dev.cuh", "eepacc_kernels.h", "eepacc_rows.cuh", "k2_build.cuh", "k4_post.cuh", "qp_rules.cuh",
+SOURCES = ["k1_eval.cu", "k2_build.cu", "k3_qp.cu", "k3r_qp.cu", "k4_post.cu", "k5_scenario.cu", "k6_ocp.cu", "eepacc_capi.cu"]
+HEADERS = ["eepacc_dev.cuh", "eepacc_kernels.h", "eepacc_rows.cuh", "k2_build.cuh", "k4_post.cuh", "qp_rules.cuh", "k6_ocp.cuh",
            os.path.join("..", "..", "include", "eepacc.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]

@@ -73,6 +73,9 @@ struct Mem {
     cudaEvent_t cyc_ev[2] = { nullptr, nullptr };   // around the last fused launch (always recorded: two events per cycle)
     int cyc_grid = 0, cyc_per_sm = 0;
     int qp_mode = 0;            // 0: reduced-space kernel + full-space fallback, 1: full-space kernel only
+    int solver = EEPACC_SOLVER_QPOASES;   // closed-loop QP solver: dense active set (K3/K3r) or stage-structured interior point (K6)
+    DBuf qz, ocp_work;          // K6 only: un-condensed gradient [B][N+1+n], per-vehicle work space [items][B]
+    double ocp_opts[6] = { 1e6, 1e-11, 1e-9, 1e-10, 1e-9, 80 };   // mu0, eps_mu, eps_p, eps_d, eps_accept, maxit
     int qp_fc = 56;             // capacity (free variables) of the reduced factorisation (measured: 48 -> 56 +1 % AB, +3 % FB; 64, 72 slower)
     long long deferred_total = 0;
     DBuf in[12], out[8];        // staging for host-pointer calls
@@ -89,7 +92,7 @@ struct Mem {
     {
         DBuf* all[] = { &routes, &s_prev, &v_prev, &Fm_prev, &Fb_prev, &a_minus1, &v_tv_meas, &fbA, &fbD, &prev_sol,
                         &x0, &dyn, &g, &lba, &uba, &sblk, &wx, &wy, &widx, &wside, &wnA, &warm, &xsol, &cost,
-                        &status, &iter, &counters, &kpi_acc, &kpi, &lead, &lead_step, &logrow, &dbg, &defer_list, &defer_cnt, &rowtab, &rowc, &hscr, &defer_list2, &cyc_counter, &cyc_big, &synth_in };
+                        &status, &iter, &counters, &kpi_acc, &kpi, &lead, &lead_step, &logrow, &dbg, &defer_list, &defer_cnt, &rowtab, &rowc, &hscr, &defer_list2, &cyc_counter, &cyc_big, &synth_in, &qz, &ocp_work };
         for (DBuf* b : all) b->release();
         for (auto& b : in) b.release();
         for (auto& b : out) b.release();
@@ -317,6 +320,7 @@ int device_step_slice(Mem* M, int g, size_t v0, long long nb, cudaStream_t st, i
     bio.kk = kk; bio.t0 = t0;
     bio.lead = lead_dev;
     slice_io(bio, v0, nb, M->m, M->n);
+    if (M->solver == EEPACC_SOLVER_OCP) bio.qz = M->qz.as<double>() + v0 * (size_t)(NH + 1 + M->n);
     if (ev) CK(cudaEventRecord(ev[0], st));
     int rc = eep_launch_build(&M->p, &bio, st);
     if (ev) CK(cudaEventRecord(ev[1], st));
@@ -324,7 +328,24 @@ int device_step_slice(Mem* M, int g, size_t v0, long long nb, cudaStream_t st, i
     eep_qp_io qio = make_qp_io(M);
     slice_io(qio, v0, nb);
     bool need_full = true;      // does anything remain for the full-space kernel?
-    if (M->qp_mode == 0) {
+    if (M->solver == EEPACC_SOLVER_OCP) {
+        // stage-structured interior-point solver, one vehicle per thread (k6_ocp.cu); cold-started every step, no solver state
+        eep_ocp_io oio;
+        memset(&oio, 0, sizeof oio);
+        oio.B = nb; oio.n = M->n; oio.m = M->m; oio.ctrl = M->ctrl;
+        oio.sblk = qio.sblk; oio.lba = qio.lba; oio.uba = qio.uba;
+        oio.dyn = M->dyn.as<double>() + v0 * 2 * (size_t)NH;
+        oio.qz = M->qz.as<double>() + v0 * (size_t)(NH + 1 + M->n);
+        oio.rowtab = M->rowtab.as<unsigned long long>(); oio.rowc = M->rowc.as<double>();
+        oio.work = M->ocp_work.as<double>() + v0; oio.work_stride = M->B;
+        oio.x = qio.x; oio.cost = qio.cost; oio.status = qio.status; oio.iter = qio.iter; oio.counters = qio.counters;
+        oio.mu0 = M->ocp_opts[0]; oio.eps_mu = M->ocp_opts[1]; oio.eps_p = M->ocp_opts[2]; oio.eps_d = M->ocp_opts[3];
+        oio.eps_accept = M->ocp_opts[4]; oio.maxit = (int)M->ocp_opts[5];
+        rc = eep_launch_ocp(&M->p, &oio, st);
+        if (rc) return fail(EEPACC_ERR_CUDA, "k6_ocp launch", (cudaError_t)rc);
+        M->launches += 1;
+        need_full = false;
+    } else if (M->qp_mode == 0) {
         // Hand-over launches (second level, full space) take a whole SM's shared memory per CTA: a CTA of theirs
         // cannot start before an SM has drained, and the slice waits for the whole grid.  Past the cold-start
         // step the hand-over lists hold well under 1 % of the vehicles, so a handful of CTAs walks them.
@@ -518,6 +539,7 @@ int eepacc_mem_setup(int mem, int ctrl, const eepacc_params* p, const eepacc_rou
         M->qp_fc2 = 0;
         if (const char* e = getenv("EEPACC_QP_FC2")) { int v = atoi(e); M->qp_fc2 = (v > M->qp_fc && v <= f2) ? v : 0; }
         if (const char* e = getenv("EEPACC_QP_FBGRID")) { int v = atoi(e); if (v >= 1 && v <= 148) M->qp_fbgrid = v; }
+        M->solver = EEPACC_SOLVER_QPOASES;
         M->fused = 0;           // measured slower than the sliced per-step path (profiles/README.md): opt-in
         if (const char* e = getenv("EEPACC_FUSED")) M->fused = atoi(e) ? 1 : 0;
     }
@@ -731,6 +753,45 @@ int eepacc_mem_get_timing(int mem, double* tot, double* step_ms, long long cap)
 /* eepacc_run mode: 0 (default) = one set of launches per MPC step (sliced, see eepacc_mem_set_groups);
  * 1 = steps >= 1 run in the fused closed-loop kernel, one launch per cycle, no synchronisation between vehicles.
  * Event timing (eepacc_mem_enable_timing) always uses the per-step launches. */
+/* Closed-loop QP solver: EEPACC_SOLVER_QPOASES (default; K3/K3r, the reference's dense qpOASES path) or
+ * EEPACC_SOLVER_OCP (K6, stage-structured interior point: the reference's solverToUse = 0 / 2 formulations). */
+int eepacc_mem_set_solver(int mem, int solver)
+{
+    Mem* M = get_mem(mem);
+    if (!M || !M->ready) return fail(EEPACC_ERR_ARG, "mem not set up");
+    if (solver == EEPACC_SOLVER_QPOASES) { M->solver = solver; return EEPACC_OK; }
+    if (solver != EEPACC_SOLVER_OCP) return fail(EEPACC_ERR_ARG, "unknown solver");
+    if (M->ctrl != EEPACC_FB && M->ctrl != EEPACC_AB)
+        return fail(EEPACC_ERR_ARG, "the stage-structured solver covers FBMPC and ABMPC (the BL/TV LPs have no unique interior solution)");
+    DeviceGuard gd;
+    CK((cudaError_t)gd.enter(M->device));
+    const long long items = eep_ocp_work_items(M->ctrl, M->n, M->m);
+    if (M->qz.ensure((size_t)M->B * (NH + 1 + M->n) * 8)) return EEPACC_ERR_MEM;
+    if (M->ocp_work.ensure((size_t)M->B * (size_t)items * 8)) return EEPACC_ERR_MEM;
+    M->solver = solver;
+    M->fused = 0;               // the fused closed-loop kernel embeds the active-set solver
+    // initial barrier parameter, measured on the bench batch: the convex ABMPC QPs want a well-centred
+    // start (1e6: no iteration-limit failures in 13 936 QPs, 1e4: 109); on the non-convex FBMPC QPs the start decides
+    // WHICH local minimiser is reached, and 1e4 is the value that reproduces the golden runs (qpOASES' minimiser)
+    M->ocp_opts[0] = (M->ctrl == EEPACC_FB) ? 1e4 : 1e6;
+    return EEPACC_OK;
+}
+int eepacc_mem_get_solver(int mem)
+{
+    Mem* M = get_mem(mem);
+    return (M && M->ready) ? M->solver : -1;
+}
+/* opts[6] = mu0, eps_mu, eps_p, eps_d, eps_accept, maxit (NaN keeps a value) */
+int eepacc_mem_set_ocp_options(int mem, const double* opts)
+{
+    Mem* M = get_mem(mem);
+    if (!M || !M->ready || !opts) return fail(EEPACC_ERR_ARG, "mem not set up");
+    for (int i = 0; i < 6; ++i) if (opts[i] == opts[i]) {
+        if (!(opts[i] > 0.0)) return fail(EEPACC_ERR_ARG, "solver options must be positive");
+        M->ocp_opts[i] = opts[i];
+    }
+    return EEPACC_OK;
+}
 int eepacc_mem_set_fused(int mem, int on)
 {
     Mem* M = get_mem(mem);

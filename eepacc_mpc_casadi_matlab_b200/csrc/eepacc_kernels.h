@@ -42,6 +42,8 @@ struct eep_build_io {
     double *H, *g, *A, *lba, *uba;   // H, A may be null (matrix-free closed loop)
     double *sblk;               // [B][EEP_SBLK] structured block (may be null)
     double *dyn;                // [B][2][N] alpha_k, Dv_k for the post kernel (may be null)
+    double *qz;                 // [B][N + 1 + n] gradient of the un-condensed QP at the free response: tv_k = (Hs d + cs)(v_k),
+                                // k = 0..N, then (Hs d + cs)(u) -- what the stage-structured solver K6 needs (may be null)
 };
 
 // K3 (k3_qp.cu)
@@ -71,6 +73,20 @@ struct eep_qp_io {
     double* hscr;                       // [B][4 (n + m)] homotopy state of the reduced-space kernel (a x, current bounds, a dx)
     int todo_grid;                      // CTAs that walk todo_list (0: 148).  These launches need a whole SM's shared
                                         // memory per CTA; a wide grid stalls the slice until that many SMs have drained
+};
+
+// K6 (k6_ocp.cu): stage-structured interior-point QP solver, one vehicle per thread (opt-in: eepacc_mem_set_solver)
+struct eep_ocp_io {
+    long long B;
+    int n, m, ctrl;
+    const double *sblk, *dyn, *qz, *lba, *uba;      // K2 outputs: [B][EEP_SBLK], [B][2][N], [B][N+1+n], [B][m], [B][m]
+    const unsigned long long* rowtab;               // [m] packed constraint rows (shared with K3r)
+    const double* rowc;                             // [96]
+    double* work; long long work_stride;            // [eep_ocp_work_items][work_stride] per-vehicle work space, vehicle fastest
+    double *x, *cost, *status, *iter;               // [B][n], [B], [B], [B]
+    unsigned long long* counters;                   // [B][4]: interior-point iterations, failed (may be null)
+    double mu0, eps_mu, eps_p, eps_d, eps_accept;
+    int maxit;
 };
 
 // post kernel (k4_post.cu): z recovery, force allocation, logging, KPI accumulation
@@ -142,6 +158,8 @@ size_t eep_qpr_smem_bytes(int n, int m, int fc);
 int eep_qpr_build_rowtab(int ctrl, const eepacc_params* p, int m, unsigned long long* tab_dev, double* consts_dev, cudaStream_t st);
 size_t eep_qp_smem_bytes(int n, int m, int smode);
 int eep_launch_post(const eepacc_params* p, const eep_post_io* io, cudaStream_t st);
+int eep_launch_ocp(const eepacc_params* p, const eep_ocp_io* io, cudaStream_t st);
+long long eep_ocp_work_items(int ctrl, int n, int m);
 int eep_launch_lead_synth(long long B, int n_steps, double ts, double tv_length, const double* base, int n_base,
                           const double* hw, int n_hw, const double* pert, double* lead, cudaStream_t st);
 int eep_launch_route_gen(long long B, const eepacc_route_spec* specs, eepacc_route* routes, int* err, cudaStream_t st);

@@ -392,6 +392,17 @@ __device__ void k2_vehicle(const eepacc_params& p, const eep_build_io& io, const
         }
         gout[a] = v;
     }
+    if (io.qz) {    // un-condensed gradient for the stage-structured solver (k6_ocp.cuh)
+        double* qz = io.qz + veh * (long long)(N + 1 + n);
+        for (int k = tid; k <= N; k += NTB) qz[k] = S.tv[k];
+        for (int a = tid; a < n; a += NTB) {
+            const int ka = a / nu, r = 1 + a % nu;
+            double v = S.Dk[ka][r * W] * S.dv[ka] + S.cs[ka][r];
+            if (ka > 0) v += S.Ck[ka][r * W] * S.dv[ka - 1];
+            if (ka + 1 < N) v += S.Ck[ka + 1][r] * S.dv[ka + 1];
+            qz[N + 1 + a] = v;
+        }
+    }
     // ---------- A (structural non-zeros only) and shifted bounds ----------
     double* Aout = io.A ? io.A + veh * (long long)m * n : nullptr;
     double* lbo = io.lba + veh * (long long)m;

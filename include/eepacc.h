@@ -194,6 +194,24 @@ int eepacc_mem_set_groups(int mem, int groups);
  * runs its remaining MPC steps inside ONE fused kernel launch (no synchronisation between vehicles). */
 int eepacc_mem_set_fused(int mem, int on);
 int eepacc_mem_get_fused(int mem);
+/* Closed-loop QP solver of eepacc_step_* / eepacc_run -- the reference's OPTsettings.solverToUse (MC/Settings.m:112):
+ *   EEPACC_SOLVER_QPOASES (default) = solverToUse 1: condensing + dense online active set (K3 / K3r kernels), the path
+ *                                     every parity claim of this library is made on;
+ *   EEPACC_SOLVER_OCP               = solverToUse 0 / 2 (sparse qpOASES / HPIPM; RunOpt_FBMPC.m:96-121,
+ *                                     CreateQP_FB.m:219-308): the same QP kept stage-structured and solved by a
+ *                                     Riccati-based primal-dual interior-point method, one vehicle per thread (K6).
+ *                                     FBMPC and ABMPC only; cold-started every step; status 0 / 1 (iteration limit) /
+ *                                     2 (breakdown); `iter` = interior-point iterations.  It returns the same minimiser
+ *                                     wherever that is unique; on a flat optimal face (FBMPC's Fm / Fb split at
+ *                                     standstill) it returns the face's analytic centre instead of a vertex.
+ * eepacc_mem_set_ocp_options: opts[6] = initial barrier parameter, tolerances on the complementarity, the primal and
+ * the stationarity residual, complementarity below which a factorisation breakdown is accepted as converged,
+ * iteration limit (NaN keeps the current value; defaults 1e6 (ABMPC) / 1e4 (FBMPC), 1e-11, 1e-9, 1e-10, 1e-9, 80). */
+#define EEPACC_SOLVER_QPOASES 0
+#define EEPACC_SOLVER_OCP     1
+int eepacc_mem_set_solver(int mem, int solver);
+int eepacc_mem_get_solver(int mem);
+int eepacc_mem_set_ocp_options(int mem, const double* opts);
 /* out[7]: [0] duration in ms (CUDA events on the launching stream) of the last fused closed-loop launch, [1] its
  * grid, [2] CTAs resident per SM, [3..6] SM clock cycles summed over all vehicle-steps spent in the build, the QP
  * solve, the hand-over solves and the post stage. */

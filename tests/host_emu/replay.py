@@ -42,7 +42,8 @@ def build(opt="-O2"):
     lib = os.path.join(out, "libk3r_emu.so")
     src = os.path.join(HERE, "k3r_emu.cpp")
     deps = [src] + [os.path.join(ROOT, "eepacc_mpc_casadi_matlab_b200", "csrc", f)
-                    for f in ("k3r_qp.cu", "eepacc_rows.cuh", "eepacc_dev.cuh", "eepacc_kernels.h")]
+                    for f in ("k3r_qp.cu", "eepacc_rows.cuh", "eepacc_dev.cuh", "eepacc_kernels.h", "k2_build.cuh", "k4_post.cuh",
+                              "k6_ocp.cuh", "qp_rules.cuh")]
     if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
         subprocess.check_call(["g++", opt, "-g", "-std=c++17", "-x", "c++", "-shared", "-fPIC", "-I", inc, src, "-o", lib])
     L = C.CDLL(lib)
@@ -144,3 +145,25 @@ def emu_run(ctrl, params, route, lead, fc=56, want_ws=False, stats=None):
                        stats.ctypes.data_as(_ip) if stats is not None else None)
     assert rc == 0, rc
     return (log, ws) if want_ws else log
+
+
+OCP_DEFAULTS = dict(mu0=1e6, eps_mu=1e-11, eps_p=1e-9, eps_d=1e-10, maxit=80, warm=0, eps_accept=1e-9, gamma=1e-3, tau0=1.0)   # = the library defaults (eepacc_capi.cu: ocp_opts)
+
+
+def ocp_emu_run(ctrl, params, route, lead, check=True, **opts):
+    """Closed loop of ONE vehicle with the stage-structured interior-point solver K6 (csrc/k6_ocp.cuh) in the
+    solver's place, single-threaded on the host: K2 -> K6 -> K4.  -> (log[n_steps, 12], diag[n_steps, 6]);
+    diag = (first-stage / all-stage max |u - u_dense|, relative objective difference, K6 iterations, K6 status,
+    dense status) against the reduced-space active-set kernel on the same QP operands when check is set."""
+    from eepacc_mpc_casadi_matlab_b200.settings import Params, Route
+    L = build()
+    L.k6_emu_run.argtypes = [C.c_int, C.POINTER(Params), C.POINTER(Route), _dp, C.c_int, _dp, _dp, _dp]
+    lead = np.ascontiguousarray(lead, dtype=np.float64)
+    ns = lead.shape[0]
+    o = dict(OCP_DEFAULTS); o["mu0"] = 1e4 if ctrl == S.FB else 1e6; o.update(opts)       # eepacc_capi.cu: eepacc_mem_set_solver
+    ov = np.array([o["mu0"], o["eps_mu"], o["eps_p"], o["eps_d"], o["maxit"], o["warm"], 1.0 if check else 0.0, o["eps_accept"], o["gamma"], o["tau0"]])
+    log = np.zeros((ns, 12)); diag = np.zeros((ns, 6))
+    rc = L.k6_emu_run(ctrl, C.byref(params), C.byref(route), lead.ctypes.data_as(_dp), ns, ov.ctypes.data_as(_dp),
+                      log.ctypes.data_as(_dp), diag.ctypes.data_as(_dp))
+    assert rc == 0, rc
+    return log, diag

@@ -1,0 +1,90 @@
+"""GPU: the stage-structured interior-point solver K6 (k6_ocp.cu; SURVEY.md 8(f)-3, the reference's solverToUse = 0 / 2
+formulations: MC/Settings.m:112, RunOpt_FBMPC.m:96-121, CreateQP_FB.m:219-308) selected through the C-ABI
+(eepacc_mem_set_solver) in the closed loop K2 -> K6 -> K4, against the oracle (the qpOASES-equivalent path) and against
+the library's own dense path on the same batch.  Tolerances as in tests/test_ocp_host_emu.py, where the same device
+code is checked on the CPU."""
+import numpy as np
+import pytest
+
+from eepacc_mpc_casadi_matlab_b200 import settings as S, usecase as U
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(ctrl, p, routes, lead, B, ns, solver):
+    from eepacc_mpc_casadi_matlab_b200 import api
+    eng = api.Engine(ctrl, p, routes, B=B)
+    eng.set_solver(solver)
+    assert eng.solver() == solver
+    eng.set_lead(lead)
+    log, kpi = eng.run(ns)
+    ctr = eng.counters()
+    eng.close()
+    return log, kpi, ctr
+
+
+@pytest.mark.parametrize("tree,cn", [("mc", "ab"), ("mc", "fb"), ("abo", "fb")])
+def test_golden_closed_loop_with_the_structured_solver(oracle, lead_urban, tree, cn):
+    p = S.default_params(tree)
+    ns = 871
+    lead = np.ascontiguousarray(lead_urban[:ns, None, :])
+    log, kpi, ctr = _run(cn, p, [U.default_route()], lead, 1, ns, "ocp")
+    ref, kref = oracle.run(S.CTRL_NAMES[cn], p, U.default_route(), lead_urban[:ns])
+    lg = log[:, 0, :]
+    assert (lg[:, 9] == 0).all()
+    assert lg[:, 10].max() <= 45 and lg[:, 10].mean() < 27                      # interior-point iterations
+    assert np.abs(lg[:, :2] - ref[:, :2]).max() < 1e-6
+    assert np.abs(lg[:, 8] - ref[:, 8]).max() < 1e-6
+    assert (np.abs(lg[:, 11] - ref[:, 11]) / (1 + np.abs(ref[:, 11]))).max() < 1e-7
+    assert np.abs((lg[:, 2] + lg[:, 3]) - (ref[:, 2] + ref[:, 3])).max() < 1e-3
+    assert abs(kpi[0, 0] - kref[0]) < 1e-6 * abs(kref[0])                       # energy KPI
+
+
+def test_headline_batch_structured_vs_dense_path_and_oracle(oracle):
+    """64 scenarios of the bench batch (delays, mass scatter, odd b = highway) x 871 steps.  FBMPC's QP is not convex:
+    both solvers are local; on the CPU (tests/test_ocp_host_emu.py) 0.2 % of the QPs have two local minimisers that the
+    two paths tell apart, after which the closed loops separate by 1e-3 .. 4e-2 m.  Scenarios without such a step must
+    agree to north_star's tolerances; scenarios 1, 3, 7 (known to have none) are also held against the oracle."""
+    import bench
+    B, ns = 64, 871
+    p, routes, lead = bench.make_workload("fb", B, 0, ns)
+    log, kpi, ctr = _run("fb", p, routes, lead, B, ns, "ocp")
+    dlog, dkpi, _ = _run("fb", p, routes, lead, B, ns, "qpoases")
+    assert (log[:, :, 9] == 0).mean() > 0.9995                                   # failed QPs (measured on the CPU: 3 of 27 872)
+    ds = np.abs(log[:, :, :2] - dlog[:, :, :2]).max(axis=(0, 2))
+    same = ds < 1e-6
+    dsum = np.abs((log[:, same, 2] + log[:, same, 3]) - (dlog[:, same, 2] + dlog[:, same, 3])).max()
+    dobj = (np.abs(log[:, same, 11] - dlog[:, same, 11]) / (1 + np.abs(dlog[:, same, 11]))).max()
+    print("structured vs dense path: %d of %d scenarios within 1e-6 m over the cycle (the others: up to %.1e m); on those Fm+Fb %.2e N, "
+          "rel obj %.2e; mean ipm iterations %.1f" % (same.sum(), B, ds.max(), dsum, dobj, log[:, :, 10].mean()))
+    assert same.mean() >= 0.5
+    assert ds.max() < 0.5                                                         # a different local minimiser, not a different drive
+    assert dsum < 1e-3 and dobj < 1e-7
+    assert np.abs(kpi[same, 0] - dkpi[same, 0]).max() < 1e-6 * np.abs(dkpi[same, 0]).max()     # energy
+    assert np.abs(kpi[:, 0] - dkpi[:, 0]).max() < 1e-3 * np.abs(dkpi[:, 0]).max()              # and close on all of them
+    for b in (1, 3, 7):
+        ref, _ = oracle.run(S.FB, p, routes[b], lead[:, b, :])
+        assert np.abs(log[:, b, :2] - ref[:, :2]).max() < 1e-6, b
+        assert (np.abs(log[:, b, 11] - ref[:, 11]) / (1 + np.abs(ref[:, 11]))).max() < 1e-7, b
+
+
+def test_structured_solver_is_deterministic_and_slicing_independent():
+    import bench
+    from eepacc_mpc_casadi_matlab_b200 import api
+    B, ns = 96, 60
+    p, routes, lead = bench.make_workload("ab", B, 0, ns)
+    outs = []
+    for groups in (1, 3, 1):
+        eng = api.Engine("ab", p, routes, B=B)
+        eng.set_solver("ocp"); eng.set_groups(groups); eng.set_lead(lead)
+        outs.append(eng.run(ns)[0])
+        eng.close()
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+
+
+def test_structured_solver_refuses_the_lps():
+    from eepacc_mpc_casadi_matlab_b200 import api
+    eng = api.Engine("bl", S.default_params("mc"), [U.default_route()], B=1)
+    with pytest.raises(api.EepaccError):
+        eng.set_solver("ocp")
+    eng.close()
