@@ -6,12 +6,19 @@
 // (x, cost, status, iter) out as the dense kernels.
 //
 // Launch shape: 32 threads per CTA so that a batch of 8192 vehicles already spreads over every SM (256 warps over
-// 148 SMs); larger batches use 64 / 128 threads.  Nothing is shared between threads: no shared memory, no barrier.
+// 148 SMs); larger batches use 64 / 128 threads.  The vehicles share nothing but the read-only row table (one copy
+// per CTA in shared memory); there is no barrier after the set-up.
 #include "k6_ocp.cuh"
 
 template <int NU, int NB>
 __global__ void __launch_bounds__(128) k6_ocp_kernel(const __grid_constant__ eepacc_params p, const eep_ocp_io io)
 {
+    // the packed row table and its coefficient tables are the same for every vehicle: one copy per CTA in shared memory
+    __shared__ unsigned long long s_tab[EEPACC_MAX_NCON];
+    __shared__ double s_rowc[96];
+    for (int i = threadIdx.x; i < io.m; i += blockDim.x) s_tab[i] = io.rowtab[i];
+    for (int i = threadIdx.x; i < 96; i += blockDim.x) s_rowc[i] = io.rowc[i];
+    __syncthreads();
     const long long veh = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (veh >= io.B) return;
     constexpr int NH = EEP_N, n = NH * NU;
@@ -21,7 +28,7 @@ __global__ void __launch_bounds__(128) k6_ocp_kernel(const __grid_constant__ eep
     A.qz = io.qz + veh * (NH + 1 + n);
     A.lba = io.lba + veh * io.m;
     A.uba = io.uba + veh * io.m;
-    A.rowtab = io.rowtab; A.rowc = io.rowc;
+    A.rowtab = s_tab; A.rowc = s_rowc;
     A.work = io.work + veh; A.ws = io.work_stride;
     A.m = io.m;
     A.T = p.Ts;

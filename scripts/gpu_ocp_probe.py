@@ -12,18 +12,19 @@ from eepacc_mpc_casadi_matlab_b200 import api  # noqa: E402
 import torch  # noqa: E402
 
 ctrl, B, ns = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+quick = len(sys.argv) > 4 and sys.argv[4] == "quick"      # structured solver only, one slicing
 p, routes, lead = bench.make_workload(ctrl, min(B, 8192), 0, ns)
 if B > lead.shape[1]:
     rep = B // lead.shape[1]
     lead = np.ascontiguousarray(np.tile(lead, (1, rep, 1)))
     routes = list(routes) * rep
 for solver in ("ocp", "qpoases"):
-    if solver == "qpoases" and B > 8192:
+    if solver == "qpoases" and (B > 8192 or quick):
         continue
     eng = api.Engine(ctrl, p, routes, B=B)
     eng.set_solver(solver)
     eng.set_lead(lead)
-    for groups in ((1, 4, 16) if solver == "ocp" else (16,)):
+    for groups in ((1, 4, 16) if solver == "ocp" and not quick else (16,)):
         eng.set_groups(groups)
         eng.run(ns, want_log=False)
         torch.cuda.synchronize()
