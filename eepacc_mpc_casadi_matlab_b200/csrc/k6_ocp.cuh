@@ -87,12 +87,6 @@ __device__ __forceinline__ void load_row(unsigned long long w, const double* __r
     }
 }
 
-// The six per-row quantities of one stage, fetched with independent back-to-back loads BEFORE any use: a thread's
-// loads are then in flight together (one memory round trip per stage and pass instead of one per row; with two
-// warps per SM at 8192 vehicles nothing else hides the latency).
-#define K6_RPS 26           // rows per stage, at most (FBMPC)
-struct StageRows { double tl[K6_RPS], ll[K6_RPS], tu[K6_RPS], lu[K6_RPS], lb[K6_RPS], ub[K6_RPS]; };
-
 struct Args {
     const double* sb;           // this vehicle's structured block [EEP_SBLK]
     const double* alpha;        // [N] A_k(2,2)
@@ -114,12 +108,6 @@ struct Args {
 };
 
 #define K6W(off) A.work[(long long)(off) * A.ws]
-#define K6_LOAD_STAGE(R, c0, c1)                                                                                   \
-    _Pragma("unroll 1") for (int c_ = (c0); c_ < (c1); ++c_) {                                                     \
-        const int i_ = c_ - (c0);                                                                                  \
-        (R).ll[i_] = K6W(oLL + c_); (R).lu[i_] = K6W(oLU + c_); (R).tl[i_] = K6W(oTL + c_); (R).tu[i_] = K6W(oTU + c_); \
-        (R).lb[i_] = K6W(oLB + c_); (R).ub[i_] = K6W(oUB + c_);                                                     \
-    }
 
 // one thread = one vehicle.  Returns status (0 solved, 1 iteration limit, 2 numerical breakdown); out: x[n], cost, iterations
 template <int NU, int NB>
@@ -184,7 +172,6 @@ __device__ int solve(const Args& A, double* __restrict__ xout, double& cost_out,
     }
     if (nside == 0) nside = 1;
 
-    StageRows R;                // one instance for every pass (a declaration per loop costs 1.2 KB of stack each)
     double nu_res = 1.0;            // factor by which the (linear) stationarity residual has shrunk
     int status = 1, it = 0;
     double mu = 0.0;
@@ -198,15 +185,14 @@ __device__ int solve(const Args& A, double* __restrict__ xout, double& cost_out,
             for (int c = 0; c < NB; ++c) zk[3 + c] = (k > 0) ? K6W(oU + (k - 1) * NU + c) : 0.0;
             for (int c = 0; c < NU; ++c) zk[NX + c] = (k < NH) ? K6W(oU + k * NU + c) : 0.0;
             const int c0 = (k < NH) ? k * rps : NH * rps, c1 = (k < NH) ? c0 + rps : c0 + nterm;
-            K6_LOAD_STAGE(R, c0, c1);
             for (int c = c0; c < c1; ++c) {
-                const double ll = R.ll[c - c0], lu = R.lu[c - c0];
+                const double ll = K6W(oLL + c), lu = K6W(oLU + c);
                 if (ll == 0.0 && lu == 0.0) continue;
                 SparseRow r; load_row<NU, NB>(A.rowtab[c], A.rowc, sb, k, r);
                 double az = 0.0, nrm = 0.0;
                 for (int e = 0; e < r.nnz; ++e) { az += r.val[e] * zk[r.idx[e]]; nrm = fmax(nrm, fabs(r.val[e])); }
-                if (ll != 0.0) { const double t = R.tl[c - c0]; smu += t * ll; rpmax = fmax(rpmax, fabs(az - t - R.lb[c - c0]) / nrm); }
-                if (lu != 0.0) { const double t = R.tu[c - c0]; smu += t * lu; rpmax = fmax(rpmax, fabs(-az - t + R.ub[c - c0]) / nrm); }
+                if (ll != 0.0) { const double t = K6W(oTL + c); smu += t * ll; rpmax = fmax(rpmax, fabs(az - t - K6W(oLB + c)) / nrm); }
+                if (lu != 0.0) { const double t = K6W(oTU + c); smu += t * lu; rpmax = fmax(rpmax, fabs(-az - t + K6W(oUB + c)) / nrm); }
             }
         }
         mu = smu / nside;
@@ -261,16 +247,15 @@ __device__ int solve(const Args& A, double* __restrict__ xout, double& cost_out,
                 f[1] += K6W(oQZ + k);
                 // ---- rows of the stage: barrier terms ----
                 const int c0 = (k < NH) ? k * rps : NH * rps, c1 = (k < NH) ? c0 + rps : c0 + nterm;
-                K6_LOAD_STAGE(R, c0, c1);
                 for (int c = c0; c < c1; ++c) {
-                    const double ll = R.ll[c - c0], lu = R.lu[c - c0];
+                    const double ll = K6W(oLL + c), lu = K6W(oLU + c);
                     if (ll == 0.0 && lu == 0.0) continue;
                     SparseRow r; load_row<NU, NB>(A.rowtab[c], A.rowc, sb, k, r);
                     double az = 0.0, adz = 0.0;
                     for (int e = 0; e < r.nnz; ++e) { az += r.val[e] * zk[r.idx[e]]; adz += r.val[e] * dk[r.idx[e]]; }
                     double w = 0.0, cf = 0.0;
                     if (ll != 0.0) {
-                        const double t = R.tl[c - c0], rp = az - t - R.lb[c - c0];
+                        const double t = K6W(oTL + c), rp = az - t - K6W(oLB + c);
                         double corr = 0.0;
                         if (pass == 1) {
                             const double dtA = adz + rp, dlA = (-t * ll - ll * dtA) / t;
@@ -280,7 +265,7 @@ __device__ int solve(const Args& A, double* __restrict__ xout, double& cost_out,
                         cf -= (sigma * mu - corr - ll * rp) / t;
                     }
                     if (lu != 0.0) {
-                        const double t = R.tu[c - c0], rp = -az - t + R.ub[c - c0];
+                        const double t = K6W(oTU + c), rp = -az - t + K6W(oUB + c);
                         double corr = 0.0;
                         if (pass == 1) {
                             const double dtA = -adz + rp, dlA = (-t * lu - lu * dtA) / t;
@@ -471,9 +456,8 @@ __device__ int solve(const Args& A, double* __restrict__ xout, double& cost_out,
                         for (int c = 0; c < NU; ++c) dA[NX + c] = (k < NH) ? K6W(oDUA + k * NU + c) : 0.0;
                     }
                     const int c0 = (k < NH) ? k * rps : NH * rps, c1 = (k < NH) ? c0 + rps : c0 + nterm;
-                    K6_LOAD_STAGE(R, c0, c1);
                     for (int c = c0; c < c1; ++c) {
-                        const double ll = R.ll[c - c0], lu = R.lu[c - c0];
+                        const double ll = K6W(oLL + c), lu = K6W(oLU + c);
                         if (ll == 0.0 && lu == 0.0) continue;
                         SparseRow r; load_row<NU, NB>(A.rowtab[c], A.rowc, sb, k, r);
                         double az = 0.0, adz = 0.0, adAz = 0.0;
@@ -482,9 +466,9 @@ __device__ int solve(const Args& A, double* __restrict__ xout, double& cost_out,
                         for (int side = 0; side < 2; ++side) {
                             const double lam = side ? lu : ll;
                             if (lam == 0.0) continue;
-                            const double t = (side ? R.tu[c - c0] : R.tl[c - c0]);
+                            const double t = K6W((side ? oTU : oTL) + c);
                             const double sg = side ? -1.0 : 1.0;
-                            const double rp = sg * az - t - (side ? -R.ub[c - c0] : R.lb[c - c0]);
+                            const double rp = sg * az - t - (side ? -K6W(oUB + c) : K6W(oLB + c));
                             double rc = sigma * mu - t * lam;
                             if (pass == 1) {
                                 const double dtA = sg * adAz + rp, dlA = (-t * lam - lam * dtA) / t;
@@ -540,9 +524,8 @@ __device__ int solve(const Args& A, double* __restrict__ xout, double& cost_out,
                     dA[NX + c] = (k < NH) ? K6W(oDUA + k * NU + c) : 0.0;
                 }
                 const int c0 = (k < NH) ? k * rps : NH * rps, c1 = (k < NH) ? c0 + rps : c0 + nterm;
-                K6_LOAD_STAGE(R, c0, c1);
                 for (int c = c0; c < c1; ++c) {
-                    const double ll = R.ll[c - c0], lu = R.lu[c - c0];
+                    const double ll = K6W(oLL + c), lu = K6W(oLU + c);
                     if (ll == 0.0 && lu == 0.0) continue;
                     SparseRow r; load_row<NU, NB>(A.rowtab[c], A.rowc, sb, k, r);
                     double az = 0.0, adz = 0.0, adAz = 0.0;
@@ -551,9 +534,9 @@ __device__ int solve(const Args& A, double* __restrict__ xout, double& cost_out,
                         const double lam = side ? lu : ll;
                         if (lam == 0.0) continue;
                         const int ot = side ? oTU : oTL, ol = side ? oLU : oLL;
-                        const double t = side ? R.tu[c - c0] : R.tl[c - c0];
+                        const double t = K6W(ot + c);
                         const double sg = side ? -1.0 : 1.0;
-                        const double rp = sg * az - t - (side ? -R.ub[c - c0] : R.lb[c - c0]);
+                        const double rp = sg * az - t - (side ? -K6W(oUB + c) : K6W(oLB + c));
                         const double dtA = sg * adAz + rp, dlA = (-t * lam - lam * dtA) / t;
                         const double rc = sigma * mu - t * lam - apA * adA * dtA * dlA;
                         const double dt = sg * adz + rp, dl = (rc - lam * dt) / t;

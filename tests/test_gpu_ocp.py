@@ -61,7 +61,8 @@ def test_headline_batch_structured_vs_dense_path_and_oracle(oracle):
     ds = np.abs(log[:, :, :2] - dlog[:, :, :2]).max(axis=(0, 2))
     same = ds < 1e-6
     dsum = np.abs((log[:, same, 2] + log[:, same, 3]) - (dlog[:, same, 2] + dlog[:, same, 3])).max()
-    dobj = (np.abs(log[:, same, 11] - dlog[:, same, 11]) / (1 + np.abs(dlog[:, same, 11]))).max()
+    solved = (log[:, same, 9] == 0) & (dlog[:, same, 9] == 0)                      # the objective of a failed QP means nothing
+    dobj = (np.abs(log[:, same, 11] - dlog[:, same, 11]) / (1 + np.abs(dlog[:, same, 11])))[solved].max()
     print("structured vs dense path: %d of %d scenarios within 1e-6 m over the cycle (the others: up to %.1e m); on those Fm+Fb %.2e N, "
           "rel obj %.2e; mean ipm iterations %.1f" % (same.sum(), B, ds.max(), dsum, dobj, log[:, :, 10].mean()))
     assert same.mean() >= 0.5
