@@ -5,7 +5,7 @@
 // MC/Settings.m:112, RunOpt_FBMPC.m:96-121, RunOpt_ABMPC.m:87-117).  K2 -> K6 -> K4: same operands in, same
 // (x, cost, status, iter) out as the dense kernels.
 //
-// Launch shape (eep_launch_ocp): few vehicles per warp, a bounded number of vehicles in flight per SM, maximum L1.
+// Launch shape (eep_launch_ocp): 32 vehicles per warp, measured; maximum L1.
 // Nothing is shared between threads: no shared memory, no barrier.
 #include "k6_ocp.cuh"
 #include <cstdlib>
@@ -14,8 +14,7 @@ template <int NU, int NB>
 __global__ void __launch_bounds__(128) k6_ocp_kernel(const __grid_constant__ eepacc_params p, const eep_ocp_io io)
 {
     constexpr int NH = EEP_N, n = NH * NU;
-    // a bounded number of vehicles is in flight (grid-stride loop): each thread keeps ~3 KB of stage blocks in local
-    // memory, and what is in flight per SM has to stay inside the L1 (eep_launch_ocp)
+    // grid-stride loop (the number of vehicles in flight is a launch knob: eep_launch_ocp)
     for (long long veh = (long long)blockIdx.x * blockDim.x + threadIdx.x; veh < io.B; veh += (long long)gridDim.x * blockDim.x) {
         k6::Args A;
         A.sb = io.sblk + veh * EEP_SBLK;
@@ -53,13 +52,14 @@ extern "C" long long eep_ocp_work_items(int ctrl, int n, int m)
 extern "C" int eep_launch_ocp(const eepacc_params* p, const eep_ocp_io* io, cudaStream_t st)
 {
     if (io->B <= 0) return 0;
-    // Measured (profiles/r2w, r2x): with 32 vehicles per warp and every vehicle of the batch in flight a solve took 0.45 s
-    // -- ~300 cycles per local-memory access, i.e. the per-thread stage blocks (3 KB x 64 threads per SM and more) were
-    // served by the L2, one access at a time.  So: (a) few vehicles per warp -- the solve is a chain of dependent
-    // operations, lanes cost nothing, warps hide latency: K6_LANES (8) vehicles per CTA puts 7 warps on an SM at 8192
-    // vehicles instead of 2; (b) at most K6_INFLIGHT (64) vehicles per SM are in flight, the rest wait in the grid-stride
-    // loop, so the local memory in use stays inside the L1; (c) the L1 / shared-memory split is set to maximum L1.
-    int lanes = 8, inflight = 64;
+    // Launch shape, measured on a B200 (profiles/r2y2_k6_sweep.txt, FBMPC, 8192 vehicles, ms per MPC step):
+    //   vehicles per warp   32: 473    16: 490    8: 584    4: 886    2: 1538      (vehicles in flight per SM: no effect)
+    // One warp needs ~0.9e9 cycles for its 32 solves however few warps share the SM, and spreading the vehicles over
+    // more warps only adds warp-instructions: the kernel is bound by the chain of dependent local- / global-memory
+    // accesses of ONE thread (stage blocks in local memory, row state in the [item][B] work space), ~11 M instructions at
+    // ~80 cycles each.  A fast version needs the stage blocks in registers / shared memory and the rows of a vehicle
+    // spread over the lanes of a warp; this one keeps 32 vehicles per warp and the grid-stride loop.
+    int lanes = 32, inflight = 2048;
     if (const char* e = getenv("EEPACC_K6_LANES")) { int v = atoi(e); if (v >= 1 && v <= 128) lanes = v; }
     if (const char* e = getenv("EEPACC_K6_INFLIGHT")) { int v = atoi(e); if (v >= 8 && v <= 2048) inflight = v; }
     long long grid = (io->B + lanes - 1) / lanes;
