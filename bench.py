@@ -51,6 +51,10 @@ def parse():
     ap.add_argument("--parity-scenarios", type=int, default=32, help="scenarios of the timed batch re-checked against the oracle for the `parity` block (0 = skip)")
     ap.add_argument("--groups", type=int, default=0, help="slices the per-step path pipelines the batch as (0 = library default)")
     ap.add_argument("--fused", action="store_true", help="time the fused closed-loop kernel (k5_cycle_kernel) instead of the sliced per-step path")
+    ap.add_argument("--solver", default="qpoases", choices=["qpoases", "ocp"],
+                    help="closed-loop QP solver: qpoases = dense online active set (K3/K3r, the default and the path the headline is quoted on); "
+                         "ocp = stage-structured interior point (K6, the reference's solverToUse = 0 / 2; ab / fb only; ~0.45 s per FBMPC step "
+                         "of 8192 vehicles in this first version: use --cycle-steps 40 or so)")
     args = ap.parse_args()
     if args.batch <= 0:
         args.batch = 8192 if args.ctrl == "fb" else 4096
@@ -178,13 +182,15 @@ def _parity_worker(args):
     return np.stack(logs, 1), np.stack(kpis, 0)
 
 
-def parity_block(ctrl, n_scen, ns, first):
+def parity_block(ctrl, n_scen, ns, first, solver="qpoases"):
     import multiprocessing as mp
     from eepacc_mpc_casadi_matlab_b200 import api
     from oracle import oracle as O
     O.build()
     p, routes, lead = make_workload(ctrl, n_scen, first, ns)
     eng = api.Engine(ctrl, p, routes, B=n_scen)
+    if solver != "qpoases":
+        eng.set_solver(solver)
     if ctrl != "tv":
         eng.set_lead(lead)
     log, kpi = eng.run(ns)
@@ -297,7 +303,9 @@ def main():
         _, k = eng.run(ns, want_log=False)         # host KPI buffer: D2H inside the call
         return k
 
-    eng.set_fused(args.fused)
+    if args.solver != "qpoases":
+        eng.set_solver(args.solver)             # K6 (k6_ocp.cu); the fused kernel and the active-set counters do not apply
+    eng.set_fused(args.fused and args.solver == "qpoases")
     for _ in range(max(args.warmup, 0)):
         run_resident()
     # ---- timed: resident inputs ----
@@ -398,6 +406,8 @@ def main():
         lat = np.concatenate(step_lat)
         tot_k = kt["build_ms"] + kt["qp_ms"] + kt["post_ms"]
         kname = "k3r_qp_kernel (+ k3_qp_kernel for the cold-start step and the hand-overs), per-step path"
+        if args.solver == "ocp":
+            kname = "k6_ocp_kernel (stage-structured interior point, one vehicle per thread), per-step path"
         launch_ms, share, fused_info = qp_ms, (kt["qp_ms"] / tot_k if tot_k else None), None
         units = B * ns
         if cyc_ms:
@@ -425,6 +435,7 @@ def main():
                        "controller": args.ctrl, "batch_per_gpu": B, "cycle_steps": ns, "qp_n": n, "qp_m": m,
                        "path": "fused closed-loop kernel after the cold-start step" if cyc_ms else
                                f"per-step launches, {groups} slices pipelined on their own streams",
+                       "solver": args.solver,
                        "cuda_device_max_connections": os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS"),
                        "slices": groups,
                        "l2": "a 256 MB buffer is written before every timed cycle (L2 flush); inside a cycle "
@@ -460,7 +471,7 @@ def main():
             "solver": {"mean_ws_changes_per_qp": it_mean, "failed_qps": int(ctr[:, 1].sum())},
         }
         if args.parity_scenarios > 0 and world == 1:
-            line["parity"] = parity_block(args.ctrl, min(args.parity_scenarios, B), ns, rank * B)
+            line["parity"] = parity_block(args.ctrl, min(args.parity_scenarios, B), ns, rank * B, args.solver)
         if not args.no_cpu_baseline and world == 1:
             v, cores, sample = cpu_run(args.ctrl, ns, args.cpu_sample or 4)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}

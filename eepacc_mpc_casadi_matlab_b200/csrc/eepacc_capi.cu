@@ -796,6 +796,8 @@ int eepacc_mem_set_fused(int mem, int on)
 {
     Mem* M = get_mem(mem);
     if (!M || !M->ready) return fail(EEPACC_ERR_ARG, "mem not set up");
+    if (on && M->solver != EEPACC_SOLVER_QPOASES)
+        return fail(EEPACC_ERR_ARG, "the fused closed-loop kernel embeds the active-set solver: select EEPACC_SOLVER_QPOASES first");
     M->fused = on ? 1 : 0;
     return EEPACC_OK;
 }

@@ -138,3 +138,31 @@ def test_bounds_estimator_quirks(oracle):
     red = np.array([((3.0 + (i + 1) * p.Ts) % 22.0) < 12.0 for i in range(N)])
     assert np.all(vtl[~red] == 1e5) and np.all(vtl[red & (np.abs(300 - s_est[:N]) < 100)] < 1e5)
     assert amax[0] == 4 and amin[0] == -5 and amax[-1] == 2 and jmax[-1] == 2.5
+
+
+def test_kkt_audit_of_the_oracle_on_bench_scenarios(oracle):
+    """Known limitation, found by the independent interior-point path (csrc/k6_ocp.cuh) and pinned here: on the convex
+    ABMPC QPs of the bench batch the oracle's active-set path (and with it the GPU kernels, which follow it step for
+    step) ends on a vertex with a wrong-sign multiplier in 1 of 13 936 QPs (scenario 11, step 379: the anti-cycling
+    shield of a run of zero-length steps is still up when the homotopy takes its last, full step).  The objective there
+    is 3.6e-4 above the optimum (2.39983e4 vs 2.39897e4).  scripts/cpu_oracle_kkt_audit.py audits any range of
+    scenarios; 0 of 27 872 FBMPC QPs (scenarios 0..31) fail it.  This test holds the count on scenarios 10..11."""
+    import bench
+    bad = []
+    for b in (10, 11):
+        p, routes, lead = bench.make_workload("ab", 1, b, 871)
+        V = oracle.Vehicle(S.AB, p, routes[0])
+        for k in range(871):
+            out = V.step(*lead[k, 0])
+            H, g, A, lba, uba = oracle.qp_arrays(V.qp())
+            x, lam = V.solution()
+            Ax = A @ x
+            tol = 1e-8 * (1 + np.abs(Ax))
+            al = (np.abs(Ax - lba) < tol) & ~(np.abs(Ax - uba) < tol)
+            au = (np.abs(Ax - uba) < tol) & ~(np.abs(Ax - lba) < tol)
+            wrong = max(lam[al].max(initial=0.0), -lam[au].min(initial=0.0))      # H x + g + A' lam = 0: lam <= 0 at a lower bound
+            assert np.abs(H @ x + g + A.T @ lam).max() < 1e-9 * (1 + np.abs(g).max())
+            assert out[9] == 0
+            if wrong > 1e-7 * (1 + np.abs(lam).max()):
+                bad.append((b, k))
+    assert bad in ([], [(11, 379)]), bad
