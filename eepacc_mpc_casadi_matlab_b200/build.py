@@ -6,9 +6,11 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libeepacc.so")
-SOURCES = ["k1_eval.cu", "k2_build.cu", "k3_qp.cu", "k3r_qp.cu", "k4_post.cu", "k5_scenario.cu", "k6_ocp.cu", "eepacc_capi.cu"]
+SOURCES = ["k1_eval.cu", "k2_build.cu", "k3_qp.cu", "k3r_qp.cu", "k4_post.cu", "k5_scenario.cu", "k6_ocp.cu", "k7_nlp.cu", "eepacc_capi.cu"]
 HEADERS = ["eepacc_dev.cuh", "eepacc_kernels.h", "eepacc_rows.cuh", "k2_build.cuh", "k4_post.cuh", "qp_rules.cuh", "k6_ocp.cuh",
            os.path.join("..", "..", "include", "eepacc.h")]
+# headers only some sources include (a change there must not recompile the 12-minute QP kernels)
+EXTRA_HEADERS = {"k7_nlp.cu": ["k7_nlp.cuh", os.path.join("..", "..", "include", "eepacc_nlp.h")]}
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 
@@ -35,7 +37,8 @@ def build_library(force=False, verbose=False, timers=None):
     for s in SOURCES:
         src = os.path.join(CSRC, s)
         obj = os.path.join(objdir, s.replace(".cu", ".o"))
-        if force or _stale(obj, [src] + hdrs):
+        extra = [os.path.join(CSRC, h) for h in EXTRA_HEADERS.get(s, [])]
+        if force or _stale(obj, [src] + hdrs + extra):
             cmd = [nvcc] + NVCC_FLAGS + (["-DEEP_K3_TIMERS"] if timers else []) + ["-c", src, "-o", obj]
             if verbose:
                 print(" ".join(cmd), flush=True)

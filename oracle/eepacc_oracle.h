@@ -115,4 +115,11 @@ int orc_qp_ncon(int ctrl, const eepacc_params* p);
 #ifdef __cplusplus
 }
 #endif
+/* nlp_oracle.c: RunOpt_NLP.m's problem functions (objective, constraint rows, bounds) in the reference's order */
+double orc_lut_linear(double x, const double* xs, const double* ys, int n);
+int    orc_nlp_rows_per_stage(const eepacc_route* r);
+int    orc_nlp_eval(const eepacc_params* p, const eepacc_route* r, const double* s_velInc, const double* v_velInc, int n_vi,
+                    const double* s_stop, const double* v_stop, int n_stop, const double* s_tv, int N, const double* z,
+                    double* f, double* g, double* lbg, double* ubg, double* lbz, double* ubz);
+
 #endif

@@ -28,7 +28,7 @@ class OrcQP(C.Structure):
 def build(force=False):
     if force or not os.path.exists(_LIB) or any(
             os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIB)
-            for f in ("eepacc_oracle.c", "qp_oracle.c", "eepacc_oracle.h")):
+            for f in ("eepacc_oracle.c", "qp_oracle.c", "nlp_oracle.c", "eepacc_oracle.h")):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _LIB
 
@@ -38,7 +38,7 @@ def build_fast():
     fast = os.path.join(_HERE, "_build", "liboracle_fast.so")
     if not os.path.exists(fast) or any(
             os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(fast)
-            for f in ("eepacc_oracle.c", "qp_oracle.c", "eepacc_oracle.h")):
+            for f in ("eepacc_oracle.c", "qp_oracle.c", "nlp_oracle.c", "eepacc_oracle.h")):
         subprocess.check_call(["make", "-C", _HERE, "-s", "fast"])
     return fast
 
@@ -94,6 +94,11 @@ def lib():
         L.orc_fb_ad_init.argtypes = [C.POINTER(Params), C.c_double, C.c_void_p]
         L.orc_kpi.argtypes = [C.POINTER(Params), C.c_double, _dp, C.c_int, _dp]
         L.orc_force_alloc.argtypes = [C.POINTER(Params), C.POINTER(Route)] + [C.c_double] * 3 + [_dp] * 3
+        L.orc_lut_linear.restype = C.c_double
+        L.orc_lut_linear.argtypes = [C.c_double, _dp, _dp, C.c_int]
+        L.orc_nlp_rows_per_stage.argtypes = [C.POINTER(Route)]
+        L.orc_nlp_eval.argtypes = [C.POINTER(Params), C.POINTER(Route), _dp, _dp, C.c_int, _dp, _dp, C.c_int, _dp, C.c_int,
+                                   _dp] + [C.c_void_p] * 6
     return _lib
 
 
@@ -194,3 +199,26 @@ class QPSolver:
         if getattr(self, "h", None):
             self.L.orc_qpws_free(self.h)
             self.h = None
+
+
+def nlp_eval(params, route, s_velInc, v_velInc, s_stop, v_stop, s_tv, z):
+    """RunOpt_NLP.m's problem functions at z (reference layout): dict with f, g, lbg, ubg, lbz, ubz (nlp_oracle.c)."""
+    L = lib()
+    z = np.ascontiguousarray(z, dtype=np.float64)
+    N = (len(z) - 4) // 10
+    s_tv = np.ascontiguousarray(s_tv[:N + 1], dtype=np.float64)
+    nr = N * L.orc_nlp_rows_per_stage(C.byref(route))
+    a = [np.ascontiguousarray(x, dtype=np.float64) for x in (s_velInc, v_velInc, s_stop, v_stop)]
+    f = np.zeros(1); g = np.zeros(nr); lbg = np.zeros(nr); ubg = np.zeros(nr); lbz = np.zeros(len(z)); ubz = np.zeros(len(z))
+    n = L.orc_nlp_eval(C.byref(params), C.byref(route), _p(a[0]), _p(a[1]), len(a[0]), _p(a[2]), _p(a[3]), len(a[2]),
+                       _p(s_tv), N, _p(z), f.ctypes.data, g.ctypes.data, lbg.ctypes.data, ubg.ctypes.data,
+                       lbz.ctypes.data, ubz.ctypes.data)
+    assert n == nr, (n, nr)
+    return dict(f=float(f[0]), g=g, lbg=lbg, ubg=ubg, lbz=lbz, ubz=ubz)
+
+
+def nlp_violation(ev, z):
+    """Largest violation of lbg <= g <= ubg and lbz <= z <= ubz."""
+    vg = np.maximum(ev["lbg"] - ev["g"], ev["g"] - ev["ubg"]).max()
+    vz = np.maximum(ev["lbz"] - z, z - ev["ubz"]).max()
+    return float(max(vg, vz, 0.0))

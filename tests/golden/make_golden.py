@@ -35,7 +35,9 @@ TREES = {"mc": "MATLAB_CasADi", "abo": "ACCMPC-ABO_CasADi"}
 MPC_FIELDS = ["s_opt", "v_opt", "Fm_opt", "Fb_opt", "xi_v_opt", "xi_h_opt", "xi_s_opt",
               "xi_f_opt", "a_opt", "P_opt", "E_opt", "rpm_opt", "exitMessage", "H", "G"]
 NLP_FIELDS = ["s_velInc", "v_velInc", "s_opt", "v_opt", "theta_opt", "j_opt", "Fm_opt",
-              "Fb_opt", "P_opt", "E_opt", "a_opt", "rpm_opt"]
+              "Fb_opt", "P_opt", "E_opt", "a_opt", "rpm_opt",
+              "xi_v_opt", "xi_h_opt", "xi_s_opt", "xi_f_opt", "tSolve",
+              "cost_P", "cost_a", "cost_j", "cost_xi_v", "cost_xi_h", "cost_xi_s", "cost_xi_f"]
 
 
 def load_struct(path):

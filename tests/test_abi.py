@@ -89,3 +89,29 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dp_, f)).read()
                 assert "oracle" not in src.replace("qp_oracle.c", "").replace("oracle/", "").lower() or f in ("k3_qp.cu",), f
+
+
+def test_nlp_header_symbols_and_loud_failure_without_device():
+    """include/eepacc_nlp.h: every declared entry point is exported; metadata answers without a GPU; set-up refuses to
+    run without a device (no CPU fallback)."""
+    import torch
+    from eepacc_mpc_casadi_matlab_b200 import nlp
+    L = api.load_library()
+    h = open(os.path.join(ROOT, "include", "eepacc_nlp.h")).read()
+    syms = re.findall(r"^(?:int|long long|double|void|const char\*)\s+\**(eepacc_nlp\w*)\(", h, flags=re.M)
+    assert len(syms) >= 16, syms
+    missing = [s for s in syms if not hasattr(L, s)]
+    assert not missing, missing
+    L.eepacc_nlp_name_in.restype = C.c_char_p
+    L.eepacc_nlp_name_out.restype = C.c_char_p
+    L.eepacc_nlp_nz.restype = C.c_longlong
+    assert [L.eepacc_nlp_name_in(i) for i in range(3)] == [b"x0", b"p", None]                  # nlpsol scheme
+    assert [L.eepacc_nlp_name_out(i) for i in range(4)] == [b"x", b"f", b"stats", None]
+    assert L.eepacc_nlp_nz(870) == 8704                                                         # RunOpt_NLP.m: 4 + 10 N
+    assert L.eepacc_nlp_sizeof_tables() == C.sizeof(nlp.NlpTables)
+    o = nlp.NlpOpts()
+    L.eepacc_nlp_default_opts(C.byref(o))
+    assert (o.tol, o.max_iter) == (1e-8, 500) and o.mu_min == 1e-9
+    if not torch.cuda.is_available():
+        with pytest.raises(api.EepaccError, match="no CPU fallback"):
+            nlp.NlpSolver(S.default_params("mc"), U.default_route(), 10)
