@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--cycle-steps", type=int, default=871, help="MPC steps per driving cycle")
     ap.add_argument("--cpu-sample", type=int, default=0, help="scenarios per core for the CPU baseline (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-nlp", action="store_true", help="skip the K7 (batched NLP benchmark) block of the N = 1 line")
+    ap.add_argument("--nlp-seconds", type=float, default=150.0, help="time limit of the K7 block (its stages that finished are kept)")
     ap.add_argument("--parity-scenarios", type=int, default=32, help="scenarios of the timed batch re-checked against the oracle for the `parity` block (0 = skip)")
     ap.add_argument("--groups", type=int, default=0, help="slices the per-step path pipelines the batch as (0 = library default)")
     ap.add_argument("--fused", action="store_true", help="time the fused closed-loop kernel (k5_cycle_kernel) instead of the sliced per-step path")
@@ -258,6 +260,32 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
+def nlp_block(limit_s):
+    """K7, the batched NLP benchmark, measured by scripts/bench_nlp.py in a child process AFTER the timed
+    region: a stage that does not finish inside the limit is dropped, the headline line is unaffected."""
+    import subprocess
+    cmd = [sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "scripts", "bench_nlp.py")]
+    out = {"what": "k7_nlp_kernel: full-route NLP of RunOpt_NLP.m, one scenario per thread; outside the timed region", "stages": []}
+    try:
+        pr = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        try:
+            so, se = pr.communicate(timeout=limit_s)
+        except subprocess.TimeoutExpired:
+            pr.kill()
+            so, se = pr.communicate()
+            out["cut_off_after_s"] = limit_s
+        for ln in so.splitlines():
+            try:
+                out["stages"].append(json.loads(ln))
+            except ValueError:
+                pass
+        if pr.returncode not in (0, None, -9) and not out["stages"]:
+            out["error"] = (se or "").strip().splitlines()[-1:] or [f"rc {pr.returncode}"]
+    except Exception as e:                                            # the block must never cost the headline line
+        out["error"] = repr(e)
+    return out
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -475,8 +503,11 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             v, cores, sample = cpu_run(args.ctrl, ns, args.cpu_sample or 4)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
-        print(json.dumps(line))
     eng.close()
+    if rank == 0:
+        if world == 1 and not args.no_nlp and args.impl == "b200":
+            line["nlp_benchmark"] = nlp_block(args.nlp_seconds)
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
