@@ -51,9 +51,11 @@ def test_nlp_full_cycle_reproduces_the_saved_ipopt_solution(oracle):
     lead = golden("lead_TO01_EAD.npz")["s_tv"]
     B, N = 32, 870
     s_tv = np.stack([lead[:N + 1]] * B)
-    s_tv[1:] = 6.0 + (s_tv[1:] - 6.0) * (1.0 - 0.03 * (np.arange(1, B) % 2))[:, None]
+    # odd scenarios: lead 0.75 % slower (converges on the host in 126 iterations; a 3 % slower lead puts a stage on a lookup
+    # corner and runs into the iteration limit)
+    s_tv[1:] = 6.0 + (s_tv[1:] - 6.0) * (1.0 - 0.0075 * (np.arange(1, B) % 2))[:, None]
     sol = nlp.RunOpt_NLP(p, r, s_tv, n_steps=N)
-    assert sol.status[0] in (0, 4) and sol.iterations[0] < 200
+    assert set(sol.status) <= {0, 4} and sol.iterations.max() < 200
     t = nlp.nlp_tables(r, p)
     sv, vv, ss, vs = tables_of(t)
     ev = oracle.nlp_eval(p, r, sv, vv, ss, vs, lead, sol.z[0])
