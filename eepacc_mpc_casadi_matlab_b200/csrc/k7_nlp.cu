@@ -45,6 +45,13 @@ int nlp_cuda_fail(cudaError_t e, const char* what)
 }
 #define K7_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return nlp_cuda_fail(e_, #call); } while (0)
 
+// restores the caller's current device on every exit path (set-up and eval switch to the mem's device)
+struct DeviceGuard {
+    int prev = -1;
+    DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 NlpMem* nlp_get(int mem) { return (mem >= 0 && mem < K7_MAX_MEM && g_nlp[mem].used) ? &g_nlp[mem] : nullptr; }
 
 void nlp_free_all(NlpMem* M)
@@ -159,7 +166,7 @@ int eepacc_nlp_set_opts(int mem, const eepacc_nlp_opts* o)
 {
     NlpMem* M = nlp_get(mem);
     if (!M || !o) return nlp_fail(EEPACC_ERR_ARG, "bad mem or options");
-    if (!(o->tol > 0) || !(o->mu0 > 0) || !(o->obj_scale > 0) || !(o->mu_min > 0) || !(o->acceptable_kkt > 0) || o->max_iter < 1)
+    if (!(o->tol > 0) || !(o->mu0 > 0) || !(o->obj_scale > 0) || !(o->mu_min > 0) || !(o->acceptable_kkt > 0) || o->max_iter < 1 || o->max_iter > 100000)
         return nlp_fail(EEPACC_ERR_ARG, "options out of range");
     M->opts = *o;
     return EEPACC_OK;
@@ -180,8 +187,7 @@ int eepacc_nlp_setup(int mem, const eepacc_params* p, const eepacc_route* routes
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1 || device < 0 || device >= ndev)
         return nlp_fail(EEPACC_ERR_NO_DEVICE, "no usable CUDA device: the NLP benchmark has no CPU fallback");
     nlp_free_all(M);
-    int prev = -1;
-    cudaGetDevice(&prev);
+    DeviceGuard guard;
     K7_CUDA(cudaSetDevice(device));
     M->device = device; M->B = B; M->N = n_steps;
     const long long nz = eepacc_nlp_nz(n_steps);
@@ -201,7 +207,6 @@ int eepacc_nlp_setup(int mem, const eepacc_params* p, const eepacc_route* routes
     K7_CUDA(cudaEventCreate(&M->ev[0]));
     K7_CUDA(cudaEventCreate(&M->ev[1]));
     M->ready = true;
-    if (prev >= 0) cudaSetDevice(prev);
     return EEPACC_OK;
 }
 
@@ -215,8 +220,7 @@ int eepacc_nlp(const double** arg, double** res, long long* iw, double* w, int m
     if (!arg[1] || !res[0] || !res[1] || !res[2]) return nlp_fail(EEPACC_ERR_ARG, "p, x, f and stats are required");
     const bool dev = (iw[1] & EEPACC_FLAG_DEVICE_PTR) != 0;
     const long long B = M->B, nz = eepacc_nlp_nz(M->N);
-    int prev = -1;
-    cudaGetDevice(&prev);
+    DeviceGuard guard;
     K7_CUDA(cudaSetDevice(M->device));
     K7Args a;
     a.p = M->p; a.routes = M->routes; a.tabs = M->tabs; a.ws = M->ws;
@@ -242,7 +246,6 @@ int eepacc_nlp(const double** arg, double** res, long long* iw, double* w, int m
         K7_CUDA(cudaMemcpy(res[1], M->d_f, sizeof(double) * B, cudaMemcpyDeviceToHost));
         K7_CUDA(cudaMemcpy(res[2], M->d_stats, sizeof(double) * EEPACC_NLP_N_STATS * B, cudaMemcpyDeviceToHost));
     }
-    if (prev >= 0) cudaSetDevice(prev);
     return EEPACC_OK;
 }
 
