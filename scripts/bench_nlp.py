@@ -34,6 +34,10 @@ def stage(tag, B, N):
            "status_counts": {nlp.STATUS[i]: int(c) for i, c in enumerate(np.bincount(sol.status, minlength=5)) if c},
            "iterations": [int(sol.iterations.min()), int(np.median(sol.iterations)), int(sol.iterations.max())],
            "kkt_error_max_of_converged": float(sol.kkt_error[np.isin(sol.status, (0, 4))].max()) if np.isin(sol.status, (0, 4)).any() else None,
+           # algorithmic work per interval of one iteration, counted from the code: ~30 kflop, ~4.8 KB
+           "roofline_estimate": {"tflops": float(sol.iterations.sum()) * N * 30e3 / (sol.ms * 1e-3) / 1e12,
+                                 "gbs": float(sol.iterations.sum()) * N * 4.8e3 / (sol.ms * 1e-3) / 1e9,
+                                 "note": "flops / bytes per interval-iteration are code counts, not ncu counters"},
            "workspace_bytes": ws, "setup_s": t1 - t0, "wall_s": t2 - t1,
            "h2d_bytes": int(s_tv.nbytes), "d2h_bytes": int(sol.z.nbytes + sol.f.nbytes + sol.stats.nbytes)}
     if N == 870:
