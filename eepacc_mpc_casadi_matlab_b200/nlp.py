@@ -242,3 +242,31 @@ def RunOpt_NLP(params, routes, s_tv, n_steps=None, device=0, **options):
         return S.solve(s_tv[:, :n_steps + 1])
     finally:
         S.close()
+
+
+def summary_rows(sol):
+    """[B][2 + N_STATS] rows a rank contributes to the gathered report: objective, travelled distance, then the stats columns."""
+    return np.concatenate([sol.f[:, None], sol.s_opt[:, -1:], sol.stats], axis=1)
+
+
+def RunOpt_NLP_sharded(params, routes, s_tv, rank, world, device=None, solve=None, **options):
+    """Multi-GPU form: the scenarios are independent, so rank g of G solves the contiguous block
+    sharding.shard_range(B, g, G) on its own GPU with no data-path collective; the only exchange is one all_gather of the
+    per-scenario summary rows (`summary_rows`) over torch.distributed (NCCL on the box, gloo in the CPU test).
+    Returns (this rank's NlpSolution, gathered rows [B][2 + N_STATS] in global scenario order).
+    `solve(params, routes_block, s_tv_block)` replaces the GPU call in the CPU test of the host-side logic."""
+    import torch
+    from . import sharding
+    s_tv = np.atleast_2d(np.asarray(s_tv, dtype=np.float64))
+    B = s_tv.shape[0]
+    if isinstance(routes, Route):
+        routes = [routes] * B
+    lo, hi = sharding.shard_range(B, rank, world)
+    if solve is None:
+        sol = RunOpt_NLP(params, routes[lo:hi], s_tv[lo:hi], device=rank if device is None else device, **options)
+    else:
+        sol = solve(params, routes[lo:hi], s_tv[lo:hi])
+    rows = torch.from_numpy(summary_rows(sol))
+    if torch.cuda.is_available() and solve is None:
+        rows = rows.cuda(rank if device is None else device)
+    return sol, sharding.gather_kpis(rows).cpu().numpy()
