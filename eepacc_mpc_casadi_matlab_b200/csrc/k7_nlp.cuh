@@ -608,7 +608,7 @@ K7_HD void k7_solve(const K7Ctx& c, K7Work& w, const eepacc_nlp_opts& op, K7Resu
     k7_init_duals(c, w, mu);
     res.status = EEPACC_NLP_MAXITER; res.iters = 0; res.backtracks = 0;
     K7Errs e;
-    int fails = 0, stall = 0;
+    int fails = 0, stall = 0, tiny = 0;
     double delta_last = 0.0;
     for (int it = 0; it < op.max_iter; ++it) {
         res.iters = it;
@@ -672,6 +672,10 @@ K7_HD void k7_solve(const K7Ctx& c, K7Work& w, const eepacc_nlp_opts& op, K7Resu
                 continue;
             }
             fails = 0;
+            // thirty accepted steps in a row shorter than 1e-5: the iterate is jammed against a corner of a lookup table
+            //  and would only burn the iteration limit -- and hold up its warp
+            tiny = alpha < 1e-5 ? tiny + 1 : 0;
+            if (tiny >= 30) { k7_accept(c, w, mu, alpha, tau); res.status = EEPACC_NLP_LINESEARCH; goto done; }
             stall = fabs(dphi) <= 1e-12 * (1.0 + fabs(e.fscaled)) ? stall + 1 : 0;
 #ifdef K7_TRACE
             printf("       alpha %.3e dphi %.3e dlin %.3e\n", alpha, dphi, dlin);
